@@ -1,0 +1,189 @@
+"""Generate tests/golden/*.npz by running the reference's own modules on CPU.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (where /root/reference exists):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/gen_golden.py
+
+The reference has no tests and no golden vectors of its own, so these
+fixtures ARE the pin for the oracle and for the CUDA path:
+
+* tiny_<kind>.npz   - small-dimension models of all four kinds with their full state_dict,
+                      inputs, outputs and per-stage taps (fp32 reference forward).
+* segola.npz        - SplitToFolds / OverlapAdd on integer-valued tensors (bit-exact pin).
+* loss.npz          - SiSNRLoss / SiSNRWavLoss values on seeded inputs.
+* prod_<kind>_*.npz - the production yaml configs with `torch.manual_seed(42)` default-init
+                      weights (NOT stored: the product modules re-create them with the same
+                      seed; a weight checksum is stored instead), seeded inputs by recipe,
+                      reference fp32 outputs.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import ref_import  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+PROD = {
+    "dptn_av": dict(num_features=128, video_emb_size=512, hidden_video=128, kernel_size_enc=7, hidden_dim=128,
+                    num_blocks=6, chunk_size=150, step_size=75, num_heads=4, dropout=0.1, bidir=True),
+    "dptn_wav": dict(num_features=64, kernel_size_enc=7, hidden_dim=128, num_blocks=6, chunk_size=150,
+                     step_size=75, num_heads=4, dropout=0.1, bidir=True),
+    "dptn_mask": dict(num_features=64, kernel_size_enc=7, hidden_dim=128, num_blocks=6, chunk_size=150,
+                      step_size=75, num_heads=4, dropout=0.1, bidir=True),
+    "dprnn": dict(num_features=64, kernel_size_enc=2, hidden_dim=128, num_blocks=6, chunk_size=250,
+                  step_size=125, bidir=True),
+}
+TINY = {
+    "dptn_av": dict(num_features=16, video_emb_size=24, hidden_video=16, kernel_size_enc=7, hidden_dim=12,
+                    num_blocks=2, chunk_size=10, step_size=5, num_heads=4, dropout=0.1, bidir=True),
+    "dptn_wav": dict(num_features=8, kernel_size_enc=4, hidden_dim=8, num_blocks=2, chunk_size=12,
+                     step_size=6, num_heads=2, dropout=0.1, bidir=False),
+    "dptn_mask": dict(num_features=8, kernel_size_enc=7, hidden_dim=8, num_blocks=1, chunk_size=10,
+                      step_size=5, num_heads=4, dropout=0.1, bidir=True),
+    "dprnn": dict(num_features=8, kernel_size_enc=2, hidden_dim=8, num_blocks=2, chunk_size=20,
+                  step_size=10, bidir=True),
+}
+
+
+def make_inputs(B, T, Tv=None, E=None, seed=1234):
+    """Synthetic-input recipe of SURVEY.md §8d: s ~ 0.1 N(0,1), mix = s1+s2, emb ~ N(0,1)."""
+    g = torch.Generator().manual_seed(seed)
+    s1 = 0.1 * torch.randn(B, T, generator=g)
+    s2 = 0.1 * torch.randn(B, T, generator=g)
+    mix = s1 + s2
+    if Tv is None:
+        return mix, s1, s2, None, None
+    e1 = torch.randn(B, E, Tv, generator=g)
+    e2 = torch.randn(B, E, Tv, generator=g)
+    return mix, s1, s2, e1, e2
+
+
+def state_checksum(sd):
+    """Order-independent fp64 checksum of a state dict: sum over tensors of sum(x*w), w from name hash."""
+    tot = 0.0
+    for k in sorted(sd.keys()):
+        v = sd[k].detach().double().flatten()
+        w = torch.cos(torch.arange(v.numel(), dtype=torch.float64) * 0.001 + (len(k) % 7))
+        tot += float((v * w).sum())
+    return tot
+
+
+def build(ref, kind, kw, seed=42):
+    cls = {"dptn_av": ref.DPTNAVWavEncDec, "dptn_wav": ref.DPTNWavEncDec,
+           "dptn_mask": ref.DPTNEncDec, "dprnn": ref.DPRNNEncDec}[kind]
+    torch.manual_seed(seed)
+    return cls(**kw).eval()
+
+
+def run(net, kind, mix, e1, e2):
+    with torch.no_grad():
+        if kind == "dptn_av":
+            out = net(mix=mix, s1_embedding=e1, s2_embedding=e2)
+        else:
+            out = net(mix=mix)
+    return out["s1_pred"], out["s2_pred"]
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_import.load()
+    torch.set_num_threads(os.cpu_count())
+
+    # ---- tiny models, all kinds, full state dict + stage taps
+    for kind, kw in TINY.items():
+        net = build(ref, kind, kw, seed=7)
+        # randomise LN affine / biases so that every parameter matters
+        g = torch.Generator().manual_seed(99)
+        with torch.no_grad():
+            for n, p in net.named_parameters():
+                if ("ln" in n or "norm" in n) and n.endswith("weight"):
+                    p.copy_(1.0 + 0.3 * torch.randn(p.shape, generator=g))
+                elif n.endswith("bias"):
+                    p.copy_(0.2 * torch.randn(p.shape, generator=g))
+        B, T = 3, 403
+        E = kw.get("video_emb_size")
+        mix, s1, s2, e1, e2 = make_inputs(B, T, Tv=9 if kind == "dptn_av" else None, E=E, seed=5)
+        taps = {}
+        def tap(name, which="out"):
+            def hook(mod, inp, out):
+                taps[name] = (inp[0] if which == "in" else out).detach().clone()
+                return None
+            return hook
+
+        hooks = [net.encoder.register_forward_hook(tap("encoder_raw")),
+                 net.dprnn.segmenter.register_forward_hook(tap("encoded", "in")),
+                 net.dprnn.segmenter.register_forward_hook(tap("segmented")),
+                 net.dprnn.model.register_forward_hook(tap("blocks_out")),
+                 net.dprnn.overladd.register_forward_hook(tap("ola_raw"))]
+        s1p, s2p = run(net, kind, mix, e1, e2)
+        for h in hooks:
+            h.remove()
+        d = {"cfg_keys": np.array(list(kw.keys())), "cfg_vals": np.array([float(v) for v in kw.values()]),
+             "mix": mix.numpy(), "s1": s1.numpy(), "s2": s2.numpy(), "s1_pred": s1p.numpy(), "s2_pred": s2p.numpy()}
+        if e1 is not None:
+            d["e1"], d["e2"] = e1.numpy(), e2.numpy()
+        for k, v in taps.items():
+            d["tap." + k] = v.numpy()
+        for k, v in net.state_dict().items():
+            d["sd." + k] = v.numpy()
+        # loss on these outputs
+        d["loss"] = ref.SiSNRWavLoss()(s1_pred=s1p, s2_pred=s2p, s1=s1, s2=s2)["loss"].numpy()
+        np.savez_compressed(os.path.join(OUT, f"tiny_{kind}.npz"), **d)
+        print("tiny", kind, "ok", float(d["loss"]))
+
+    # ---- segmentation / overlap-add, integer-valued (bit-exact)
+    d = {}
+    for i, (B, N, L, C, P) in enumerate([(2, 3, 53, 10, 5), (1, 4, 150, 150, 75), (2, 2, 533, 150, 75), (1, 2, 64, 8, 4),
+                                         (2, 5, 31, 6, 3)]):
+        g = torch.Generator().manual_seed(i)
+        x = torch.randint(-1000, 1000, (B, N, L), generator=g).float()
+        seg = ref.SplitToFolds(C, P)(x)
+        y = torch.randint(-1000, 1000, tuple(seg.shape), generator=g).float()
+        ola = ref.OverlapAdd(C, P)(y)
+        d[f"c{i}.meta"] = np.array([B, N, L, C, P])
+        d[f"c{i}.x"], d[f"c{i}.seg"], d[f"c{i}.y"], d[f"c{i}.ola"] = x.numpy(), seg.numpy(), y.numpy(), ola.numpy()
+    np.savez_compressed(os.path.join(OUT, "segola.npz"), **d)
+    print("segola ok")
+
+    # ---- loss values
+    d = {}
+    g = torch.Generator().manual_seed(11)
+    for i, (B, T) in enumerate([(1, 100), (4, 1601), (5, 4001)]):
+        s1 = torch.randn(B, T, generator=g)
+        s2 = torch.randn(B, T, generator=g) * 0.5 + 0.1
+        s1p = s1 + 0.3 * torch.randn(B, T, generator=g)
+        s2p = 0.7 * s2 + 0.2 * torch.randn(B, T, generator=g) + 0.05
+        if i == 1:  # swapped speakers: PIT must pick permutation 2
+            s1p, s2p = s2p, s1p
+        d[f"c{i}.s1"], d[f"c{i}.s2"], d[f"c{i}.s1p"], d[f"c{i}.s2p"] = s1.numpy(), s2.numpy(), s1p.numpy(), s2p.numpy()
+        d[f"c{i}.pair"] = np.array([float(ref.SiSNRLoss()(a, b)) for a, b in
+                                    [(s1p, s1), (s2p, s2), (s1p, s2), (s2p, s1)]])
+        d[f"c{i}.loss"] = ref.SiSNRWavLoss()(s1_pred=s1p, s2_pred=s2p, s1=s1, s2=s2)["loss"].numpy()
+    np.savez_compressed(os.path.join(OUT, "loss.npz"), **d)
+    print("loss ok")
+
+    # ---- production configs, seed-42 default-init weights
+    cases = [("dptn_av", 2, 16000), ("dptn_av", 1, 64000), ("dptn_wav", 2, 16000), ("dptn_mask", 2, 16000),
+             ("dprnn", 2, 16000)]
+    for kind, B, T in cases:
+        kw = PROD[kind]
+        net = build(ref, kind, kw, seed=42)
+        Tv = 25 * T // 16000 if kind == "dptn_av" else None
+        mix, s1, s2, e1, e2 = make_inputs(B, T, Tv=Tv, E=kw.get("video_emb_size"), seed=1234)
+        s1p, s2p = run(net, kind, mix, e1, e2)
+        loss = ref.SiSNRWavLoss()(s1_pred=s1p, s2_pred=s2p, s1=s1, s2=s2)["loss"]
+        d = {"B": B, "T": T, "Tv": -1 if Tv is None else Tv, "weight_seed": 42, "input_seed": 1234,
+             "weight_checksum": state_checksum(net.state_dict()),
+             "mix_checksum": float(mix.double().sum()), "s1_pred": s1p.numpy(), "s2_pred": s2p.numpy(),
+             "loss": loss.numpy()}
+        np.savez_compressed(os.path.join(OUT, f"prod_{kind}_B{B}_T{T}.npz"), **d)
+        print("prod", kind, B, T, "ok loss", float(loss))
+
+
+if __name__ == "__main__":
+    main()

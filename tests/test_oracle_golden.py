@@ -1,0 +1,113 @@
+"""Pin the numpy oracle against fixtures produced by the reference's own modules.
+
+The fixtures come from oracle/gen_golden.py (reference imported unmodified, CPU fp32).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import vatss_oracle as O
+
+KINDS = ["dptn_av", "dptn_wav", "dptn_mask", "dprnn"]
+
+
+def load_tiny(golden_dir, kind):
+    z = np.load(os.path.join(golden_dir, f"tiny_{kind}.npz"))
+    kw = {k: v for k, v in zip(z["cfg_keys"], z["cfg_vals"])}
+    cfg = O.PathConfig(
+        kind=kind,
+        num_features=int(kw["num_features"]),
+        kernel_size_enc=int(kw["kernel_size_enc"]),
+        hidden_dim=int(kw["hidden_dim"]),
+        num_blocks=int(kw["num_blocks"]),
+        chunk_size=int(kw["chunk_size"]),
+        step_size=int(kw["step_size"]),
+        num_heads=int(kw.get("num_heads", 4)),
+        bidir=bool(kw["bidir"]),
+        video_emb_size=int(kw.get("video_emb_size", 0)),
+    )
+    sd = {k[3:]: z[k] for k in z.files if k.startswith("sd.")}
+    return z, cfg, sd
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_oracle_matches_reference_forward(golden_dir, kind):
+    z, cfg, sd = load_tiny(golden_dir, kind)
+    P = O.to_numpy_state(sd, np.float64)
+    taps = {}
+    e1 = z["e1"] if "e1" in z.files else None
+    e2 = z["e2"] if "e2" in z.files else None
+    s1p, s2p = O.forward(P, cfg, z["mix"], e1, e2, taps=taps)
+    # the reference ran in fp32, the oracle in fp64: agreement at fp32 round-off level
+    assert rel_l2(s1p, z["s1_pred"]) < 2e-5
+    assert rel_l2(s2p, z["s2_pred"]) < 2e-5
+    # stage taps: encoded is (B,N,L) in the reference, token-major here
+    assert rel_l2(taps["encoded"].transpose(0, 2, 1), z["tap.encoded"]) < 1e-5
+    last = taps[f"block{cfg.num_blocks - 1}"]  # (B,S,C,N) -> reference (B,N,S,C)
+    assert rel_l2(last.transpose(0, 3, 1, 2), z["tap.blocks_out"]) < 2e-5
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_oracle_fp32_mode_close(golden_dir, kind):
+    z, cfg, sd = load_tiny(golden_dir, kind)
+    P = O.to_numpy_state(sd, np.float32)
+    e1 = z["e1"] if "e1" in z.files else None
+    e2 = z["e2"] if "e2" in z.files else None
+    s1p, s2p = O.forward(P, cfg, z["mix"], e1, e2)
+    assert s1p.dtype == np.float32
+    assert rel_l2(s1p, z["s1_pred"]) < 5e-5
+    assert rel_l2(s2p, z["s2_pred"]) < 5e-5
+
+
+def test_segmentation_and_overlap_add_bit_exact(golden_dir):
+    z = np.load(os.path.join(golden_dir, "segola.npz"))
+    n = len([k for k in z.files if k.endswith(".meta")])
+    assert n >= 5
+    for i in range(n):
+        B, N, L, C, P = (int(v) for v in z[f"c{i}.meta"])
+        seg = O.segment_channel_major(z[f"c{i}.x"], C, P)
+        assert seg.shape == z[f"c{i}.seg"].shape
+        assert np.array_equal(seg, z[f"c{i}.seg"])
+        ola = O.overlap_add_channel_major(z[f"c{i}.y"], P)
+        assert np.array_equal(ola, z[f"c{i}.ola"])
+        # token-major view agrees with the channel-major one
+        tm = O.segment_token_major(z[f"c{i}.x"].transpose(0, 2, 1), C, P)
+        assert np.array_equal(tm.transpose(0, 3, 1, 2), z[f"c{i}.seg"])
+
+
+def test_loss_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "loss.npz"))
+    for i in range(3):
+        s1, s2, s1p, s2p = (z[f"c{i}.{k}"].astype(np.float64) for k in ("s1", "s2", "s1p", "s2p"))
+        pair = [O.sisnr_loss_rows(a, b).mean() for a, b in [(s1p, s1), (s2p, s2), (s1p, s2), (s2p, s1)]]
+        np.testing.assert_allclose(pair, z[f"c{i}.pair"], rtol=2e-5)
+        np.testing.assert_allclose(O.pit_sisnr_loss(s1p, s2p, s1, s2), z[f"c{i}.loss"], rtol=2e-5)
+        # the restated torchmetrics SI-SNR is -loss/2 up to the eps terms (SURVEY.md §8c cross-check)
+        m = np.mean(O.si_snr_metric_rows(s1p, s1))
+        np.testing.assert_allclose(m, -0.5 * z[f"c{i}.pair"][0], rtol=1e-4)
+    # case 1 was built with swapped speakers: batch-level PIT must choose permutation 2
+    pair = z["c1.pair"]
+    assert (pair[2] + pair[3]) / 2 < (pair[0] + pair[1]) / 2
+    np.testing.assert_allclose(z["c1.loss"], (pair[2] + pair[3]) / 2, rtol=1e-6)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_tiny_loss_golden(golden_dir, kind):
+    z, cfg, sd = load_tiny(golden_dir, kind)
+    got = O.pit_sisnr_loss(*(z[k].astype(np.float64) for k in ("s1_pred", "s2_pred", "s1", "s2")))
+    np.testing.assert_allclose(got, z["loss"], rtol=1e-4)
+
+
+def test_prod_goldens_present(golden_dir):
+    files = sorted(glob.glob(os.path.join(golden_dir, "prod_*.npz")))
+    assert len(files) >= 5
+    for f in files:
+        z = np.load(f)
+        assert z["s1_pred"].shape == (int(z["B"]), int(z["T"]))
+        assert np.isfinite(z["s1_pred"]).all() and np.isfinite(z["s2_pred"]).all()

@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: DPTN-AV separation forward (+ PIT SI-SNRi) in separated audio-seconds/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--batch 32] [--seconds 4] [--engine auto|generic|tensor]
+
+One "step" = one forward pass of DPTN-AV (src/configs/model/dptn_wav_av.yaml) over one batch of
+synthetic 16 kHz mixtures + synthetic lip embeddings, followed by the PIT SI-SNRi reduction.
+N=1 workload = BASELINE.json configs[1] (batch 32 x 4 s).  For N>1 (torchrun, one rank per GPU) every
+rank processes its own batch of the same size (utterance sharding, weak scaling) and the ranks
+all-reduce their SI-SNRi sums over NCCL each step - the path's only exchange.
+
+Prints ONE JSON line (see the task contract): `value` = whole-job audio-s/s with inputs resident in
+HBM; `e2e` = the same through the public nn.Module API from pinned host buffers (H2D + D2H inside
+the timed region); `roofline` for the dominant stage; `cpu_baseline` = the torch-op CPU port of the
+reference (oracle/torch_port.py) on the host cores for a bounded sample.
+`--impl reference` times that CPU port as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 16000
+MODEL_KW = dict(num_features=128, video_emb_size=512, hidden_video=128, kernel_size_enc=7, hidden_dim=128,
+                num_blocks=6, chunk_size=150, step_size=75, num_heads=4, dropout=0.1, bidir=True)
+METRIC = "dptn_av_separated_audio_seconds_per_second"
+UNIT = "audio-s/s"
+
+
+def geometry(T):
+    L = (T - 7) // 3 + 1
+    S = (L - 150) // 75 + 1
+    return L, S
+
+
+def stage_flops(B, T):
+    """Algorithmic FLOPs (2MNK) per forward by stage (SURVEY.md §8a per-token figures)."""
+    L, S = geometry(T)
+    tok = B * S * 150
+    N, H = 128, 128
+    per_sub = {
+        "qkv": 2 * N * 3 * N,
+        "outproj_ln1": 2 * N * N,
+        "lstm_input": 2 * N * 8 * H,
+        "lstm_recurrent": 2 * H * 8 * H,
+        "ffn_ln2": 2 * 2 * H * N,
+    }
+    fl = {k: 12 * tok * v for k, v in per_sub.items()}
+    fl["attention"] = 6 * tok * 4 * N * (150 + S)  # QK^T and PV, intra (len C) + inter (len S)
+    fl["tail"] = tok * 2 * N * 2 * N + 2 * B * L * (2 * N * N + 2 * N * 7)
+    fl["frontend"] = B * L * 2 * N * 7 + 2 * B * (T // 640) * 512 * N
+    return fl
+
+
+def make_batch(B, T, seed):
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    s1 = 0.1 * torch.randn(B, T, generator=g)
+    s2 = 0.1 * torch.randn(B, T, generator=g)
+    Tv = 25 * T // SR
+    e1 = torch.randn(B, 512, Tv, generator=g)
+    e2 = torch.randn(B, 512, Tv, generator=g)
+    return s1 + s2, s1, s2, e1, e2
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            sm_sorted = sorted(sm)
+            out.update(sm_mhz=sm_sorted[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power))
+        return out
+
+
+def cpu_reference_arm(steps, warmup, B_sample, T):
+    """The reference's CPU path (torch-op port) on the host cores; returns (audio-s/s, ms/step, info)."""
+    import torch
+
+    import speech_separation_b200 as V
+    from oracle import torch_port
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(42)
+    net = V.DPTNAVWavEncDec(**MODEL_KW).eval()
+    mix, s1, s2, e1, e2 = make_batch(B_sample, T, 1234)
+    for _ in range(warmup):
+        torch_port.forward(net, mix, e1, e2)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        torch_port.forward(net, mix, e1, e2)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    val = B_sample * T / SR / dt
+    info = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{B_sample} utterance(s) x {T / SR:g} s of the same workload per step, fp32 torch ops "
+                      f"(oracle/torch_port.py), {steps} step(s) after {warmup} warm-up"}
+    return val, dt * 1e3, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--seconds", type=float, default=4.0)
+    ap.add_argument("--engine", default="auto", choices=["auto", "generic", "tensor"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    B, T = args.batch, int(round(args.seconds * SR))
+    config = {"workload": f"DPTN-AV (dptn_wav_av.yaml) inference, batch {B} x {args.seconds:g} s 16 kHz per GPU, "
+                          f"synthetic lip embeddings (B,512,{25 * T // SR}), random-init weights seed 42, "
+                          "+ PIT SI-SNRi reduction",
+              "batch_per_gpu": B, "seconds": args.seconds, "sharding": f"utterance x{max(world, args.gpus)}",
+              "l2": "256 MiB buffer written between timed steps (L2 flush); per-step activations >> 126 MB L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        # bounded sample: 1 utterance per step keeps K steps within minutes on the host cores
+        val, ms, info = cpu_reference_arm(max(args.steps, 1), min(args.warmup, 1), 1, T)
+        print(json.dumps({"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                          "impl": "reference", "cpu_baseline": info, "gpu_launches": 0,
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    import speech_separation_b200 as V
+    from speech_separation_b200 import _lib
+    from speech_separation_b200.sharding import reduce_sisnr, sisnr_sums
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    torch.manual_seed(42)
+    net = V.DPTNAVWavEncDec(**MODEL_KW).eval().to(dev).set_engine(args.engine)
+    metric = V.SISNRiMetric()
+    mix_h, s1_h, s2_h, e1_h, e2_h = (t.pin_memory() for t in make_batch(B, T, 1234 + rank))
+    mix, s1, s2, e1, e2 = (t.to(dev) for t in (mix_h, s1_h, s2_h, e1_h, e2_h))
+    out_h = [torch.empty(B, T).pin_memory() for _ in range(2)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_resident():
+        out = net(mix=mix, s1_embedding=e1, s2_embedding=e2)
+        rows, rows_loss, _ = V.pit_sisnr_all(out["s1_pred"], out["s2_pred"], s1, s2, mix)
+        return reduce_sisnr(sisnr_sums(rows, rows_loss)) if world > 1 else rows
+
+    def step_e2e():
+        m = mix_h.to(dev, non_blocking=True)
+        a = e1_h.to(dev, non_blocking=True)
+        b = e2_h.to(dev, non_blocking=True)
+        out = net(mix=m, s1_embedding=a, s2_embedding=b)
+        out_h[0].copy_(out["s1_pred"], non_blocking=True)
+        out_h[1].copy_(out["s2_pred"], non_blocking=True)
+        val = metric(s1_pred=out["s1_pred"], s2_pred=out["s2_pred"], s1=s1, s2=s2, mix=m)
+        return float(val)  # device -> host read of the step's metric (synchronises)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """Per-step CUDA events on the current stream, L2 flush between steps (outside the events)."""
+        evs = []
+        barrier()
+        wall0 = time.perf_counter()
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        wall = time.perf_counter() - wall0
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), wall
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.vatss_launch_count()
+    total_ms, wall = timed(step_resident, args.steps)
+    launches = lib.vatss_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else {}
+
+    for _ in range(2):
+        step_e2e()
+    e2e_ms, _ = timed(step_e2e, args.steps)
+
+    # per-stage device time (CUDA events recorded by the library on the launching stream)
+    with _lib.stage_profile() as prof:
+        for _ in range(2):
+            step_resident()
+        torch.cuda.synchronize()
+    stage_ms = {k: v / 2 for k, v in prof.ms.items()}
+    stage_launches = {k: v // 2 for k, v in prof.launches.items()}
+
+    # parity signal carried with the number: SI-SNRi of this rank's batch
+    with torch.no_grad():
+        out = net(mix=mix, s1_embedding=e1, s2_embedding=e2)
+        snri = float(metric(s1_pred=out["s1_pred"], s2_pred=out["s2_pred"], s1=s1, s2=s2, mix=mix))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    n = max(world, 1)
+    audio_s_per_step = n * B * T / SR
+    ms_per_step = total_ms / args.steps
+    value = audio_s_per_step / (ms_per_step / 1e3)
+    e2e_value = audio_s_per_step / (e2e_ms / args.steps / 1e3)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"
+    fl = stage_flops(B, T)
+    compute = {k: v for k, v in stage_ms.items() if k in fl and k not in ("frontend", "tail")}
+    dom = max(compute, key=compute.get)
+    dom_launches = max(stage_launches.get(dom, 1), 1)
+    achieved = fl[dom] / (stage_ms[dom] / 1e3) / 1e12
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "launches_per_step": dom_launches, "ms_per_step": stage_ms[dom],
+                "whole_forward_frac": sum(fl.values()) / (sum(stage_ms[k] for k in fl) / 1e3) / 1e12 / peak_tf,
+                "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()}}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.engine == "generic" or not _engine_is_tensor(lib, net) else "f16",
+            "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(mix_h.numel() + e1_h.numel() + e2_h.numel()) * 4,
+                    "d2h_bytes_per_step": int(2 * B * T) * 4 + 4},
+            "gpu_launches": int(launches), "roofline": roofline, "si_snri_db": snri, "wall_s_timed": wall}
+    if world == 1 and not args.no_cpu_baseline:
+        _, _, info = cpu_reference_arm(2, 1, 1, T)
+        line["cpu_baseline"] = info
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def _engine_is_tensor(lib, net):
+    import ctypes
+
+    return lib.vatss_packed_weight_bytes(ctypes.byref(net._desc)) > 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

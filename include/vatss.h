@@ -1,0 +1,180 @@
+/*
+ * vatss.h - C ABI of the B200-native VAT-SS separation hot path (libvatss_b200.so).
+ *
+ * The reference (teasgen/speech_separation) is pure Python/PyTorch and has no FFI or
+ * plugin interface of its own: its seam is Hydra `_target_` instantiation
+ * of Python nn.Modules.  Every entry point below therefore cites the reference Python
+ * interface it replaces (paths relative to the reference repo root), and
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - All pointers except `params` tables are DEVICE pointers owned by the caller (PyTorch's
+ *    caching allocator); the library never allocates or frees device memory.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *    synchronises the device.
+ *  - Return value: 0 = OK, <0 = error; `vatss_last_error()` gives the message (thread-local).
+ *  - Activations inside the library are TOKEN-MAJOR: one row of N features per frame.
+ */
+#ifndef VATSS_H_
+#define VATSS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VATSS_ABI_VERSION 1
+
+/* model kinds: which reference nn.Module the forward reproduces */
+#define VATSS_KIND_DPTN_AV 0   /* src/model/dptn_wav.py:129-194  DPTNAVWavEncDec */
+#define VATSS_KIND_DPTN_WAV 1  /* src/model/dptn_wav.py:64-113   DPTNWavEncDec   */
+#define VATSS_KIND_DPTN_MASK 2 /* src/model/dptn.py:146-195      DPTNEncDec      */
+#define VATSS_KIND_DPRNN 3     /* src/model/dprnn.py:230-276     DPRNNEncDec     */
+
+/* execution engines for the dual-path blocks (shape specialisation, not a backend switch):
+ * GENERIC = fp32 SIMT kernels for any dimensions; TENSOR = tcgen05/TMEM kernels for the
+ * production dimensions (N in {64,128}, H=128).  AUTO picks TENSOR when the shape allows. */
+#define VATSS_ENGINE_AUTO 0
+#define VATSS_ENGINE_GENERIC 1
+#define VATSS_ENGINE_TENSOR 2
+
+typedef struct vatss_model_desc {
+  int32_t kind;        /* VATSS_KIND_*                                   */
+  int32_t N;           /* num_features                                   */
+  int32_t K;           /* kernel_size_enc (stride = K/2)                 */
+  int32_t H;           /* hidden_dim of the LSTMs                        */
+  int32_t num_blocks;  /* dual-path blocks                               */
+  int32_t C;           /* chunk_size                                     */
+  int32_t P;           /* step_size                                      */
+  int32_t heads;       /* attention heads (ignored for DPRNN)            */
+  int32_t bidir;       /* inter-chunk LSTM bidirectional (intra always)  */
+  int32_t E;           /* video_emb_size (DPTN_AV only)                  */
+  int32_t engine;      /* VATSS_ENGINE_*                                 */
+  int32_t reserved;
+} vatss_model_desc;
+
+/* Canonical parameter table: host array of device pointers to fp32 tensors, in this order.
+ * Names are the reference state_dict keys.  Absent entries are NULL. */
+enum {
+  VATSS_P_ENCODER_W = 0,   /* encoder.weight (N,1,K)                                    */
+  VATSS_P_DECODER_W,       /* decoder.weight (N,1,K)                                    */
+  VATSS_P_VIS_W,           /* visual_compression.weight (N/2,E)                         */
+  VATSS_P_VIS_B,           /* visual_compression.bias (N/2)                             */
+  VATSS_P_GATE,            /* gate (1)                                                  */
+  VATSS_P_VLN_W,           /* video_ln.weight (N)                                       */
+  VATSS_P_VLN_B,           /* video_ln.bias (N)                                         */
+  VATSS_P_PRELU,           /* dprnn.speakers_separation.0.weight (1)                    */
+  VATSS_P_SPK_W,           /* dprnn.speakers_separation.1.weight (2N,N,1,1)             */
+  VATSS_P_SPK_B,           /* dprnn.speakers_separation.1.bias (2N)                     */
+  VATSS_P_HEAD_W,          /* dprnn.postprocessing.0.weight | dprnn.output.0.weight (N,N,1) */
+  VATSS_P_HEAD_B,          /* ... bias (N)                                              */
+  VATSS_P_HGATE_W,         /* dprnn.output_gate.0.weight (N,N,1)   (DPTN_MASK only)     */
+  VATSS_P_HGATE_B,         /* dprnn.output_gate.0.bias (N)                              */
+  VATSS_P_GLOBAL_COUNT
+};
+/* per sub-block (blocks x {intra,inter}), prefix dprnn.model.<i>.{intra,inter}_chunk_block. */
+enum {
+  VATSS_S_INPROJ_W = 0, /* mha.in_proj_weight (3N,N)        (NULL for DPRNN)   */
+  VATSS_S_INPROJ_B,     /* mha.in_proj_bias (3N)                               */
+  VATSS_S_OUTPROJ_W,    /* mha.out_proj.weight (N,N)                           */
+  VATSS_S_OUTPROJ_B,    /* mha.out_proj.bias (N)                               */
+  VATSS_S_LN1_W,        /* ln1.weight (N)                                      */
+  VATSS_S_LN1_B,        /* ln1.bias (N)                                        */
+  VATSS_S_WIH,          /* rnn.weight_ih_l0 (4H,N)                             */
+  VATSS_S_WHH,          /* rnn.weight_hh_l0 (4H,H)                             */
+  VATSS_S_BIH,          /* rnn.bias_ih_l0 (4H)                                 */
+  VATSS_S_BHH,          /* rnn.bias_hh_l0 (4H)                                 */
+  VATSS_S_WIH_R,        /* rnn.weight_ih_l0_reverse (NULL if unidirectional)   */
+  VATSS_S_WHH_R,
+  VATSS_S_BIH_R,
+  VATSS_S_BHH_R,
+  VATSS_S_FFN_W,        /* ffn.1.weight | fc.weight (N, H*(1+bidir))           */
+  VATSS_S_FFN_B,        /* ffn.1.bias | fc.bias (N)                            */
+  VATSS_S_LN2_W,        /* ln2.weight | norm1d.weight (N)                      */
+  VATSS_S_LN2_B,        /* ln2.bias | norm1d.bias (N)                          */
+  VATSS_S_COUNT
+};
+/* table length = VATSS_P_GLOBAL_COUNT + num_blocks*2*VATSS_S_COUNT;
+ * entry(block b, path p in {0 intra,1 inter}, slot s) = GLOBAL_COUNT + (2*b+p)*S_COUNT + s */
+
+const char* vatss_last_error(void);
+int vatss_abi_version(void);
+
+/* Geometry helpers (exact integer index maths of the reference).
+ *   L = (T-K)/(K/2)+1      nn.Conv1d output length        src/model/dptn_wav.py:153
+ *   S = (L-C)/P+1          F.unfold, no padding           src/model/dprnn.py:131-135 */
+int vatss_frames(const vatss_model_desc* d, int T);
+int vatss_chunks(const vatss_model_desc* d, int L);
+
+/* Bytes of caller-provided scratch needed by vatss_forward for this shape. */
+size_t vatss_workspace_bytes(const vatss_model_desc* d, int B, int T, int Tv);
+/* Bytes of the packed-weight buffer used by the TENSOR engine (0 if GENERIC only). */
+size_t vatss_packed_weight_bytes(const vatss_model_desc* d);
+/* Re-lay the fp32 parameters into the TENSOR engine's operand formats (fp16, K-major,
+ * fused LSTM bias, ...).  Call once per weight update.  Replaces nothing in the reference;
+ * it is the analogue of nn.LSTM.flatten_parameters() (src/model/dptn.py:44). */
+int vatss_pack_weights(const vatss_model_desc* d, const float* const* params, int n_params,
+                       void* packed, size_t packed_bytes, void* stream);
+
+/* Whole forward pass.  Replaces
+ *   DPTNAVWavEncDec.forward(mix, s1_embedding, s2_embedding)   src/model/dptn_wav.py:171-194
+ *   DPTNWavEncDec.forward(mix)                                 src/model/dptn_wav.py:101-113
+ *   DPTNEncDec.forward(mix)                                    src/model/dptn.py:183-195
+ *   DPRNNEncDec.forward(mix)                                   src/model/dprnn.py:263-276
+ * mix (B,T) f32; emb1/emb2 (B,E,Tv) f32 or NULL; s1_pred/s2_pred (B,T) f32 outputs. */
+int vatss_forward(const vatss_model_desc* d, const float* const* params, int n_params,
+                  const void* packed, const float* mix, const float* emb1, const float* emb2,
+                  int B, int T, int Tv, float* s1_pred, float* s2_pred,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* SplitToFolds.forward  src/model/dprnn.py:122-136 : x (B,N,L) -> out (B,N,S,C), bit-exact copy */
+int vatss_segment(const float* x, int B, int N, int L, int C, int P, float* out, void* stream);
+/* OverlapAdd.forward    src/model/dprnn.py:145-163 : y (B,N,S,C) -> out (B,N,(S-1)P+C), plain sum */
+int vatss_overlap_add(const float* y, int B, int N, int S, int C, int P, float* out, void* stream);
+
+/* Encoder + (optional) AV fusion + token-major segmentation.
+ * nn.Conv1d encoder and the gated fusion, src/model/dptn_wav.py:173-184.
+ * enc_out (B,L,N) token-major; seg_out (B,S,C,N) token-major or NULL.
+ * emb1/emb2 NULL -> audio only.  vis_scratch: B*Tv*N floats (AV only). */
+int vatss_encoder(const vatss_model_desc* d, const float* const* params, const float* mix,
+                  const float* emb1, const float* emb2, int B, int T, int Tv,
+                  float* enc_out, float* seg_out, float* vis_scratch, void* stream);
+/* ConvTranspose1d decoder + centred pad, src/model/dptn_wav.py:187-193.
+ * u (B,L,N) token-major -> wav (B,T); proj_scratch: B*L*K floats. */
+int vatss_decoder(const vatss_model_desc* d, const float* dec_w, const float* u, int B, int T,
+                  float* wav, float* proj_scratch, void* stream);
+
+/* PIT SI-SNR loss and SI-SNR / SI-SNRi metrics in one pass.
+ * Replaces SiSNRLoss/BaseSSLoss.forward (src/loss/ss_losses.py:10-26,100-114) and
+ * SS2BaseMetric.forward / SISNRiMetric.__call__ (src/metrics/base_metric.py:41-60,
+ * src/metrics/si_snri.py:12-30).
+ * Inputs (B,T) f32, mix may be NULL.  rows_out (B,6) f64: per-utterance SI-SNR in dB of the
+ * pairs [s1p.s1, s2p.s2, s1p.s2, s2p.s1, mix.s1, mix.s2] (torchmetrics form, eps = FLT_EPSILON);
+ * rows_loss_out (B,4) f64: per-utterance -20log10 power ratios of the first four pairs
+ * (no eps, reference loss form); summary_out (8) f64:
+ *   [0] loss (batch-level PIT)  [1] loss perm1  [2] loss perm2
+ *   [3] SI-SNR (batch-level PIT max)  [4] SI-SNRi  [5] mean SI-SNR(mix,s1)  [6] mean SI-SNR(mix,s2)
+ *   [7] B
+ * scratch: B*chunks*16 doubles with chunks = vatss_sisnr_chunks(T). */
+int vatss_sisnr_chunks(int T);
+int vatss_pit_sisnr(const float* s1p, const float* s2p, const float* s1, const float* s2,
+                    const float* mix, int B, int T, double* rows_out, double* rows_loss_out,
+                    double* summary_out, double* scratch, void* stream);
+
+/* Instrumentation (no reference counterpart; used by bench.py).
+ * vatss_launch_count: number of kernels this library has launched in this process.
+ * vatss_profile_begin: start recording CUDA-event pairs around the stages of subsequent calls
+ * (on the stream they are launched on); vatss_profile_end synchronises those events and returns
+ * accumulated milliseconds and launch counts per stage (VATSS_STAGE_* order), then disables. */
+#define VATSS_STAGE_COUNT 9
+/* 0 frontend 1 qkv 2 attention 3 outproj+ln1 4 lstm-input 5 lstm-recurrent 6 ffn+ln2 7 tail 8 sisnr */
+unsigned long long vatss_launch_count(void);
+int vatss_profile_begin(void);
+int vatss_profile_end(float* ms_per_stage, int* launches_per_stage, int n_stages);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VATSS_H_ */

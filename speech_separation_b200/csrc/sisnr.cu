@@ -1,0 +1,145 @@
+// PIT SI-SNR loss and SI-SNR / SI-SNRi metrics in one pass over the five waveforms.
+//
+// Reference: SiSNRLoss.forward src/loss/ss_losses.py:100-114 (zero-mean, no eps, -20 log10 of the
+// power ratio, batch mean), BaseSSLoss.forward :10-26 (batch-level 2-permutation PIT),
+// SS2BaseMetric.forward src/metrics/base_metric.py:41-60 and SISNRiMetric.__call__
+// src/metrics/si_snri.py:12-30 (torchmetrics SI-SNR: zero-mean, eps = FLT_EPSILON, 10 log10).
+//
+// Stage 1 (HBM-bound): every CTA reads one chunk of one utterance of all five signals once and
+// reduces 16 raw moments (5 sums, 5 square sums, 6 cross products) with warp shuffles, in fp64.
+// Stage 2 (one CTA): combines the chunks, centres the moments algebraically
+//   <p_c,g_c> = Spg - Sp Sg / T,  ||g_c||^2 = Sgg - Sg^2/T, ...
+// and evaluates the per-utterance values, the batch means and both PIT decisions on the device,
+// so the host needs a single small read instead of the reference's 4-6 `.item()` syncs.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace vatss {
+
+constexpr int SISNR_CHUNK = 8192;
+constexpr int SISNR_NM = 16;
+
+int sisnr_chunks(int T) { return T <= 0 ? 1 : (T + SISNR_CHUNK - 1) / SISNR_CHUNK; }
+
+__global__ void __launch_bounds__(256)
+k_sisnr_moments(const float* __restrict__ s1p, const float* __restrict__ s2p, const float* __restrict__ s1,
+                const float* __restrict__ s2, const float* __restrict__ mix, int T, int chunks,
+                double* __restrict__ scratch) {
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const int t0 = ch * SISNR_CHUNK;
+  const int t1 = min(T, t0 + SISNR_CHUNK);
+  const size_t base = (size_t)b * T;
+  double m[SISNR_NM];
+#pragma unroll
+  for (int i = 0; i < SISNR_NM; ++i) m[i] = 0.0;
+  for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+    const double a = s1p[base + t], c = s2p[base + t], x = s1[base + t], y = s2[base + t];
+    const double z = mix ? (double)mix[base + t] : 0.0;
+    m[0] += a; m[1] += c; m[2] += x; m[3] += y; m[4] += z;
+    m[5] += a * a; m[6] += c * c; m[7] += x * x; m[8] += y * y; m[9] += z * z;
+    m[10] += a * x;  // s1p.s1
+    m[11] += c * y;  // s2p.s2
+    m[12] += a * y;  // s1p.s2
+    m[13] += c * x;  // s2p.s1
+    m[14] += z * x;  // mix.s1
+    m[15] += z * y;  // mix.s2
+  }
+  __shared__ double red[8][SISNR_NM];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < SISNR_NM; ++i) {
+    const double v = warp_sum_d(m[i]);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < SISNR_NM) {
+    double v = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
+    scratch[((size_t)b * chunks + ch) * SISNR_NM + threadIdx.x] = v;
+  }
+}
+
+struct PairMoments {
+  double dot, pp, gg;  // centred <p,g>, ||p||^2, ||g||^2
+};
+
+__device__ __forceinline__ PairMoments centred(const double* m, int ip, int ig, int icross, double invT) {
+  PairMoments r;
+  r.dot = m[icross] - m[ip] * m[ig] * invT;
+  r.pp = m[5 + ip] - m[ip] * m[ip] * invT;
+  r.gg = m[5 + ig] - m[ig] * m[ig] * invT;
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+k_sisnr_finalize(const double* __restrict__ scratch, int B, int T, int chunks, int has_mix,
+                 double* __restrict__ rows, double* __restrict__ rows_loss, double* __restrict__ summary) {
+  const double invT = 1.0 / (double)T;
+  const double eps = (double)FLT_EPSILON;
+  // pairs: (pred index, target index, cross index)
+  const int P_[6] = {0, 1, 0, 1, 4, 4};
+  const int G_[6] = {2, 3, 3, 2, 2, 3};
+  const int X_[6] = {10, 11, 12, 13, 14, 15};
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    double m[SISNR_NM];
+    for (int i = 0; i < SISNR_NM; ++i) m[i] = 0.0;
+    for (int c = 0; c < chunks; ++c)
+      for (int i = 0; i < SISNR_NM; ++i) m[i] += scratch[((size_t)b * chunks + c) * SISNR_NM + i];
+    for (int q = 0; q < 6; ++q) {
+      if (q >= 4 && !has_mix) {
+        rows[b * 6 + q] = 0.0;
+        continue;
+      }
+      const PairMoments pm = centred(m, P_[q], G_[q], X_[q], invT);
+      // torchmetrics form
+      const double alpha = (pm.dot + eps) / (pm.gg + eps);
+      const double sig = alpha * alpha * pm.gg;
+      double noise = sig - 2.0 * alpha * pm.dot + pm.pp;
+      if (noise < 0.0) noise = 0.0;
+      rows[b * 6 + q] = 10.0 * log10((sig + eps) / (noise + eps));
+      if (q < 4) {
+        // reference loss form, no eps: signal = dot^2/gg, noise = pp - dot^2/gg
+        const double s = pm.dot * pm.dot / pm.gg;
+        const double n = pm.pp - s;
+        rows_loss[b * 4 + q] = -20.0 * log10(s / n);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double mean_m[6] = {0, 0, 0, 0, 0, 0}, mean_l[4] = {0, 0, 0, 0};
+    for (int b = 0; b < B; ++b) {
+      for (int q = 0; q < 6; ++q) mean_m[q] += rows[b * 6 + q];
+      for (int q = 0; q < 4; ++q) mean_l[q] += rows_loss[b * 4 + q];
+    }
+    for (int q = 0; q < 6; ++q) mean_m[q] /= (double)B;
+    for (int q = 0; q < 4; ++q) mean_l[q] /= (double)B;
+    const double l1 = (mean_l[0] + mean_l[1]) * 0.5, l2 = (mean_l[2] + mean_l[3]) * 0.5;
+    const double s1 = (mean_m[0] + mean_m[1]) * 0.5, s2 = (mean_m[2] + mean_m[3]) * 0.5;
+    const double sep = s1 > s2 ? s1 : s2;  // Python max(perm_1, perm_2)
+    summary[0] = (l2 < l1) ? l2 : l1;
+    summary[1] = l1;
+    summary[2] = l2;
+    summary[3] = sep;
+    summary[4] = has_mix ? sep - (mean_m[4] + mean_m[5]) * 0.5 : 0.0;
+    summary[5] = mean_m[4];
+    summary[6] = mean_m[5];
+    summary[7] = (double)B;
+  }
+}
+
+int launch_pit_sisnr(const float* s1p, const float* s2p, const float* s1, const float* s2, const float* mix,
+                     int B, int T, double* rows, double* rows_loss, double* summary, double* scratch,
+                     cudaStream_t st) {
+  VATSS_CHECK_ARG(B > 0 && T > 0, "pit_sisnr: empty batch (B=%d, T=%d)", B, T);
+  const int chunks = sisnr_chunks(T);
+  dim3 grid(chunks, B);
+  k_sisnr_moments<<<grid, 256, 0, st>>>(s1p, s2p, s1, s2, mix, T, chunks, scratch);
+  VATSS_LAUNCH_OK();
+  k_sisnr_finalize<<<1, 256, 0, st>>>(scratch, B, T, chunks, mix != nullptr, rows, rows_loss, summary);
+  VATSS_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace vatss

@@ -1,0 +1,134 @@
+// Separator tail: token-major overlap-add (+ centred pad), the masking head and the
+// ConvTranspose1d decoder.  HBM-bound row-streaming kernels.
+// Reference: src/model/dptn_wav.py:47-59,186-194; src/model/dptn.py:129-141,189;
+//            src/model/dprnn.py:145-163.
+#include "common.cuh"
+
+namespace vatss {
+
+// ola[b,t,:] for t in [0,L): t' = t - padl; sum over chunks s with 0 <= t'-P*s < C of y[b,s,t'-P*s,:]
+// (plain sum, increasing s), zero outside [0,(S-1)P+C).  W = row width (2N).
+__global__ void __launch_bounds__(256)
+k_ola_token_major(const float* __restrict__ y, int S, int C, int P, int L, int W4, int padl, int Lo,
+                  long long total, float4* __restrict__ ola) {
+  const float4* y4 = reinterpret_cast<const float4*>(y);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / W4;
+    const int c = (int)(i - row * W4);
+    const int b = (int)(row / L);
+    const int t = (int)(row - (long long)b * L) - padl;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < Lo) {
+      int s_lo = t - C + 1 + P - 1;
+      s_lo = s_lo <= 0 ? 0 : s_lo / P;
+      int s_hi = t / P;
+      if (s_hi > S - 1) s_hi = S - 1;
+      for (int s = s_lo; s <= s_hi; ++s) {
+        const float4 v = y4[(((long long)b * S + s) * C + (t - P * s)) * W4 + c];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    ola[i] = acc;
+  }
+}
+
+int launch_ola_token_major(const float* y, int B, int S, int C, int P, int L, int W, float* ola,
+                           cudaStream_t st) {
+  VATSS_CHECK_ARG(W % 4 == 0, "overlap-add: row width %d must be a multiple of 4", W);
+  const int Lo = (S - 1) * P + C;
+  const int padl = (L - Lo) / 2;
+  const long long total = (long long)B * L * (W / 4);
+  if (total == 0) return 0;
+  int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  k_ola_token_major<<<blocks, 256, 0, st>>>(y, S, C, P, L, W / 4, padl, Lo, total,
+                                            reinterpret_cast<float4*>(ola));
+  VATSS_LAUNCH_OK();
+  return 0;
+}
+
+// masking head (dptn.py:103-115,141,189): u = ReLU(tanh(t) * sigmoid(g)) * enc
+__global__ void k_mask_combine(const float* __restrict__ t, const float* __restrict__ g,
+                               const float* __restrict__ enc, float* __restrict__ u, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float m = tanhf(t[i]) * sigmoidf_precise(g[i]);
+    u[i] = fmaxf(m, 0.f) * enc[i];
+  }
+}
+
+int launch_mask_combine(const float* t, const float* g, const float* enc, float* u, long long n,
+                        cudaStream_t st) {
+  if (n == 0) return 0;
+  int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  k_mask_combine<<<blocks, 256, 0, st>>>(t, g, enc, u, n);
+  VATSS_LAUNCH_OK();
+  return 0;
+}
+
+// decoder stage 1: proj[b,l,k] = sum_n Wd[n,k] u[b,l,n]      (one warp per frame)
+constexpr int DEC_MAX_K = 16;
+__global__ void __launch_bounds__(256)
+k_decoder_proj(const float* __restrict__ u, const float* __restrict__ Wd, long long rows, int N, int K,
+               float* __restrict__ proj) {
+  extern __shared__ float s_w[];  // [N][K]
+  for (int i = threadIdx.x; i < N * K; i += blockDim.x) s_w[i] = Wd[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float acc[DEC_MAX_K];
+#pragma unroll
+  for (int k = 0; k < DEC_MAX_K; ++k) acc[k] = 0.f;
+  for (int n = lane; n < N; n += 32) {
+    const float x = u[row * N + n];
+#pragma unroll
+    for (int k = 0; k < DEC_MAX_K; ++k)
+      if (k < K) acc[k] = fmaf(s_w[n * K + k], x, acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < DEC_MAX_K; ++k)
+    if (k < K) {
+      const float v = warp_sum(acc[k]);
+      if (lane == 0) proj[row * K + k] = v;
+    }
+}
+
+// decoder stage 2: wav[b,i] = sum_{(l,k): st*l+k = i-padl} proj[b,l,k], zero outside (centred pad)
+__global__ void k_decoder_ola(const float* __restrict__ proj, int L, int K, int st, int T, int padl,
+                              long long total, float* __restrict__ wav) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / T);
+    const int j = (int)(i - (long long)b * T) - padl;
+    float acc = 0.f;
+    if (j >= 0 && j < (L - 1) * st + K) {
+      // frames l with 0 <= j - st*l < K
+      int l_lo = j - K + 1 + st - 1;
+      l_lo = l_lo <= 0 ? 0 : l_lo / st;
+      int l_hi = j / st;
+      if (l_hi > L - 1) l_hi = L - 1;
+      for (int l = l_lo; l <= l_hi; ++l) acc += proj[((long long)b * L + l) * K + (j - st * l)];
+    }
+    wav[i] = acc;
+  }
+}
+
+int launch_decoder(const float* u, const float* Wd, int B, int L, int N, int K, int T, float* proj, float* wav,
+                   cudaStream_t st) {
+  VATSS_CHECK_ARG(K <= DEC_MAX_K, "decoder: kernel_size_enc %d > %d unsupported", K, DEC_MAX_K);
+  const long long rows = (long long)B * L;
+  if (rows == 0) return 0;
+  k_decoder_proj<<<ceil_div(rows, 8), 256, (size_t)N * K * sizeof(float), st>>>(u, Wd, rows, N, K, proj);
+  VATSS_LAUNCH_OK();
+  const int stride = K / 2;
+  const int Lw = (L - 1) * stride + K;
+  const int padl = (T - Lw) / 2;
+  const long long total = (long long)B * T;
+  int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  k_decoder_ola<<<blocks, 256, 0, st>>>(proj, L, K, stride, T, padl, total, wav);
+  VATSS_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace vatss

@@ -1,0 +1,56 @@
+"""Utterance sharding across GPUs and the one exchange step of the path.
+
+Utterances are independent in the forward pass, so rank r of W processes the contiguous range
+[r*n/W, (r+1)*n/W) with replicated weights and no data-path collective.  The only exchange is
+an all-reduce(sum) of a 9-element fp64 vector of SI-SNR sums (NCCL over NVLink on GPUs, gloo
+in the CPU tests).  Host-side logic only; the tensors it reduces are produced by
+`vatss_pit_sisnr`.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world):
+    """Contiguous, balanced split of n utterances; earlier ranks take the remainder."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def sisnr_sums(rows, rows_loss=None):
+    """Local sums to be reduced: six per-pair SI-SNR sums, per-utterance-PIT SI-SNRi sum, count, loss sums x4."""
+    rows = rows.double()
+    sep = torch.maximum((rows[:, 0] + rows[:, 1]) / 2, (rows[:, 2] + rows[:, 3]) / 2)
+    snri = sep - (rows[:, 4] + rows[:, 5]) / 2
+    parts = [rows.sum(0), snri.sum().reshape(1), torch.tensor([rows.shape[0]], dtype=torch.float64, device=rows.device)]
+    if rows_loss is not None:
+        parts.append(rows_loss.double().sum(0))
+    else:
+        parts.append(torch.zeros(4, dtype=torch.float64, device=rows.device))
+    return torch.cat(parts)
+
+
+def reduce_sisnr(sums, group=None):
+    """all-reduce(sum) the vector of `sisnr_sums` and derive the global metrics.
+
+    Returns dict with: si_snri_batch_pit (reference batch-level PIT over the GLOBAL batch),
+    si_snri_utt_pit (mean of per-utterance PIT SI-SNRi), si_snr_batch_pit, loss_batch_pit, count.
+    """
+    sums = sums.clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    s = sums.tolist()
+    n = s[7]
+    m = [v / n for v in s[:6]]
+    sep = max((m[0] + m[1]) / 2, (m[2] + m[3]) / 2)
+    l = [v / n for v in s[8:12]]
+    l1, l2 = (l[0] + l[1]) / 2, (l[2] + l[3]) / 2
+    return {
+        "si_snr_batch_pit": sep,
+        "si_snri_batch_pit": sep - (m[4] + m[5]) / 2,
+        "si_snri_utt_pit": s[6] / n,
+        "loss_batch_pit": l2 if l2 < l1 else l1,
+        "count": int(round(n)),
+    }

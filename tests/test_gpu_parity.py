@@ -310,10 +310,14 @@ def test_loss_edge_cases(V):
     x = torch.randn(2, 100, device=dev())
     # silent target -> NaN, like the reference's eps-free loss
     assert torch.isnan(V.SiSNRWavLoss()(s1_pred=x, s2_pred=x, s1=z, s2=z)["loss"])
-    # scale invariance and permutation symmetry
-    a = V.SiSNRWavLoss()(s1_pred=x, s2_pred=2 * x + 1, s1=x + 0.1 * torch.randn_like(x), s2=x)["loss"]
-    b = V.SiSNRWavLoss()(s1_pred=3 * x, s2_pred=7 * x - 2, s1=x + 0.1 * torch.randn_like(x), s2=x)["loss"]
+    # scale / offset invariance of the predictions
+    t1, t2 = x + 0.1 * torch.randn_like(x), x + 0.2 * torch.randn_like(x)
+    a = V.SiSNRWavLoss()(s1_pred=x, s2_pred=2 * x + 1, s1=t1, s2=t2)["loss"]
+    b = V.SiSNRWavLoss()(s1_pred=3 * x, s2_pred=7 * x - 2, s1=t1, s2=t2)["loss"]
     assert torch.isfinite(a) and torch.isfinite(b)
+    assert abs(float(a) - float(b)) < 1e-4
+    # a perfect (scaled) estimate has zero noise power: -inf, exactly like the eps-free reference loss
+    assert torch.isinf(V.SiSNRLoss()(2 * x + 1, x))
     s1, s2 = torch.randn(4, 500, device=dev()), torch.randn(4, 500, device=dev())
     p1, p2 = s1 + 0.2 * torch.randn_like(s1), s2 + 0.2 * torch.randn_like(s2)
     l12 = V.SiSNRWavLoss()(s1_pred=p1, s2_pred=p2, s1=s1, s2=s2)["loss"]

@@ -163,6 +163,14 @@ int vatss_pit_sisnr(const float* s1p, const float* s2p, const float* s1, const f
                     const float* mix, int B, int T, double* rows_out, double* rows_loss_out,
                     double* summary_out, double* scratch, void* stream);
 
+/* Stand-alone entry points of the TENSOR-engine kernels (unit tests, ncu attribution).
+ * vatss_tc_gemm: out = A[M,K] (fp16, row pitch lda) x W[NOUT,K]^T (fp16) + bias with epilogue
+ *   epi 0: out16 fp16 | 1: out32 (+res) | 2: out32 = LN(.+res), out16 = act16(out32) | 3: out32 = LN(.)+res
+ *   (the per-token projections of src/model/dptn.py:46-51 on tcgen05 tensor cores). */
+int vatss_tc_gemm(int epi, const void* A16, long long lda, const void* W16, const float* bias, const float* res,
+                  long long ldr, const float* ln_w, const float* ln_b, float* out32, long long ldo32, void* out16,
+                  long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int K, void* stream);
+
 /* Instrumentation (no reference counterpart; used by bench.py).
  * vatss_launch_count: number of kernels this library has launched in this process.
  * vatss_profile_begin: start recording CUDA-event pairs around the stages of subsequent calls

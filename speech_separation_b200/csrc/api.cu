@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "tensor_engine.cuh"
+#include "tc_kernels.cuh"
 
 namespace vatss {
 
@@ -371,6 +372,14 @@ int vatss_decoder(const vatss_model_desc* d, const float* dec_w, const float* u,
   VATSS_CHECK_ARG(B > 0 && T >= d->K, "decoder: bad shape");
   const int L = (T - d->K) / stride_of(d) + 1;
   return launch_decoder(u, dec_w, B, L, d->N, d->K, T, proj_scratch, wav, (cudaStream_t)stream);
+}
+
+int vatss_tc_gemm(int epi, const void* A16, long long lda, const void* W16, const float* bias, const float* res,
+                  long long ldr, const float* ln_w, const float* ln_b, float* out32, long long ldo32, void* out16,
+                  long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int K, void* stream) {
+  VATSS_CHECK_ARG(A16 && W16 && M >= 0, "tc_gemm: NULL operand");
+  return launch_tc_gemm(epi, (const __half*)A16, lda, (const __half*)W16, bias, res, ldr, ln_w, ln_b, out32, ldo32,
+                        (__half*)out16, ldo16, act16, prelu_a, M, NOUT, K, (cudaStream_t)stream);
 }
 
 unsigned long long vatss_launch_count(void) { return g_launches.load(); }

@@ -1,0 +1,394 @@
+// TENSOR engine: per-token projections on tcgen05 tensor cores.
+//
+//   out[M, NOUT] = A[M, KDIM] (fp16, TMA, SWIZZLE_128B) x W[NOUT, KDIM]^T (fp16, smem-resident) + epilogue
+//
+// Persistent kernel, one CTA per SM, warp-specialised:
+//   warp 0      TMA producer   (W once, then a 2-stage ring of 128-row A tiles)
+//   warp 1      MMA issuer     (one thread; tcgen05.mma kind::f16, M=128, N<=256, fp32 accum in TMEM)
+//   warps 2..5  epilogue       (tcgen05.ld, thread = output row; bias / residual / LayerNorm / casts)
+// K is only 64..256 here, so a whole K extent of A and all of W fit in shared memory: no K pipeline,
+// W is read from HBM/L2 once per CTA and A exactly once per forward.  These GEMMs are HBM-bound
+// (AI ~ 96 flop/B < ridge ~ 255), hence everything that can be folded into the epilogue is.
+//
+// Used for: QKV in-projection, attention out-projection (+residual+LayerNorm), FFN (+residual+LN),
+// DPRNN fc (+LN, +residual), speaker split, post-conv / mask heads
+// (src/model/dptn.py:46-51, dprnn.py:39-45, dptn_wav.py:47,59).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tc_kernels.cuh"
+
+namespace vatss {
+
+using namespace ptx;
+
+// ------------------------------------------------------------------------------------------
+// host: tensor-map construction through the driver entry point
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  VATSS_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[5], gstr[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VATSS_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d (rank %d)", (int)r, rank);
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+struct TcGemmArgs {
+  long long M;
+  int num_tiles;
+  const float* bias;
+  const float* res;
+  long long ldr;
+  const float* ln_w;
+  const float* ln_b;
+  float* out32;
+  long long ldo32;
+  __half* out16;
+  long long ldo16;
+  int act16;  // activation applied to the fp16 copy only: 0 none, 1 relu, 2 prelu
+  const float* prelu_a;
+};
+
+constexpr int TCG_THREADS = 192;
+
+template <int NOUT, int KDIM>
+struct TcGemmSmem {
+  static constexpr int KB = KDIM / 64;
+  static constexpr int W_BYTES = KB * NOUT * 128;
+  static constexpr int A_STAGE_BYTES = KB * 128 * 128;
+  static constexpr int OFF_W = 0;
+  static constexpr int OFF_A = OFF_W + W_BYTES;
+  static constexpr int OFF_PAR = OFF_A + 2 * A_STAGE_BYTES;  // bias, ln_w, ln_b
+  static constexpr int OFF_BAR = OFF_PAR + 3 * NOUT * 4;
+  static constexpr int TOTAL = OFF_BAR + 128 + 1024;  // + alignment slack
+  static constexpr int ACC_STAGES = (2 * NOUT <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS = (ACC_STAGES * NOUT <= 32)    ? 32
+                                   : (ACC_STAGES * NOUT <= 64)  ? 64
+                                   : (ACC_STAGES * NOUT <= 128) ? 128
+                                   : (ACC_STAGES * NOUT <= 256) ? 256
+                                                                : 512;
+};
+
+template <int NOUT, int KDIM, int EPI>
+__global__ void __launch_bounds__(TCG_THREADS, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapW, TcGemmArgs p) {
+  using L = TcGemmSmem<NOUT, KDIM>;
+  static_assert(NOUT % 16 == 0 && NOUT <= 512 && KDIM % 64 == 0, "shape");
+  static_assert(EPI != TC_EPI_LN && EPI != TC_EPI_LN_POST || NOUT <= 128, "LayerNorm epilogue needs the row in regs");
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sW = base + L::OFF_W;
+  const uint32_t sA = base + L::OFF_A;
+  float* sPar = reinterpret_cast<float*>(gen + L::OFF_PAR);
+  const uint32_t bars = base + L::OFF_BAR;
+  const uint32_t bar_w = bars, bar_afull = bars + 8, bar_aempty = bars + 24, bar_accfull = bars + 40,
+                 bar_accempty = bars + 56;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + L::OFF_BAR + 96);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_afull + 8 * s, 1);
+      mbar_init(bar_aempty + 8 * s, 1);
+      mbar_init(bar_accfull + 8 * s, 1);
+      mbar_init(bar_accempty + 8 * s, 128);
+    }
+    fence_mbar_init();
+    prefetch_tmap(&tmapA);
+    prefetch_tmap(&tmapW);
+  }
+  for (int i = threadIdx.x; i < NOUT; i += blockDim.x) {
+    sPar[i] = p.bias ? p.bias[i] : 0.f;
+    sPar[NOUT + i] = p.ln_w ? p.ln_w[i] : 1.f;
+    sPar[2 * NOUT + i] = p.ln_b ? p.ln_b[i] : 0.f;
+  }
+  if (warp == 1) {
+    tmem_alloc<1>(bars + 96, L::TMEM_COLS);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(bar_w, L::W_BYTES);
+      for (int kb = 0; kb < L::KB; ++kb)
+        for (int n0 = 0; n0 < NOUT; n0 += 64) tma_load_2d(sW + kb * NOUT * 128 + n0 * 128, &tmapW, bar_w, kb * 64, n0);
+      int i = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
+        const int s = i & 1, ph = (i >> 1) & 1;
+        mbar_wait(bar_aempty + 8 * s, ph ^ 1);
+        mbar_expect_tx(bar_afull + 8 * s, L::A_STAGE_BYTES);
+        for (int kb = 0; kb < L::KB; ++kb)
+          tma_load_2d(sA + s * L::A_STAGE_BYTES + kb * 16384, &tmapA, bar_afull + 8 * s, kb * 64, tile * 128);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      mbar_wait(bar_w, 0);
+      int i = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
+        const int s = i & 1, ph = (i >> 1) & 1;
+        const int as = i % L::ACC_STAGES, aph = (i / L::ACC_STAGES) & 1;
+        mbar_wait(bar_accempty + 8 * as, aph ^ 1);
+        mbar_wait(bar_afull + 8 * s, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int n0 = 0; n0 < NOUT; n0 += 256) {
+          const int nn = (NOUT - n0) < 256 ? (NOUT - n0) : 256;
+          const uint32_t idesc = idesc_f16(128, nn, 0);
+#pragma unroll
+          for (int k16 = 0; k16 < KDIM / 16; ++k16) {
+            const int kb = k16 >> 2, kk = k16 & 3;
+            const uint64_t a_desc = smem_desc_sw128_kmajor(sA + s * L::A_STAGE_BYTES + kb * 16384) + (uint64_t)(kk * 2);
+            const uint64_t b_desc = smem_desc_sw128_kmajor(sW + kb * NOUT * 128 + n0 * 128) + (uint64_t)(kk * 2);
+            umma_f16<1>(tmem + as * NOUT + n0, a_desc, b_desc, idesc, k16 > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(bar_aempty + 8 * s);
+        umma_commit(bar_accfull + 8 * as);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (thread = row)
+    const int q = warp & 3;
+    const float* sBias = sPar;
+    const float* sLw = sPar + NOUT;
+    const float* sLb = sPar + 2 * NOUT;
+    const float slope = (p.act16 == 2 && p.prelu_a) ? p.prelu_a[0] : 0.f;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
+      const int as = i % L::ACC_STAGES, aph = (i / L::ACC_STAGES) & 1;
+      mbar_wait(bar_accfull + 8 * as, aph);
+      tc_fence_after();
+      const long long row = (long long)tile * 128 + q * 32 + lane;
+      const bool live = row < p.M;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + as * NOUT;
+      if constexpr (EPI == TC_EPI_F16 || EPI == TC_EPI_F32) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < NOUT; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c0, r);
+          tmem_ld_wait();
+          if (live) {
+            if constexpr (EPI == TC_EPI_F16) {
+              uint4* dst = reinterpret_cast<uint4*>(p.out16 + row * p.ldo16 + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int c = j * 8 + e * 2;
+                  const __half2 h = __floats2half2_rn(__uint_as_float(r[c]) + sBias[c0 + c],
+                                                      __uint_as_float(r[c + 1]) + sBias[c0 + c + 1]);
+                  w[e] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            } else {
+              float4* dst = reinterpret_cast<float4*>(p.out32 + row * p.ldo32 + c0);
+              const float4* rs = p.res ? reinterpret_cast<const float4*>(p.res + row * p.ldr + c0) : nullptr;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 v;
+                v.x = __uint_as_float(r[4 * j + 0]) + sBias[c0 + 4 * j + 0];
+                v.y = __uint_as_float(r[4 * j + 1]) + sBias[c0 + 4 * j + 1];
+                v.z = __uint_as_float(r[4 * j + 2]) + sBias[c0 + 4 * j + 2];
+                v.w = __uint_as_float(r[4 * j + 3]) + sBias[c0 + 4 * j + 3];
+                if (rs) {
+                  const float4 x = rs[j];
+                  v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+                }
+                dst[j] = v;
+              }
+            }
+          }
+        }
+      } else {
+        // LayerNorm over the whole row held in registers
+        float v[NOUT];
+#pragma unroll
+        for (int c0 = 0; c0 < NOUT; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[c0 + j] = __uint_as_float(r[j]) + sBias[c0 + j];
+        }
+        if (live) {
+          const float4* rs = reinterpret_cast<const float4*>(p.res + row * p.ldr);
+          if constexpr (EPI == TC_EPI_LN) {
+#pragma unroll
+            for (int j = 0; j < NOUT / 4; ++j) {
+              const float4 x = rs[j];
+              v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+            }
+          }
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < NOUT; ++j) sum += v[j];
+          const float mean = sum * (1.f / NOUT);
+          float sq = 0.f;
+#pragma unroll
+          for (int j = 0; j < NOUT; ++j) {
+            const float d = v[j] - mean;
+            sq = fmaf(d, d, sq);
+          }
+          const float rstd = rsqrtf(sq * (1.f / NOUT) + 1e-5f);
+#pragma unroll
+          for (int j = 0; j < NOUT; ++j) v[j] = (v[j] - mean) * rstd * sLw[j] + sLb[j];
+          if constexpr (EPI == TC_EPI_LN_POST) {
+#pragma unroll
+            for (int j = 0; j < NOUT / 4; ++j) {
+              const float4 x = rs[j];
+              v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+            }
+          }
+          float4* d32 = reinterpret_cast<float4*>(p.out32 + row * p.ldo32);
+#pragma unroll
+          for (int j = 0; j < NOUT / 4; ++j) d32[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (p.out16) {
+            uint4* d16 = reinterpret_cast<uint4*>(p.out16 + row * p.ldo16);
+#pragma unroll
+            for (int j = 0; j < NOUT / 8; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
+                if (p.act16 == 1) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                else if (p.act16 == 2) { a = a >= 0.f ? a : slope * a; b = b >= 0.f ? b : slope * b; }
+                const __half2 h = __floats2half2_rn(a, b);
+                w[e] = *reinterpret_cast<const uint32_t*>(&h);
+              }
+              d16[j] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_accempty + 8 * as);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<1>(tmem, L::TMEM_COLS);
+}
+
+template <int NOUT, int KDIM, int EPI>
+static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const TcGemmArgs& args, cudaStream_t st) {
+  using L = TcGemmSmem<NOUT, KDIM>;
+  static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
+  CUtensorMap tmA, tmW;
+  {
+    const uint64_t dims[2] = {(uint64_t)KDIM, (uint64_t)args.M};
+    const uint64_t str[1] = {(uint64_t)lda * 2};
+    const uint32_t box[2] = {64, 128};
+    if (make_tmap_f16(&tmA, A, 2, dims, str, box)) return -1;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)KDIM, (uint64_t)NOUT};
+    const uint64_t str[1] = {(uint64_t)KDIM * 2};
+    const uint32_t box[2] = {64, 64};
+    if (make_tmap_f16(&tmW, W, 2, dims, str, box)) return -1;
+  }
+  auto kern = k_tc_gemm<NOUT, KDIM, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    VATSS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int grid = args.num_tiles < num_sms() ? args.num_tiles : num_sms();
+  kern<<<grid, TCG_THREADS, L::TOTAL, st>>>(tmA, tmW, args);
+  VATSS_LAUNCH_OK();
+  return 0;
+}
+
+int launch_tc_gemm(int epi, const __half* A, long long lda, const __half* W, const float* bias, const float* res,
+                   long long ldr, const float* ln_w, const float* ln_b, float* out32, long long ldo32, __half* out16,
+                   long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int KDIM,
+                   cudaStream_t st) {
+  if (M == 0) return 0;
+  VATSS_CHECK_ARG(((uintptr_t)A & 15) == 0 && (lda * 2) % 16 == 0, "tc_gemm: A must be 16-byte aligned with 16-byte row pitch");
+  TcGemmArgs a;
+  a.M = M;
+  a.num_tiles = (int)((M + 127) / 128);
+  a.bias = bias; a.res = res; a.ldr = ldr; a.ln_w = ln_w; a.ln_b = ln_b;
+  a.out32 = out32; a.ldo32 = ldo32; a.out16 = out16; a.ldo16 = ldo16; a.act16 = act16; a.prelu_a = prelu_a;
+  if (epi == TC_EPI_F16) VATSS_CHECK_ARG(out16 != nullptr, "tc_gemm: fp16 output missing");
+  if (epi == TC_EPI_F32) VATSS_CHECK_ARG(out32 != nullptr, "tc_gemm: fp32 output missing");
+  if (epi == TC_EPI_LN || epi == TC_EPI_LN_POST)
+    VATSS_CHECK_ARG(out32 && res && ln_w && ln_b, "tc_gemm: LayerNorm epilogue needs out32/res/ln_w/ln_b");
+#define TCG_CASE(N_, K_, E_) \
+  if (NOUT == N_ && KDIM == K_ && epi == E_) return tc_gemm_launch<N_, K_, E_>(A, lda, W, a, st);
+  // N = 128 models
+  TCG_CASE(384, 128, TC_EPI_F16)
+  TCG_CASE(128, 128, TC_EPI_LN)
+  TCG_CASE(128, 256, TC_EPI_LN)
+  TCG_CASE(128, 256, TC_EPI_LN_POST)
+  TCG_CASE(128, 128, TC_EPI_LN_POST)
+  TCG_CASE(256, 128, TC_EPI_F32)
+  TCG_CASE(128, 128, TC_EPI_F32)
+  // N = 64 models
+  TCG_CASE(192, 64, TC_EPI_F16)
+  TCG_CASE(64, 64, TC_EPI_LN)
+  TCG_CASE(64, 256, TC_EPI_LN)
+  TCG_CASE(64, 128, TC_EPI_LN)
+  TCG_CASE(64, 256, TC_EPI_LN_POST)
+  TCG_CASE(64, 128, TC_EPI_LN_POST)
+  TCG_CASE(128, 64, TC_EPI_F32)
+  TCG_CASE(64, 64, TC_EPI_F32)
+#undef TCG_CASE
+  set_error("tc_gemm: no tensor-core instantiation for NOUT=%d K=%d epilogue=%d", NOUT, KDIM, epi);
+  return -1;
+}
+
+}  // namespace vatss

@@ -1,0 +1,92 @@
+"""Unit tests of the tcgen05 TENSOR-engine kernels through their stand-alone C-ABI entry points.
+
+Each kernel is compared with a plain PyTorch fp32 evaluation of the same op on the same
+fp16-rounded operands (so the only difference is fp32 accumulation order)."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    assert torch.cuda.is_available()
+    from speech_separation_b200 import _lib
+
+    return _lib.load()
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def ln(x, w, b):
+    return torch.nn.functional.layer_norm(x, (x.shape[-1],), w, b, 1e-5)
+
+
+GEMM_CASES = [
+    # epi, NOUT, K, M
+    (0, 384, 128, 128), (0, 384, 128, 1000), (0, 384, 128, 150 * 283 + 5),
+    (1, 256, 128, 777), (1, 128, 128, 4097),
+    (2, 128, 128, 300), (2, 128, 256, 12345), (3, 128, 256, 513),
+    (0, 192, 64, 999), (2, 64, 64, 1025), (2, 64, 256, 2050), (3, 64, 256, 400), (1, 128, 64, 640), (1, 64, 64, 130),
+]
+
+
+@pytest.mark.parametrize("epi,NOUT,K,M", GEMM_CASES)
+def test_tc_gemm_matches_torch(lib, epi, NOUT, K, M):
+    from speech_separation_b200 import _lib
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(M + NOUT + K + epi)
+    A = torch.randn(M, K, generator=g).to(dev).half()
+    W = (torch.randn(NOUT, K, generator=g) / K ** 0.5).to(dev).half()
+    bias = torch.randn(NOUT, generator=g).to(dev)
+    res = torch.randn(M, NOUT, generator=g).to(dev)
+    lw = (1 + 0.2 * torch.randn(NOUT, generator=g)).to(dev)
+    lb = (0.1 * torch.randn(NOUT, generator=g)).to(dev)
+    slope = torch.tensor([0.25], device=dev)
+    out32 = torch.full((M, NOUT), float("nan"), device=dev)
+    out16 = torch.full((M, NOUT), float("nan"), device=dev, dtype=torch.float16)
+    act16 = 2 if epi == 2 else 0
+    rc = lib.vatss_tc_gemm(epi, _p(A), K, _p(W), _p(bias), _p(res), NOUT, _p(lw), _p(lb), _p(out32), NOUT, _p(out16),
+                           NOUT, act16, _p(slope), M, NOUT, K, None)
+    _lib.check(rc, "vatss_tc_gemm")
+    torch.cuda.synchronize()
+    base = A.float() @ W.float().t() + bias
+    if epi == 0:
+        assert torch.allclose(out16.float(), base, atol=2e-2, rtol=2e-3)
+        err = (out16.float() - base).norm() / base.norm()
+        assert err < 1e-3
+    elif epi == 1:
+        want = base + res
+        assert (out32 - want).norm() / want.norm() < 1e-5
+    elif epi == 2:
+        want = ln(base + res, lw, lb)
+        assert (out32 - want).norm() / want.norm() < 1e-5
+        want16 = torch.where(want >= 0, want, 0.25 * want)
+        assert (out16.float() - want16).norm() / want16.norm() < 1e-3
+    else:
+        want = ln(base, lw, lb) + res
+        assert (out32 - want).norm() / want.norm() < 1e-5
+
+
+def test_tc_gemm_strided_operand(lib):
+    """A taken as a column slice of a wider matrix (the per-speaker halves of the overlap-add output)."""
+    from speech_separation_b200 import _lib
+
+    dev = torch.device("cuda:0")
+    M, K, NOUT = 1000, 128, 128
+    big = torch.randn(M, 2 * K, device=dev).half()
+    W = (torch.randn(NOUT, K, device=dev) / K ** 0.5).half()
+    bias = torch.randn(NOUT, device=dev)
+    for j in range(2):
+        A = big[:, j * K:(j + 1) * K]
+        out32 = torch.empty(M, NOUT, device=dev)
+        rc = lib.vatss_tc_gemm(1, ctypes.c_void_p(A.data_ptr()), 2 * K, _p(W), _p(bias), None, 0, None, None, _p(out32),
+                               NOUT, None, 0, 0, None, M, NOUT, K, None)
+        _lib.check(rc, "vatss_tc_gemm")
+        want = A.float() @ W.float().t() + bias
+        assert (out32 - want).norm() / want.norm() < 1e-5

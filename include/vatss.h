@@ -171,6 +171,14 @@ int vatss_tc_gemm(int epi, const void* A16, long long lda, const void* W16, cons
                   long long ldr, const float* ln_w, const float* ln_b, float* out32, long long ldo32, void* out16,
                   long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int K, void* stream);
 
+/* vatss_tc_lstm: nn.LSTM(N->128) recurrence (src/model/dptn.py:23-29,49) on a CTA pair, input and recurrent
+ * contractions fused per time step.  x16 (B,S,C,N) fp16 token-major; params: fp32 nn.LSTM tensors of the
+ * forward (and reverse, if ndir=2) direction; out16 (B*S*C, ndir*128) fp16, relu(h) if act=1.
+ * mode 0 = intra-chunk sequences, 1 = inter-chunk.  wpack: ndir*512*(N+128) halfs, bias_pack: ndir*512 floats. */
+int vatss_tc_lstm(const void* x16, const float* const* lstm_params /* [8]: Wih,Whh,bih,bhh fwd then rev */,
+                  void* out16, int mode, int B, int S, int C, int N, int ndir, int act, void* wpack,
+                  float* bias_pack, void* stream);
+
 /* Instrumentation (no reference counterpart; used by bench.py).
  * vatss_launch_count: number of kernels this library has launched in this process.
  * vatss_profile_begin: start recording CUDA-event pairs around the stages of subsequent calls

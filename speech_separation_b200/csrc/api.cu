@@ -382,6 +382,20 @@ int vatss_tc_gemm(int epi, const void* A16, long long lda, const void* W16, cons
                         (__half*)out16, ldo16, act16, prelu_a, M, NOUT, K, (cudaStream_t)stream);
 }
 
+int vatss_tc_lstm(const void* x16, const float* const* lp, void* out16, int mode, int B, int S, int C, int N, int ndir,
+                  int act, void* wpack, float* bias_pack, void* stream) {
+  VATSS_CHECK_ARG(x16 && lp && out16 && wpack && bias_pack, "tc_lstm: NULL pointer");
+  VATSS_CHECK_ARG(ndir == 1 || ndir == 2, "tc_lstm: ndir must be 1 or 2");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int dir = 0; dir < ndir; ++dir) {
+    int rc = launch_pack_lstm(lp[4 * dir + 0], lp[4 * dir + 1], lp[4 * dir + 2], lp[4 * dir + 3], N, dir,
+                              (__half*)wpack, bias_pack, st);
+    if (rc) return rc;
+  }
+  return launch_tc_lstm((const __half*)x16, (const __half*)wpack, bias_pack, (__half*)out16, mode, B, S, C, N, ndir,
+                        act, st);
+}
+
 unsigned long long vatss_launch_count(void) { return g_launches.load(); }
 
 int vatss_profile_begin(void) {

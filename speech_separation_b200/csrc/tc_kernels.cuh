@@ -20,4 +20,13 @@ int launch_tc_gemm(int epi, const __half* A, long long lda, const __half* W, con
                    long long ldr, const float* ln_w, const float* ln_b, float* out32, long long ldo32, __half* out16,
                    long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int KDIM, cudaStream_t st);
 
+// Persistent LSTM recurrence on a CTA pair (tc_lstm.cu).  x16: token-major (B,S,C,NFEAT) fp16 activation,
+// Wpack / bias_pack from launch_pack_lstm, out16: (tokens, ndir*128) fp16 (relu(h) when act=1).
+// mode 0: intra-chunk sequences (time = chunk position), mode 1: inter-chunk sequences (time = chunk index).
+int launch_tc_lstm(const __half* x16, const __half* Wpack, const float* bias_pack, __half* out16, int mode, int B,
+                   int S, int C, int NFEAT, int ndir, int act, cudaStream_t st);
+// Wpack: [ndir][512][NFEAT+128] fp16, bias_pack: [ndir][512] fp32
+int launch_pack_lstm(const float* Wih, const float* Whh, const float* bih, const float* bhh, int N, int dir,
+                     __half* Wpack, float* bias_pack, cudaStream_t st);
+
 }  // namespace vatss

@@ -1,0 +1,429 @@
+// TENSOR engine: persistent LSTM recurrence on a CTA pair (tcgen05 cta_group::2).
+//
+// nn.LSTM(N -> H=128), one layer, h0 = c0 = 0, gate order i,f,g,o (src/model/dptn.py:23-29,49;
+// src/model/dprnn.py:18,60).  One cluster of two CTAs owns 2 x 128 sequences of one direction for all
+// time steps.  Per step and per sequence tile the gate pre-activations
+//     G[256 seq, 512] = [x_t | h_{t-1}] [256, N+128] x [W_ih | W_hh]^T
+// are one M=256 tensor-core contraction (input and recurrent halves fused, so the 1.36 M x 1024
+// pre-activation tensor never exists in HBM).  The fp16 weights of a direction (256 KB) are split over
+// the two SMs' shared memory (each CTA supplies half of the B rows of every MMA, hardware shares them),
+// the fp32 accumulators fill each CTA's TMEM (128 lanes x 512 columns), x_t tiles arrive by TMA
+// (4-D tensor map over the token-major activation: works for intra- and inter-chunk sequences), h_t is
+// written back to shared memory as the next step's A operand and to HBM as the layer output.
+//
+// The 512 gate columns are processed as 4 chunks of 128 columns = 32 hidden units x (i,f,g,o), so that
+// the gate math of chunk c overlaps the MMAs of the other chunks and the x-part of step t+1.
+//
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA) + TMEM allocator,
+// warps 2..9 gate math (thread = sequence row, 16 hidden units per chunk).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tc_kernels.cuh"
+
+namespace vatss {
+
+using namespace ptx;
+
+constexpr int LSTM_H = 128;
+constexpr int LSTM_THREADS = 320;
+constexpr int LSTM_CHUNKS = 4;          // 4 x (32 units x 4 gates) = 512 accumulator columns
+constexpr int LSTM_UNITS_PER_CHUNK = 32;
+
+struct TcLstmArgs {
+  int mode;        // 0 intra (sequences = flattened (b,s), time = k), 1 inter (sequences = (b,k), time = s)
+  int len;         // time steps
+  int ndir;
+  int G;           // intra: number of sequences
+  int B, S, C;     // geometry of the (B,S,C,N) activation
+  int Kc, Bc;      // inter: tile = Kc chunk positions x Bc utterances (Kc*Bc <= 128)
+  int kblocks;     // inter: ceil(C / Kc)
+  int num_tiles;   // sequence tiles of 128 rows (per direction)
+  int act;         // 1: store relu(h) (DPTN feeds the LSTM output through ReLU only), 0: store h
+  const float* bias;   // [ndir][512] b_ih + b_hh in accumulator-column order
+  __half* out;         // [tokens, ndir*128]
+};
+
+template <int NFEAT>
+struct TcLstmSmem {
+  static constexpr int KBX = NFEAT / 64;             // x k-blocks
+  static constexpr int KBT = KBX + 2;                // + 2 h k-blocks
+  static constexpr int W_BLOCK = 64 * 128;           // 64 B-rows x 128 B
+  static constexpr int W_BYTES = LSTM_CHUNKS * KBT * W_BLOCK;
+  static constexpr int X_STAGE = KBX * 16384;
+  static constexpr int H_BYTES = 2 * 16384;
+  static constexpr int OFF_W = 0;
+  static constexpr int OFF_X = OFF_W + W_BYTES;
+  static constexpr int OFF_H = OFF_X + 2 * X_STAGE;
+  static constexpr int OFF_BIAS = OFF_H + H_BYTES;
+  static constexpr int OFF_BAR = OFF_BIAS + 512 * 4;
+  static constexpr int TOTAL = OFF_BAR + 256;
+};
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+template <int NFEAT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
+k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapW, TcLstmArgs p) {
+  using L = TcLstmSmem<NFEAT>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t base = smem_u32(smem);
+  const uint32_t sW = base + L::OFF_W, sX = base + L::OFF_X, sH = base + L::OFF_H;
+  float* sBias = reinterpret_cast<float*>(smem + L::OFF_BIAS);
+  const uint32_t bars = base + L::OFF_BAR;
+  // barrier map (8 bytes each)
+  const uint32_t bar_w = bars;                 // local: weights landed
+  const uint32_t bar_xfull = bars + 8;         // [2] leader: x tiles of both CTAs landed
+  const uint32_t bar_xempty = bars + 24;       // [2] both: MMAs finished reading the x stage
+  const uint32_t bar_accfull = bars + 40;      // [4] both: gate pre-activations of chunk c complete
+  const uint32_t bar_accempty = bars + 72;     // [4] leader: both CTAs' gate warps drained chunk c
+  const uint32_t bar_hfull = bars + 104;       // leader: h_t of both CTAs in shared memory
+  const uint32_t tmem_slot = bars + 128;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int dir = blockIdx.y;
+  const int tile = (blockIdx.x >> 1) * 2 + (int)rank;   // this CTA's 128-sequence tile
+  const int len = p.len;
+
+  if ((base & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_xfull + 8 * s, 1);
+      mbar_init(bar_xempty + 8 * s, 1);
+    }
+    for (int c = 0; c < LSTM_CHUNKS; ++c) {
+      mbar_init(bar_accfull + 8 * c, 1);
+      mbar_init(bar_accempty + 8 * c, 16);  // 8 gate warps x 2 CTAs
+    }
+    mbar_init(bar_hfull, 16);
+    fence_mbar_init();
+    prefetch_tmap(&tmapX);
+    prefetch_tmap(&tmapW);
+  }
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) sBias[i] = p.bias[dir * 512 + i];
+  // clean operand buffers: rows that no TMA box covers must not hold NaN bit patterns
+  for (int i = threadIdx.x; i < (2 * L::X_STAGE + L::H_BYTES) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem + L::OFF_X)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 1) {
+    tmem_alloc<2>(tmem_slot, 512);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();   // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + L::OFF_BAR + 128);
+
+  // this CTA's half of the weights: packed rows (dir, rank, chunk, 64) x K, resident for the whole kernel
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar_w, L::W_BYTES);
+    const int wrow0 = (dir * 2 + (int)rank) * (LSTM_CHUNKS * 64);
+    for (int c = 0; c < LSTM_CHUNKS; ++c)
+      for (int kb = 0; kb < L::KBT; ++kb)
+        tma_load_2d(sW + (c * L::KBT + kb) * L::W_BLOCK, &tmapW, bar_w, kb * 64, wrow0 + c * 64);
+  }
+  mbar_wait(bar_w, 0);
+  cluster_sync();   // both halves of the weights are in place before the leader issues any MMA
+
+  // tile geometry
+  int c0 = 0, c1 = 0, c2 = 0;  // TMA coordinates other than feature/time
+  if (p.mode == 0) {
+    c0 = tile * 128;           // g0
+  } else {
+    c1 = (tile % p.kblocks) * p.Kc;   // k0
+    c2 = (tile / p.kblocks) * p.Bc;   // b0
+  }
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      // x tiles: both CTAs' loads complete on the leader's barrier
+      uint32_t xfull_leader[2];
+      for (int s = 0; s < 2; ++s)
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(xfull_leader[s]) : "r"(bar_xfull + 8 * s));
+      const uint32_t box_bytes = (p.mode == 0 ? 128 : p.Kc * p.Bc) * 128;
+      for (int step = 0; step < len; ++step) {
+        const int t = dir == 0 ? step : len - 1 - step;
+        const int s = step & 1, n = step >> 1;
+        mbar_wait(bar_xempty + 8 * s, (n & 1) ^ 1);
+        if (leader) mbar_expect_tx(bar_xfull + 8 * s, 2 * L::KBX * box_bytes);
+        for (int kb = 0; kb < L::KBX; ++kb) {
+          const uint32_t dst = sX + s * L::X_STAGE + kb * 16384;
+          if (p.mode == 0) tma_load_4d_cg2(dst, &tmapX, xfull_leader[s], kb * 64, t, c0, 0);
+          else tma_load_4d_cg2(dst, &tmapX, xfull_leader[s], kb * 64, c1, t, c2);
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  constexpr uint32_t IDESC = idesc_f16(256, 128, 0);
+
+  if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (leader && lane == 0) {
+      auto issue_x = [&](int c, int s) {
+#pragma unroll
+        for (int k16 = 0; k16 < NFEAT / 16; ++k16) {
+          const int kb = k16 >> 2, kk = k16 & 3;
+          const uint64_t a = smem_desc_sw128_kmajor(sX + s * L::X_STAGE + kb * 16384) + (uint64_t)(kk * 2);
+          const uint64_t b = smem_desc_sw128_kmajor(sW + (c * L::KBT + kb) * L::W_BLOCK) + (uint64_t)(kk * 2);
+          umma_f16<2>(tmem + c * 128, a, b, IDESC, k16 > 0 ? 1u : 0u);
+        }
+      };
+      auto issue_h = [&](int c) {
+#pragma unroll
+        for (int k16 = 0; k16 < LSTM_H / 16; ++k16) {
+          const int kb = k16 >> 2, kk = k16 & 3;
+          const uint64_t a = smem_desc_sw128_kmajor(sH + kb * 16384) + (uint64_t)(kk * 2);
+          const uint64_t b = smem_desc_sw128_kmajor(sW + (c * L::KBT + L::KBX + kb) * L::W_BLOCK) + (uint64_t)(kk * 2);
+          umma_f16<2>(tmem + c * 128, a, b, IDESC, 1u);
+        }
+      };
+      // step 0: x-part only (h_{-1} = 0)
+      mbar_wait_cluster(bar_xfull, 0);
+      tc_fence_after();
+      for (int c = 0; c < LSTM_CHUNKS; ++c) {
+        issue_x(c, 0);
+        umma_commit_cg2(bar_accfull + 8 * c, 3);
+      }
+      umma_commit_cg2(bar_xempty, 3);
+      for (int step = 1; step < len; ++step) {
+        const int s = step & 1;
+        mbar_wait_cluster(bar_xfull + 8 * s, (step >> 1) & 1);
+        tc_fence_after();
+        // x-part of this step for chunks 0..2 as soon as the gate warps have drained them (step-1)
+        for (int c = 0; c < LSTM_CHUNKS - 1; ++c) {
+          mbar_wait_cluster(bar_accempty + 8 * c, (step - 1) & 1);
+          tc_fence_after();
+          issue_x(c, s);
+        }
+        // h_{step-1} complete in both CTAs
+        mbar_wait_cluster(bar_hfull, (step - 1) & 1);
+        tc_fence_after();
+        for (int c = 0; c < LSTM_CHUNKS - 1; ++c) {
+          issue_h(c);
+          umma_commit_cg2(bar_accfull + 8 * c, 3);
+        }
+        mbar_wait_cluster(bar_accempty + 8 * (LSTM_CHUNKS - 1), (step - 1) & 1);
+        tc_fence_after();
+        issue_x(LSTM_CHUNKS - 1, s);
+        umma_commit_cg2(bar_xempty + 8 * s, 3);
+        issue_h(LSTM_CHUNKS - 1);
+        umma_commit_cg2(bar_accfull + 8 * (LSTM_CHUNKS - 1), 3);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 2) {
+    // ------------------------------------------------------------------ gate math
+    const int gw = warp - 2;
+    const int q = warp & 3;            // TMEM lane quadrant this warp may touch
+    const int half = gw >> 2;          // which 16 of the chunk's 32 units
+    const int r = q * 32 + lane;       // sequence row inside the tile
+    // global output row of this sequence at time t: row_base + t * row_tstride (or invalid)
+    long long row_base = 0, row_tstride = 0;
+    bool valid;
+    if (p.mode == 0) {
+      const long long g = (long long)c0 + r;
+      valid = g < p.G;
+      row_base = g * p.C;
+      row_tstride = 1;
+    } else {
+      const int bl = r / p.Kc, kl = r - bl * p.Kc;
+      valid = (r < p.Kc * p.Bc) && (c2 + bl < p.B) && (c1 + kl < p.C);
+      row_base = (long long)(c2 + bl) * p.S * p.C + (c1 + kl);
+      row_tstride = p.C;
+    }
+    const int ldo = p.ndir * LSTM_H;
+    float cst[LSTM_CHUNKS][16];
+#pragma unroll
+    for (int c = 0; c < LSTM_CHUNKS; ++c)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) cst[c][j] = 0.f;
+    uint32_t accempty_leader[LSTM_CHUNKS], hfull_leader;
+#pragma unroll
+    for (int c = 0; c < LSTM_CHUNKS; ++c)
+      asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(accempty_leader[c]) : "r"(bar_accempty + 8 * c));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(hfull_leader) : "r"(bar_hfull));
+
+    for (int step = 0; step < len; ++step) {
+      const int t = dir == 0 ? step : len - 1 - step;
+      uint32_t hp[LSTM_CHUNKS][8];   // packed fp16 h of this step (kept until all h-part MMAs have read sH)
+#pragma unroll
+      for (int c = 0; c < LSTM_CHUNKS; ++c) {
+        mbar_wait(bar_accfull + 8 * c, step & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + c * 128 + half * 16;
+        uint32_t gi[16], gf[16], gg[16], go[16];
+        tmem_ld_32x32b_x16(taddr + 0, gi);
+        tmem_ld_32x32b_x16(taddr + 32, gf);
+        tmem_ld_32x32b_x16(taddr + 64, gg);
+        tmem_ld_32x32b_x16(taddr + 96, go);
+        tmem_ld_wait();
+        // accumulator chunk drained -> the MMA warp may start the next step's x-part into it
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(accempty_leader[c]) : "memory");
+        const float* bc = sBias + c * 128 + half * 16;
+        float hv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float ig = sigmoid_fast(__uint_as_float(gi[j]) + bc[j]);
+          const float fg = sigmoid_fast(__uint_as_float(gf[j]) + bc[32 + j]);
+          const float g_ = tanh_fast(__uint_as_float(gg[j]) + bc[64 + j]);
+          const float og = sigmoid_fast(__uint_as_float(go[j]) + bc[96 + j]);
+          const float cc = fmaf(fg, cst[c][j], ig * g_);
+          cst[c][j] = cc;
+          hv[j] = og * tanh_fast(cc);
+        }
+        uint32_t ho[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __half2 a = __floats2half2_rn(hv[2 * j], hv[2 * j + 1]);
+          hp[c][j] = *reinterpret_cast<const uint32_t*>(&a);
+          const __half2 o = p.act ? __floats2half2_rn(fmaxf(hv[2 * j], 0.f), fmaxf(hv[2 * j + 1], 0.f)) : a;
+          ho[j] = *reinterpret_cast<const uint32_t*>(&o);
+        }
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (row_base + (long long)t * row_tstride) * ldo + dir * LSTM_H +
+                                                c * LSTM_UNITS_PER_CHUNK + half * 16);
+          dst[0] = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+          dst[1] = make_uint4(ho[4], ho[5], ho[6], ho[7]);
+        }
+      }
+      // acc_full of the last chunk implies every h-part MMA of this step has finished reading sH
+      if (step + 1 < len) {
+#pragma unroll
+        for (int c = 0; c < LSTM_CHUNKS; ++c) {
+          const int k = c * LSTM_UNITS_PER_CHUNK + half * 16;   // hidden-unit index = K index of the h operand
+          const int kb = k >> 6, ch = (k & 63) >> 3;
+          const uint32_t a0 = sH + kb * 16384 + sw128_offset((uint32_t)r, (uint32_t)ch);
+          const uint32_t a1 = sH + kb * 16384 + sw128_offset((uint32_t)r, (uint32_t)ch + 1);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(hp[c][0]), "r"(hp[c][1]),
+                       "r"(hp[c][2]), "r"(hp[c][3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(hp[c][4]), "r"(hp[c][5]),
+                       "r"(hp[c][6]), "r"(hp[c][7]) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(hfull_leader) : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 1) tmem_dealloc<2>(tmem, 512);
+}
+
+template <int NFEAT>
+static int tc_lstm_launch(const __half* x16, const __half* Wpack, const TcLstmArgs& a, cudaStream_t st) {
+  using L = TcLstmSmem<NFEAT>;
+  static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
+  CUtensorMap tmX, tmW;
+  if (a.mode == 0) {
+    const uint64_t dims[4] = {(uint64_t)NFEAT, (uint64_t)a.C, (uint64_t)a.G, 1};
+    const uint64_t str[3] = {(uint64_t)NFEAT * 2, (uint64_t)a.C * NFEAT * 2, (uint64_t)a.G * a.C * NFEAT * 2};
+    const uint32_t box[4] = {64, 1, 128, 1};
+    if (make_tmap_f16(&tmX, x16, 4, dims, str, box)) return -1;
+  } else {
+    const uint64_t dims[4] = {(uint64_t)NFEAT, (uint64_t)a.C, (uint64_t)a.S, (uint64_t)a.B};
+    const uint64_t str[3] = {(uint64_t)NFEAT * 2, (uint64_t)a.C * NFEAT * 2, (uint64_t)a.S * a.C * NFEAT * 2};
+    const uint32_t box[4] = {64, (uint32_t)a.Kc, 1, (uint32_t)a.Bc};
+    if (make_tmap_f16(&tmX, x16, 4, dims, str, box)) return -1;
+  }
+  {
+    const uint64_t ktot = NFEAT + LSTM_H;
+    const uint64_t dims[2] = {ktot, (uint64_t)a.ndir * 2 * LSTM_CHUNKS * 64};
+    const uint64_t str[1] = {ktot * 2};
+    const uint32_t box[2] = {64, 64};
+    if (make_tmap_f16(&tmW, Wpack, 2, dims, str, box)) return -1;
+  }
+  auto kern = k_tc_lstm<NFEAT>;
+  static bool configured = false;
+  if (!configured) {
+    VATSS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int pairs = (a.num_tiles + 1) / 2;
+  dim3 grid(2 * pairs, a.ndir);
+  kern<<<grid, LSTM_THREADS, L::TOTAL, st>>>(tmX, tmW, a);
+  VATSS_LAUNCH_OK();
+  return 0;
+}
+
+// choose the inter-chunk tile shape (Kc chunk positions x Bc utterances, Kc*Bc <= 128) with the fewest tiles
+static void pick_inter_tile(int C, int B, int* Kc, int* Bc) {
+  long long best = -1;
+  for (int k = 1; k <= 128 && k <= C; ++k) {
+    int b = 128 / k;
+    if (b > B) b = B;
+    if (b < 1) continue;
+    const long long tiles = (long long)((C + k - 1) / k) * ((B + b - 1) / b);
+    if (best < 0 || tiles < best || (tiles == best && k * b > (*Kc) * (*Bc))) {
+      best = tiles; *Kc = k; *Bc = b;
+    }
+  }
+}
+
+int launch_tc_lstm(const __half* x16, const __half* Wpack, const float* bias_pack, __half* out16, int mode, int B,
+                   int S, int C, int NFEAT, int ndir, int act, cudaStream_t st) {
+  TcLstmArgs a;
+  a.mode = mode; a.ndir = ndir; a.B = B; a.S = S; a.C = C; a.act = act; a.bias = bias_pack; a.out = out16;
+  a.Kc = 0; a.Bc = 0; a.kblocks = 1; a.G = 0;
+  if (mode == 0) {
+    a.len = C;
+    a.G = B * S;
+    a.num_tiles = (a.G + 127) / 128;
+  } else {
+    a.len = S;
+    pick_inter_tile(C, B, &a.Kc, &a.Bc);
+    a.kblocks = (C + a.Kc - 1) / a.Kc;
+    a.num_tiles = a.kblocks * ((B + a.Bc - 1) / a.Bc);
+  }
+  if (a.num_tiles == 0 || a.len == 0) return 0;
+  if (NFEAT == 128) return tc_lstm_launch<128>(x16, Wpack, a, st);
+  if (NFEAT == 64) return tc_lstm_launch<64>(x16, Wpack, a, st);
+  set_error("tc_lstm: num_features %d unsupported (64 or 128)", NFEAT);
+  return -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing: fp32 nn.LSTM parameters -> per (direction, CTA rank, chunk) B-operand rows
+//   packed row (dir, rank, c, j): gate = 2*rank + j/32, unit = 32*c + j%32, source row = gate*128 + unit
+//   columns [0,N) = W_ih row, [N, N+128) = W_hh row
+//   bias_pack[dir][128*c + 32*gate + u] = b_ih + b_hh of (gate, unit 32*c+u)   (accumulator-column order)
+// ------------------------------------------------------------------------------------------
+__global__ void k_pack_lstm(const float* __restrict__ Wih, const float* __restrict__ Whh,
+                            const float* __restrict__ bih, const float* __restrict__ bhh, int N, int dir,
+                            __half* __restrict__ Wpack, float* __restrict__ bias_pack) {
+  const int ktot = N + LSTM_H;
+  const int prow = blockIdx.x;  // 0..511 within this direction: (rank, c, j)
+  const int rank = prow / 256, c = (prow % 256) / 64, j = prow % 64;
+  const int gate = 2 * rank + j / 32, unit = 32 * c + j % 32;
+  const int src = gate * LSTM_H + unit;
+  __half* dst = Wpack + ((size_t)dir * 512 + prow) * ktot;
+  for (int k = threadIdx.x; k < ktot; k += blockDim.x)
+    dst[k] = __float2half_rn(k < N ? Wih[(size_t)src * N + k] : Whh[(size_t)src * LSTM_H + (k - N)]);
+  if (threadIdx.x == 0) bias_pack[dir * 512 + 128 * c + 32 * gate + unit % 32] = bih[src] + bhh[src];
+}
+
+int launch_pack_lstm(const float* Wih, const float* Whh, const float* bih, const float* bhh, int N, int dir,
+                     __half* Wpack, float* bias_pack, cudaStream_t st) {
+  k_pack_lstm<<<512, 128, 0, st>>>(Wih, Whh, bih, bhh, N, dir, Wpack, bias_pack);
+  VATSS_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace vatss

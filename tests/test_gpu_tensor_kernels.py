@@ -90,3 +90,50 @@ def test_tc_gemm_strided_operand(lib):
         _lib.check(rc, "vatss_tc_gemm")
         want = A.float() @ W.float().t() + bias
         assert (out32 - want).norm() / want.norm() < 1e-5
+
+
+LSTM_CASES = [
+    # mode, B, S, C, N, ndir, act
+    (0, 1, 3, 5, 128, 1, 0),       # one partial tile, forward only, tiny
+    (0, 2, 70, 12, 128, 2, 1),     # 140 sequences -> 2 tiles (1 pair), both directions
+    (1, 3, 9, 150, 128, 2, 1),     # inter: sequences (b,k), time = chunk index
+    (1, 32, 6, 150, 128, 2, 0),    # inter with the production tile shape (30 x 4)
+    (0, 5, 77, 10, 64, 2, 1),      # N = 64 models, 385 sequences -> 4 tiles (2 pairs)
+    (1, 2, 7, 250, 64, 1, 0),      # DPRNN-like chunk, unidirectional inter
+]
+
+
+@pytest.mark.parametrize("mode,B,S,C,N,ndir,act", LSTM_CASES)
+def test_tc_lstm_matches_torch(lib, mode, B, S, C, N, ndir, act):
+    from speech_separation_b200 import _lib
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(mode * 100 + B + S + C + N)
+    H = 128
+    rnn = torch.nn.LSTM(N, H, batch_first=True, bidirectional=(ndir == 2))
+    with torch.no_grad():
+        for p_ in rnn.parameters():
+            p_.copy_(p_.half().float() if p_.dim() == 2 else p_)  # fp16-representable weights
+    x = torch.randn(B, S, C, N).half()
+    xf = x.float()
+    seqs = xf.reshape(B * S, C, N) if mode == 0 else xf.permute(0, 2, 1, 3).reshape(B * C, S, N)
+    with torch.no_grad():
+        ref = rnn(seqs)[0]  # (G, len, ndir*H), CPU fp32
+    ref = ref.reshape(B, S, C, ndir * H) if mode == 0 else ref.reshape(B, C, S, ndir * H).permute(0, 2, 1, 3)
+    if act:
+        ref = torch.relu(ref)
+    names = ["weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"]
+    keep = [getattr(rnn, n + suf).detach().to(dev).contiguous() for suf in (["", "_reverse"][:ndir]) for n in names]
+    table = (ctypes.c_void_p * 8)(*([t.data_ptr() for t in keep] + [None] * (8 - len(keep))))
+    xd = x.to(dev).contiguous()
+    out = torch.full((B * S * C, ndir * H), float("nan"), dtype=torch.float16, device=dev)
+    wpack = torch.empty(ndir * 512 * (N + H), dtype=torch.float16, device=dev)
+    bpack = torch.empty(ndir * 512, dtype=torch.float32, device=dev)
+    rc = lib.vatss_tc_lstm(_p(xd), table, _p(out), mode, B, S, C, N, ndir, act, _p(wpack), _p(bpack), None)
+    _lib.check(rc, "vatss_tc_lstm")
+    torch.cuda.synchronize()
+    got = out.float().cpu().reshape(B, S, C, ndir * H)
+    assert torch.isfinite(got).all()
+    err = (got - ref).norm() / ref.norm()
+    print(f"tc_lstm mode={mode} B={B} S={S} C={C} N={N} ndir={ndir}: rel err {err:.3e}, max abs {(got - ref).abs().max():.3e}")
+    assert err < 3e-3  # fp16 h feedback + fp16 output + tanh.approx

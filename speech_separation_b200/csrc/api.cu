@@ -246,7 +246,7 @@ static int run_tail_generic(const vatss_model_desc* d, const float* const* param
   if ((rc = launch_gemm_simt(w.xa, N, params[VATSS_P_SPK_W], params[VATSS_P_SPK_B], nullptr, nullptr, 0, w.y,
                              2 * N, g.tokens, 2 * N, N, 2, params[VATSS_P_PRELU], st)))
     return rc;
-  if ((rc = launch_ola_token_major(w.y, g.B, g.S, d->C, d->P, g.L, 2 * N, w.ola, st))) return rc;
+  if ((rc = launch_ola_token_major(w.y, g.B, g.S, d->C, d->P, g.L, 2 * N, w.ola, nullptr, st))) return rc;
   float* preds[2] = {s1_pred, s2_pred};
   for (int j = 0; j < 2; ++j) {
     if (d->kind == VATSS_KIND_DPTN_MASK) {

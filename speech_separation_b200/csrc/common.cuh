@@ -116,7 +116,8 @@ int launch_lstm_simt(const float* pre, const float* Whh_f, const float* Whh_r, f
                      int H, int ndir, cudaStream_t st);
 
 // tail.cu
-int launch_ola_token_major(const float* y, int B, int S, int C, int P, int L, int W, float* ola, cudaStream_t st);
+int launch_ola_token_major(const float* y, int B, int S, int C, int P, int L, int W, float* ola, __half* ola16,
+                           cudaStream_t st);
 int launch_mask_combine(const float* t, const float* g, const float* enc, float* u, long long n, cudaStream_t st);
 int launch_decoder(const float* u, const float* Wd, int B, int L, int N, int K, int T, float* proj,
                    float* wav, cudaStream_t st);

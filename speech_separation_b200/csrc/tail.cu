@@ -10,7 +10,7 @@ namespace vatss {
 // (plain sum, increasing s), zero outside [0,(S-1)P+C).  W = row width (2N).
 __global__ void __launch_bounds__(256)
 k_ola_token_major(const float* __restrict__ y, int S, int C, int P, int L, int W4, int padl, int Lo,
-                  long long total, float4* __restrict__ ola) {
+                  long long total, float4* __restrict__ ola, uint2* __restrict__ ola16) {
   const float4* y4 = reinterpret_cast<const float4*>(y);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -30,10 +30,14 @@ k_ola_token_major(const float* __restrict__ y, int S, int C, int P, int L, int W
       }
     }
     ola[i] = acc;
+    if (ola16) {
+      const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi = __floats2half2_rn(acc.z, acc.w);
+      ola16[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
   }
 }
 
-int launch_ola_token_major(const float* y, int B, int S, int C, int P, int L, int W, float* ola,
+int launch_ola_token_major(const float* y, int B, int S, int C, int P, int L, int W, float* ola, __half* ola16,
                            cudaStream_t st) {
   VATSS_CHECK_ARG(W % 4 == 0, "overlap-add: row width %d must be a multiple of 4", W);
   const int Lo = (S - 1) * P + C;
@@ -42,7 +46,7 @@ int launch_ola_token_major(const float* y, int B, int S, int C, int P, int L, in
   if (total == 0) return 0;
   int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   k_ola_token_major<<<blocks, 256, 0, st>>>(y, S, C, P, L, W / 4, padl, Lo, total,
-                                            reinterpret_cast<float4*>(ola));
+                                            reinterpret_cast<float4*>(ola), reinterpret_cast<uint2*>(ola16));
   VATSS_LAUNCH_OK();
   return 0;
 }

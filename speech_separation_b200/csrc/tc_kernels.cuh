@@ -29,4 +29,7 @@ int launch_tc_lstm(const __half* x16, const __half* Wpack, const float* bias_pac
 int launch_pack_lstm(const float* Wih, const float* Whh, const float* bih, const float* bhh, int N, int dir,
                      __half* Wpack, float* bias_pack, cudaStream_t st);
 
+// attention core on fp16 packed qkv (tokens, 3N) -> out16 (tokens, N); q is pre-scaled by log2(e)/sqrt(hd)
+int launch_attention_f16(const __half* qkv, __half* out, SeqMap map, int N, int heads, cudaStream_t st);
+
 }  // namespace vatss

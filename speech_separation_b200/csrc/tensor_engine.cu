@@ -1,15 +1,272 @@
+// TENSOR engine: host-side launch sequence of the forward pass on the tcgen05 kernels.
+//
+// Residual stream: fp32 master copy + fp16 copy (the A operand of the next projection) written by the
+// LayerNorm epilogues; every contraction runs on tcgen05 with fp16 operands and fp32 accumulation.
+// (fp16 rather than bf16 operands: same tensor-core rate, and bf16 at every site misses the 1e-3
+// waveform tolerance - SURVEY.md §7.3.)
 #include "tensor_engine.cuh"
+
+#include "tc_kernels.cuh"
 
 namespace vatss {
 
-bool tensor_engine_supports(const vatss_model_desc* d) { (void)d; return false; }
-size_t tensor_engine_packed_bytes(const vatss_model_desc* d) { (void)d; return 0; }
-size_t tensor_engine_workspace_bytes(const vatss_model_desc*, int, int, int, int, int) { return 0; }
-int tensor_engine_pack(const vatss_model_desc*, const float* const*, void*, cudaStream_t) { return 0; }
-int tensor_engine_forward(const vatss_model_desc*, const float* const*, const void*, const float*, const float*,
-                          const float*, int, int, int, int, int, float*, float*, void*, cudaStream_t) {
-  set_error("tensor engine not built");
-  return -1;
+namespace {
+
+inline const float* sub_param(const float* const* params, int blk, int path, int slot) {
+  return params[VATSS_P_GLOBAL_COUNT + (2 * blk + path) * VATSS_S_COUNT + slot];
+}
+
+struct Bump {
+  char* base;
+  size_t off = 0;
+  explicit Bump(void* p) : base(reinterpret_cast<char*>(p)) {}
+  template <typename T>
+  T* take(size_t count) {
+    T* r = reinterpret_cast<T*>(base + off);
+    off += ((count * sizeof(T) + 1023) / 1024) * 1024;
+    return r;
+  }
+};
+
+// ---- packed weights -----------------------------------------------------------------------
+struct SubPacked {
+  __half* win;     // [3N, N], q rows pre-scaled by log2(e)/sqrt(hd)
+  float* bin;      // [3N]
+  __half* wout;    // [N, N]
+  __half* wffn;    // [N, ndir*H]
+  __half* wlstm;   // [ndir][512][N+128]
+  float* blstm;    // [ndir][512]
+};
+struct Packed {
+  SubPacked sub[64];
+  __half *wspk, *whead, *wgate;
+};
+
+size_t carve_packed(const vatss_model_desc* d, void* buf, Packed* out) {
+  Bump b(buf);
+  Packed p;
+  const size_t N = d->N, H = d->H;
+  const bool dprnn = d->kind == VATSS_KIND_DPRNN;
+  for (int i = 0; i < d->num_blocks * 2; ++i) {
+    const int ndir = (i % 2 == 0 || d->bidir) ? 2 : 1;
+    SubPacked& s = p.sub[i];
+    s.win = b.take<__half>(dprnn ? 0 : 3 * N * N);
+    s.bin = b.take<float>(dprnn ? 0 : 3 * N);
+    s.wout = b.take<__half>(dprnn ? 0 : N * N);
+    s.wffn = b.take<__half>(N * ndir * H);
+    s.wlstm = b.take<__half>((size_t)ndir * 512 * (N + 128));
+    s.blstm = b.take<float>((size_t)ndir * 512);
+  }
+  p.wspk = b.take<__half>(2 * N * N);
+  p.whead = b.take<__half>(N * N);
+  p.wgate = b.take<__half>(d->kind == VATSS_KIND_DPTN_MASK ? N * N : 0);
+  if (out) *out = p;
+  return b.off;
+}
+
+// dst[i] = half(src[i] * (row < scaled_rows ? scale : 1))
+__global__ void k_to_half(const float* __restrict__ src, __half* __restrict__ dst, long long n, int cols,
+                          int scaled_rows, float scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float s = (i / cols) < scaled_rows ? scale : 1.f;
+    dst[i] = __float2half_rn(src[i] * s);
+  }
+}
+__global__ void k_scale_bias(const float* __restrict__ src, float* __restrict__ dst, int n, int scaled, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * (i < scaled ? scale : 1.f);
+}
+
+int to_half(const float* src, __half* dst, long long rows, int cols, int scaled_rows, float scale, cudaStream_t st) {
+  const long long n = rows * cols;
+  k_to_half<<<(int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>(src, dst, n, cols, scaled_rows, scale);
+  VATSS_LAUNCH_OK();
+  return 0;
+}
+
+// ---- workspace ----------------------------------------------------------------------------
+struct Work {
+  float *enc32, *vis, *xa32, *xb32, *y32, *ola32, *u32, *hT, *hG, *proj;
+  __half *xa16, *xb16, *qkv16, *att16, *rnn16, *ola16;
+};
+
+size_t carve_work(const vatss_model_desc* d, int B, int Tv, int L, int S, void* buf, Work* out) {
+  Bump b(buf);
+  const size_t N = d->N, H = d->H, tok = (size_t)B * S * d->C, fr = (size_t)B * L;
+  const bool dprnn = d->kind == VATSS_KIND_DPRNN, mask = d->kind == VATSS_KIND_DPTN_MASK;
+  Work w;
+  w.enc32 = b.take<float>(fr * N);
+  w.vis = b.take<float>(d->kind == VATSS_KIND_DPTN_AV ? (size_t)B * Tv * N : 0);
+  w.xa32 = b.take<float>(tok * N);
+  w.xb32 = b.take<float>(tok * N);
+  w.xa16 = b.take<__half>(tok * N);
+  w.xb16 = b.take<__half>(tok * N);
+  w.qkv16 = b.take<__half>(dprnn ? 0 : tok * 3 * N);
+  w.att16 = b.take<__half>(dprnn ? 0 : tok * N);
+  w.rnn16 = b.take<__half>(tok * 2 * H);
+  w.y32 = b.take<float>(tok * 2 * N);
+  w.ola32 = b.take<float>(fr * 2 * N);
+  w.ola16 = b.take<__half>(fr * 2 * N);
+  w.u32 = b.take<float>(fr * N);
+  w.hT = b.take<float>(mask ? fr * N : 0);
+  w.hG = b.take<float>(mask ? fr * N : 0);
+  w.proj = b.take<float>(fr * d->K);
+  if (out) *out = w;
+  return b.off;
+}
+
+}  // namespace
+
+bool tensor_engine_supports(const vatss_model_desc* d) {
+  if (d->H != 128) return false;
+  if (d->N != 128 && d->N != 64) return false;
+  if (d->kind != VATSS_KIND_DPRNN) {
+    const int hd = d->N / d->heads;
+    if (d->N % d->heads != 0 || (hd != 16 && hd != 32)) return false;
+  }
+  if (d->num_blocks > 32) return false;
+  return true;
+}
+
+size_t tensor_engine_packed_bytes(const vatss_model_desc* d) { return carve_packed(d, nullptr, nullptr); }
+
+size_t tensor_engine_workspace_bytes(const vatss_model_desc* d, int B, int T, int Tv, int L, int S) {
+  (void)T;
+  return carve_work(d, B, Tv, L, S, nullptr, nullptr);
+}
+
+int tensor_engine_pack(const vatss_model_desc* d, const float* const* params, void* packed, cudaStream_t st) {
+  Packed p;
+  carve_packed(d, packed, &p);
+  const int N = d->N, H = d->H;
+  const bool dprnn = d->kind == VATSS_KIND_DPRNN;
+  int rc;
+  for (int blk = 0; blk < d->num_blocks; ++blk)
+    for (int path = 0; path < 2; ++path) {
+      const int ndir = (path == 0 || d->bidir) ? 2 : 1;
+      SubPacked& s = p.sub[2 * blk + path];
+      auto sp = [&](int slot) { return sub_param(params, blk, path, slot); };
+      if (!dprnn) {
+        const float qscale = 1.4426950408889634f / sqrtf((float)(N / d->heads));
+        if ((rc = to_half(sp(VATSS_S_INPROJ_W), s.win, 3 * N, N, N, qscale, st))) return rc;
+        k_scale_bias<<<(3 * N + 255) / 256, 256, 0, st>>>(sp(VATSS_S_INPROJ_B), s.bin, 3 * N, N, qscale);
+        VATSS_LAUNCH_OK();
+        if ((rc = to_half(sp(VATSS_S_OUTPROJ_W), s.wout, N, N, 0, 1.f, st))) return rc;
+      }
+      if ((rc = to_half(sp(VATSS_S_FFN_W), s.wffn, N, ndir * H, 0, 1.f, st))) return rc;
+      for (int dir = 0; dir < ndir; ++dir) {
+        const int o = dir ? (VATSS_S_WIH_R - VATSS_S_WIH) : 0;
+        if ((rc = launch_pack_lstm(sp(VATSS_S_WIH + o), sp(VATSS_S_WHH + o), sp(VATSS_S_BIH + o), sp(VATSS_S_BHH + o),
+                                   N, dir, s.wlstm, s.blstm, st)))
+          return rc;
+      }
+    }
+  if ((rc = to_half(params[VATSS_P_SPK_W], p.wspk, 2 * N, N, 0, 1.f, st))) return rc;
+  if ((rc = to_half(params[VATSS_P_HEAD_W], p.whead, N, N, 0, 1.f, st))) return rc;
+  if (d->kind == VATSS_KIND_DPTN_MASK)
+    if ((rc = to_half(params[VATSS_P_HGATE_W], p.wgate, N, N, 0, 1.f, st))) return rc;
+  return 0;
+}
+
+int tensor_engine_forward(const vatss_model_desc* d, const float* const* params, const void* packed,
+                          const float* mix, const float* emb1, const float* emb2, int B, int T, int Tv, int L,
+                          int S, float* s1_pred, float* s2_pred, void* workspace, cudaStream_t st) {
+  Packed p;
+  carve_packed(d, const_cast<void*>(packed), &p);
+  Work w;
+  carve_work(d, B, Tv, L, S, workspace, &w);
+  const int N = d->N, H = d->H, C = d->C;
+  const long long tok = (long long)B * S * C, fr = (long long)B * L;
+  const bool dprnn = d->kind == VATSS_KIND_DPRNN, av = d->kind == VATSS_KIND_DPTN_AV;
+  int rc;
+  {
+    StageScope sc(ST_FRONTEND, st);
+    if (av) {
+      VATSS_CHECK_ARG(emb1 && emb2 && Tv > 0, "DPTN-AV needs both lip-embedding streams (Tv=%d)", Tv);
+      if ((rc = launch_visual_compress(emb1, emb2, params[VATSS_P_VIS_W], params[VATSS_P_VIS_B], B, d->E, Tv, N, w.vis,
+                                       st)))
+        return rc;
+    }
+    if ((rc = launch_encoder(mix, params[VATSS_P_ENCODER_W], av ? w.vis : nullptr, params[VATSS_P_GATE],
+                             params[VATSS_P_VLN_W], params[VATSS_P_VLN_B], B, T, Tv, N, d->K, L, S, C, d->P, w.enc32,
+                             w.xa32, w.xa16, st)))
+      return rc;
+  }
+  for (int blk = 0; blk < d->num_blocks; ++blk)
+    for (int path = 0; path < 2; ++path) {
+      const int ndir = (path == 0 || d->bidir) ? 2 : 1;
+      const SubPacked& s = p.sub[2 * blk + path];
+      auto sp = [&](int slot) { return sub_param(params, blk, path, slot); };
+      const SeqMap map = path == 0 ? intra_map(B, S, C) : inter_map(B, S, C);
+      const bool last = (blk == d->num_blocks - 1) && path == 1;
+      if (dprnn) {
+        {
+          StageScope sc(ST_LSTM_RECURRENT, st);
+          if ((rc = launch_tc_lstm(w.xa16, s.wlstm, s.blstm, w.rnn16, path, B, S, C, N, ndir, 0, st))) return rc;
+        }
+        StageScope sc(ST_FFN_LN, st);
+        if ((rc = launch_tc_gemm(TC_EPI_LN_POST, w.rnn16, ndir * H, s.wffn, sp(VATSS_S_FFN_B), w.xa32, N,
+                                 sp(VATSS_S_LN2_W), sp(VATSS_S_LN2_B), w.xb32, N, w.xb16, N, last ? 2 : 0,
+                                 params[VATSS_P_PRELU], tok, N, ndir * H, st)))
+          return rc;
+        float* t32 = w.xa32; w.xa32 = w.xb32; w.xb32 = t32;
+        __half* t16 = w.xa16; w.xa16 = w.xb16; w.xb16 = t16;
+      } else {
+        {
+          StageScope sc(ST_QKV, st);
+          if ((rc = launch_tc_gemm(TC_EPI_F16, w.xa16, N, s.win, s.bin, nullptr, 0, nullptr, nullptr, nullptr, 0,
+                                   w.qkv16, 3 * N, 0, nullptr, tok, 3 * N, N, st)))
+            return rc;
+        }
+        {
+          StageScope sc(ST_ATTENTION, st);
+          if ((rc = launch_attention_f16(w.qkv16, w.att16, map, N, d->heads, st))) return rc;
+        }
+        {
+          StageScope sc(ST_OUTPROJ_LN, st);
+          if ((rc = launch_tc_gemm(TC_EPI_LN, w.att16, N, s.wout, sp(VATSS_S_OUTPROJ_B), w.xa32, N, sp(VATSS_S_LN1_W),
+                                   sp(VATSS_S_LN1_B), w.xb32, N, w.xb16, N, 0, nullptr, tok, N, N, st)))
+            return rc;
+        }
+        {
+          StageScope sc(ST_LSTM_RECURRENT, st);
+          if ((rc = launch_tc_lstm(w.xb16, s.wlstm, s.blstm, w.rnn16, path, B, S, C, N, ndir, 1, st))) return rc;
+        }
+        StageScope sc(ST_FFN_LN, st);
+        if ((rc = launch_tc_gemm(TC_EPI_LN, w.rnn16, ndir * H, s.wffn, sp(VATSS_S_FFN_B), w.xb32, N, sp(VATSS_S_LN2_W),
+                                 sp(VATSS_S_LN2_B), w.xa32, N, w.xa16, N, last ? 2 : 0, params[VATSS_P_PRELU], tok, N,
+                                 ndir * H, st)))
+          return rc;
+      }
+    }
+  // tail: (PReLU already applied to the fp16 copy) speaker split -> overlap-add -> head -> decoder
+  StageScope sc(ST_TAIL, st);
+  if (d->num_blocks == 0) {
+    set_error("tensor engine needs at least one dual-path block");
+    return -1;
+  }
+  if ((rc = launch_tc_gemm(TC_EPI_F32, w.xa16, N, p.wspk, params[VATSS_P_SPK_B], nullptr, 0, nullptr, nullptr, w.y32,
+                           2 * N, nullptr, 0, 0, nullptr, tok, 2 * N, N, st)))
+    return rc;
+  if ((rc = launch_ola_token_major(w.y32, B, S, C, d->P, L, 2 * N, w.ola32, w.ola16, st))) return rc;
+  float* preds[2] = {s1_pred, s2_pred};
+  for (int j = 0; j < 2; ++j) {
+    if (d->kind == VATSS_KIND_DPTN_MASK) {
+      if ((rc = launch_tc_gemm(TC_EPI_F32, w.ola16 + j * N, 2 * N, p.whead, params[VATSS_P_HEAD_B], nullptr, 0, nullptr,
+                               nullptr, w.hT, N, nullptr, 0, 0, nullptr, fr, N, N, st)))
+        return rc;
+      if ((rc = launch_tc_gemm(TC_EPI_F32, w.ola16 + j * N, 2 * N, p.wgate, params[VATSS_P_HGATE_B], nullptr, 0, nullptr,
+                               nullptr, w.hG, N, nullptr, 0, 0, nullptr, fr, N, N, st)))
+        return rc;
+      if ((rc = launch_mask_combine(w.hT, w.hG, w.enc32, w.u32, fr * N, st))) return rc;
+    } else {
+      if ((rc = launch_tc_gemm(TC_EPI_F32, w.ola16 + j * N, 2 * N, p.whead, params[VATSS_P_HEAD_B], w.enc32, N, nullptr,
+                               nullptr, w.u32, N, nullptr, 0, 0, nullptr, fr, N, N, st)))
+        return rc;
+    }
+    if ((rc = launch_decoder(w.u32, params[VATSS_P_DECODER_W], B, L, N, d->K, T, w.proj, preds[j], st))) return rc;
+  }
+  return 0;
 }
 
 }  // namespace vatss

@@ -179,6 +179,11 @@ int vatss_tc_lstm(const void* x16, const float* const* lstm_params /* [8]: Wih,W
                   void* out16, int mode, int B, int S, int C, int N, int ndir, int act, void* wpack,
                   float* bias_pack, void* stream);
 
+/* vatss_tc_attention: softmax(q k^T) v per (sequence, head) on packed fp16 qkv (B*S*C, 3N) whose q part is
+ * pre-scaled by log2(e)/sqrt(hd); out16 (B*S*C, N).  mode 0 intra / 1 inter; force_simt=1 runs the SIMT fallback. */
+int vatss_tc_attention(const void* qkv16, void* out16, int mode, int B, int S, int C, int N, int heads, int force_simt,
+                       void* stream);
+
 /* Instrumentation (no reference counterpart; used by bench.py).
  * vatss_launch_count: number of kernels this library has launched in this process.
  * vatss_profile_begin: start recording CUDA-event pairs around the stages of subsequent calls

@@ -396,6 +396,14 @@ int vatss_tc_lstm(const void* x16, const float* const* lp, void* out16, int mode
                         act, st);
 }
 
+int vatss_tc_attention(const void* qkv16, void* out16, int mode, int B, int S, int C, int N, int heads, int force_simt,
+                       void* stream) {
+  VATSS_CHECK_ARG(qkv16 && out16 && heads > 0, "tc_attention: bad argument");
+  const SeqMap map = mode == 0 ? intra_map(B, S, C) : inter_map(B, S, C);
+  return launch_attention_f16((const __half*)qkv16, (__half*)out16, map, mode, B, S, C, N, heads, force_simt,
+                              (cudaStream_t)stream);
+}
+
 unsigned long long vatss_launch_count(void) { return g_launches.load(); }
 
 int vatss_profile_begin(void) {

@@ -30,6 +30,8 @@ int launch_pack_lstm(const float* Wih, const float* Whh, const float* bih, const
                      __half* Wpack, float* bias_pack, cudaStream_t st);
 
 // attention core on fp16 packed qkv (tokens, 3N) -> out16 (tokens, N); q is pre-scaled by log2(e)/sqrt(hd)
-int launch_attention_f16(const __half* qkv, __half* out, SeqMap map, int N, int heads, cudaStream_t st);
+// mode 0 intra / 1 inter (map must be intra_map / inter_map of (B,S,C)); force_simt selects the SIMT fallback
+int launch_attention_f16(const __half* qkv, __half* out, SeqMap map, int mode, int B, int S, int C, int N, int heads,
+                         int force_simt, cudaStream_t st);
 
 }  // namespace vatss

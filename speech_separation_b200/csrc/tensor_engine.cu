@@ -220,7 +220,7 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
         }
         {
           StageScope sc(ST_ATTENTION, st);
-          if ((rc = launch_attention_f16(w.qkv16, w.att16, map, N, d->heads, st))) return rc;
+          if ((rc = launch_attention_f16(w.qkv16, w.att16, map, path, B, S, C, N, d->heads, 0, st))) return rc;
         }
         {
           StageScope sc(ST_OUTPROJ_LN, st);

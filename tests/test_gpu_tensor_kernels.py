@@ -137,3 +137,46 @@ def test_tc_lstm_matches_torch(lib, mode, B, S, C, N, ndir, act):
     err = (got - ref).norm() / ref.norm()
     print(f"tc_lstm mode={mode} B={B} S={S} C={C} N={N} ndir={ndir}: rel err {err:.3e}, max abs {(got - ref).abs().max():.3e}")
     assert err < 3e-3  # fp16 h feedback + fp16 output + tanh.approx
+
+
+ATT_CASES = [
+    # mode, B, S, C, N, heads
+    (0, 1, 2, 150, 128, 4),      # intra, production chunk, single kv block
+    (0, 2, 5, 150, 128, 4),
+    (1, 2, 141, 6, 128, 4),      # inter 2 s: len 141 (two query tiles, one kv block)
+    (1, 1, 283, 4, 128, 4),      # inter 4 s: len 283 -> two kv blocks of 144 (two-pass softmax)
+    (0, 3, 4, 40, 128, 4),       # short sequences
+    (0, 2, 3, 150, 64, 4),       # N = 64: head dim 16, one group of four heads
+    (1, 2, 283, 3, 64, 4),
+    (0, 1, 2, 250, 128, 4),      # longer chunk: two kv blocks of 128
+]
+
+
+@pytest.mark.parametrize("force_simt", [0, 1])
+@pytest.mark.parametrize("mode,B,S,C,N,heads", ATT_CASES)
+def test_tc_attention_matches_torch(lib, mode, B, S, C, N, heads, force_simt):
+    from speech_separation_b200 import _lib
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(7 * mode + B + S + C + N)
+    hd = N // heads
+    qkv = torch.randn(B, S, C, 3 * N)
+    qkv[..., :N] *= 1.4426950408889634 / hd ** 0.5 * 2.0  # pre-scaled q (x2 for a peakier softmax)
+    qkv = qkv.half()
+    x = qkv.float().to(dev)
+    seq = x.reshape(B * S, C, 3 * N) if mode == 0 else x.permute(0, 2, 1, 3).reshape(B * C, S, 3 * N)
+    G, Ls = seq.shape[0], seq.shape[1]
+    q, k, v = (seq[..., i * N:(i + 1) * N].reshape(G, Ls, heads, hd).transpose(1, 2) for i in range(3))
+    p = torch.softmax((q @ k.transpose(-1, -2)) * 0.6931471805599453, dim=-1)  # exp2 scores
+    ref = (p @ v).transpose(1, 2).reshape(G, Ls, N)
+    ref = ref.reshape(B, S, C, N) if mode == 0 else ref.reshape(B, C, S, N).permute(0, 2, 1, 3)
+    qd = qkv.to(dev).contiguous()
+    out = torch.full((B * S * C, N), float("nan"), dtype=torch.float16, device=dev)
+    rc = lib.vatss_tc_attention(_p(qd), _p(out), mode, B, S, C, N, heads, force_simt, None)
+    _lib.check(rc, "vatss_tc_attention")
+    torch.cuda.synchronize()
+    got = out.float().reshape(B, S, C, N)
+    assert torch.isfinite(got).all()
+    err = ((got - ref).norm() / ref.norm()).item()
+    print(f"attention simt={force_simt} mode={mode} B={B} S={S} C={C} N={N}: rel err {err:.3e}")
+    assert err < 2e-3

@@ -190,7 +190,7 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
         }
       };
       // step 0: x-part only (h_{-1} = 0)
-      mbar_wait_cluster(bar_xfull, 0);
+      mbar_wait(bar_xfull, 0);
       tc_fence_after();
       for (int c = 0; c < LSTM_CHUNKS; ++c) {
         issue_x(c, 0);
@@ -199,22 +199,22 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
       umma_commit_cg2(bar_xempty, 3);
       for (int step = 1; step < len; ++step) {
         const int s = step & 1;
-        mbar_wait_cluster(bar_xfull + 8 * s, (step >> 1) & 1);
+        mbar_wait(bar_xfull + 8 * s, (step >> 1) & 1);
         tc_fence_after();
         // x-part of this step for chunks 0..2 as soon as the gate warps have drained them (step-1)
         for (int c = 0; c < LSTM_CHUNKS - 1; ++c) {
-          mbar_wait_cluster(bar_accempty + 8 * c, (step - 1) & 1);
+          mbar_wait(bar_accempty + 8 * c, (step - 1) & 1);
           tc_fence_after();
           issue_x(c, s);
         }
         // h_{step-1} complete in both CTAs
-        mbar_wait_cluster(bar_hfull, (step - 1) & 1);
+        mbar_wait(bar_hfull, (step - 1) & 1);
         tc_fence_after();
         for (int c = 0; c < LSTM_CHUNKS - 1; ++c) {
           issue_h(c);
           umma_commit_cg2(bar_accfull + 8 * c, 3);
         }
-        mbar_wait_cluster(bar_accempty + 8 * (LSTM_CHUNKS - 1), (step - 1) & 1);
+        mbar_wait(bar_accempty + 8 * (LSTM_CHUNKS - 1), (step - 1) & 1);
         tc_fence_after();
         issue_x(LSTM_CHUNKS - 1, s);
         umma_commit_cg2(bar_xempty + 8 * s, 3);
@@ -273,7 +273,7 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
         tc_fence_before();
         __syncwarp();
         if (lane == 0)
-          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(accempty_leader[c]) : "memory");
+          asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(accempty_leader[c]) : "memory");
         const float* bc = sBias + c * 128 + half * 16;
         float hv[16];
 #pragma unroll
@@ -317,7 +317,7 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
         fence_proxy_async();
         __syncwarp();
         if (lane == 0)
-          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(hfull_leader) : "memory");
+          asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(hfull_leader) : "memory");
       }
     }
   }

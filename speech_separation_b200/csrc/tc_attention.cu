@@ -96,16 +96,18 @@ struct TcAttnArgs {
   int len;        // tokens per sequence
   int N;          // features (row of qkv is 3N halfs)
   int groups;     // 64-feature head groups per sequence (N / 64)
-  int nblk, NB;   // kv blocks per sequence and rows per block (NB % 16 == 0, NB <= 224)
+  int nblk;       // 64-row kv blocks per sequence
   int mtiles;     // 128-query tiles per sequence
-  int pkb;        // 64-column k-blocks of the P tile (ceil(NB / 64))
   int num_items;  // sequences * groups
   SeqMap map;
   __half* out;    // (tokens, N)
 };
 
 constexpr int ATT_THREADS = 320;
-constexpr uint32_t ATT_S_COLS = 224;   // S slot (<= 224 columns) then O (<= 32 columns) per warpgroup
+constexpr int ATT_NB = 64;             // kv rows per block = one SWIZZLE_128B k-block of the P tile
+constexpr int ATT_RING = 3;            // S slots per warpgroup in TMEM
+constexpr uint32_t ATT_WG_COLS = 256;  // TMEM columns per warpgroup: 3 x 64 (S ring) + 32 (O) + 16 (row sums)
+constexpr uint32_t ATT_O_COL = 192, ATT_SUM_COL = 224;
 
 // MN-major (N contiguous) B operand with 128-byte rows, SWIZZLE_128B: 8-row (K) groups 1024 B apart
 __device__ __forceinline__ uint64_t smem_desc_sw128_mnmajor(uint32_t smem_addr) {
@@ -118,11 +120,20 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_mnmajor(uint32_t smem_addr) 
   return d;
 }
 
-__device__ __forceinline__ float ex2_fast(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+// p = 2^(a), 2^(b) as packed fp16 (one MUFU op for the pair)
+__device__ __forceinline__ uint32_t ex2_f16x2(float a, float b) {
+  uint32_t packed, y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(packed) : "f"(b), "f"(a));   // low half = a, high half = b
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(packed));
   return y;
 }
+
+struct AttBars {
+  uint32_t kfull, kfree, vfull, vfree, qfull, qfree;   // qfull/qfree: [2]
+  uint32_t sfull, sfree;                               // [2 wg][3 slots]
+  uint32_t pfull, pfree;                               // [2 wg][2 buffers]
+  uint32_t ofull, ofree;                               // [2 wg]
+};
 
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -132,34 +143,37 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t base = smem_u32(smem);
   if ((base & 1023u) != 0) __trap();
-  const int kvrows = p.nblk * p.NB;
-  const uint32_t KV_BYTES = (uint32_t)kvrows * 128u;
-  const uint32_t P_BYTES = (uint32_t)p.pkb * 16384u;
+  const uint32_t KV_BYTES = (uint32_t)p.nblk * ATT_NB * 128u;
   const uint32_t sQ = base;                        // [2][128 x 128 B]
-  const uint32_t sK = sQ + 2 * 16384;
+  const uint32_t sP = sQ + 2 * 16384;              // [2 wg][2][128 x 128 B]
+  const uint32_t sOnes = sP + 4 * 16384;           // [64 x 128 B] of fp16 1.0 (B operand of the row-sum MMA)
+  const uint32_t sK = sOnes + 8192;
   const uint32_t sV = sK + KV_BYTES;
-  const uint32_t sP = sV + KV_BYTES;               // [2 warpgroups]
-  const uint32_t bars = sP + 2 * P_BYTES;
-  const uint32_t bar_kfull = bars, bar_kfree = bars + 8, bar_vfull = bars + 16, bar_vfree = bars + 24;
-  const uint32_t bar_qfull = bars + 32, bar_qfree = bars + 48;       // [2]
-  const uint32_t bar_sfull = bars + 64, bar_sfree = bars + 80;       // [2 warpgroups]
-  const uint32_t bar_pfull = bars + 96, bar_pfree = bars + 112;
-  const uint32_t bar_ofull = bars + 128, bar_ofree = bars + 144;
-  const uint32_t tmem_slot = bars + 160;
+  const uint32_t bars = sV + KV_BYTES;
+  AttBars B;
+  B.kfull = bars; B.kfree = bars + 8; B.vfull = bars + 16; B.vfree = bars + 24;
+  B.qfull = bars + 32; B.qfree = bars + 48;
+  B.sfull = bars + 64; B.sfree = bars + 112;      // 6 each
+  B.pfull = bars + 160; B.pfree = bars + 192;     // 4 each
+  B.ofull = bars + 224; B.ofree = bars + 240;     // 2 each
+  const uint32_t tmem_slot = bars + 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool resident = p.nblk <= ATT_RING;        // all S blocks of a (tile, head) fit the ring: single S pass
+  const int jobs_per_head = resident ? p.nblk : 2 * p.nblk;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_kfull, 1); mbar_init(bar_kfree, 1); mbar_init(bar_vfull, 1); mbar_init(bar_vfree, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_qfull + 8 * i, 1); mbar_init(bar_qfree + 8 * i, 1);
-      mbar_init(bar_sfull + 8 * i, 1); mbar_init(bar_sfree + 8 * i, 128);
-      mbar_init(bar_pfull + 8 * i, 128); mbar_init(bar_pfree + 8 * i, 1);
-      mbar_init(bar_ofull + 8 * i, 1); mbar_init(bar_ofree + 8 * i, 128);
-    }
+    mbar_init(B.kfull, 1); mbar_init(B.kfree, 1); mbar_init(B.vfull, 1); mbar_init(B.vfree, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(B.qfull + 8 * i, 1); mbar_init(B.qfree + 8 * i, 1); }
+    for (int i = 0; i < 6; ++i) { mbar_init(B.sfull + 8 * i, 1); mbar_init(B.sfree + 8 * i, 128); }
+    for (int i = 0; i < 4; ++i) { mbar_init(B.pfull + 8 * i, 128); mbar_init(B.pfree + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(B.ofull + 8 * i, 1); mbar_init(B.ofree + 8 * i, 128); }
     fence_mbar_init();
     prefetch_tmap(&tmapQ);
     prefetch_tmap(&tmapKV);
   }
+  for (int i = threadIdx.x; i < 8192 / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem + (sOnes - base))[i] = 0x3C003C00u;
+  fence_proxy_async();
   if (warp == 1) {
     tmem_alloc<1>(tmem_slot, 512);
     tmem_relinquish<1>();
@@ -176,25 +190,27 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
         const int g = item / p.groups, grp = item - g * p.groups;
         const int colq = grp * 64, colk = p.N + grp * 64, colv = 2 * p.N + grp * 64;
-        int cb = 0, ck = 0;         // inter: utterance and chunk position of the sequence
-        long long row0 = 0;         // intra: first token row
+        int cb = 0, ck = 0;
+        long long row0 = 0;
         if (p.mode == 0) row0 = (long long)g * p.len;
         else { cb = g / p.map.J; ck = g - cb * p.map.J; }
         auto load_rows = [&](const CUtensorMap* tm, uint32_t dst, uint32_t bar, int col, int r0) {
           if (p.mode == 0) tma_load_2d(dst, tm, bar, col, (int)(row0 + r0));
           else tma_load_4d(dst, tm, bar, col, ck, r0, cb);
         };
-        mbar_wait(bar_kfree, (it & 1) ^ 1);
-        mbar_expect_tx(bar_kfull, KV_BYTES);
-        for (int j = 0; j < p.nblk; ++j) load_rows(&tmapKV, sK + j * p.NB * 128, bar_kfull, colk, j * p.NB);
-        mbar_wait(bar_vfree, (it & 1) ^ 1);
-        mbar_expect_tx(bar_vfull, KV_BYTES);
-        for (int j = 0; j < p.nblk; ++j) load_rows(&tmapKV, sV + j * p.NB * 128, bar_vfull, colv, j * p.NB);
+        mbar_wait(B.kfree, (it & 1) ^ 1);
+        mbar_expect_tx(B.kfull, KV_BYTES);
+        for (int j = 0; j < p.nblk; ++j) load_rows(&tmapKV, sK + j * ATT_NB * 128, B.kfull, colk, j * ATT_NB);
         for (int m = 0; m < p.mtiles; ++m, ++qn) {
           const int s = qn & 1;
-          mbar_wait(bar_qfree + 8 * s, ((qn >> 1) & 1) ^ 1);
-          mbar_expect_tx(bar_qfull + 8 * s, 16384);
-          load_rows(&tmapQ, sQ + s * 16384, bar_qfull + 8 * s, colq, m * 128);
+          mbar_wait(B.qfree + 8 * s, ((qn >> 1) & 1) ^ 1);
+          mbar_expect_tx(B.qfull + 8 * s, 16384);
+          load_rows(&tmapQ, sQ + s * 16384, B.qfull + 8 * s, colq, m * 128);
+          if (m == 0) {
+            mbar_wait(B.vfree, (it & 1) ^ 1);
+            mbar_expect_tx(B.vfull, KV_BYTES);
+            for (int j = 0; j < p.nblk; ++j) load_rows(&tmapKV, sV + j * ATT_NB * 128, B.vfull, colv, j * ATT_NB);
+          }
         }
       }
     }
@@ -202,68 +218,85 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_s = idesc_f16(128, p.NB, 0);
-      const uint32_t idesc_o = idesc_f16(128, HD, 0) | (1u << 16);   // B (= V) is MN-major
+      const uint32_t idesc_s = idesc_f16(128, ATT_NB, 0);
+      const uint32_t idesc_o = idesc_f16(128, HD, 0) | (1u << 16);     // B (= V) is MN-major
+      const uint32_t idesc_1 = idesc_f16(128, 16, 0) | (1u << 16);     // row sums: P x ones
+      uint32_t kjob = 0;      // S jobs issued (same sequence for both warpgroups)
+      uint32_t pjob = 0;      // exp jobs whose P V has been issued
+      uint32_t ohead = 0;     // (tile, head) accumulators started
       int it = 0, qn = 0;
-      uint32_t n_s[2] = {0, 0}, n_p[2] = {0, 0}, n_o[2] = {0, 0};   // barrier use counters per warpgroup
+      // software pipeline: the P V of job k-1 is issued after the S of job k
+      struct { bool valid; int j, hsel_hh, it; bool last_of_item; } pend = {false, 0, 0, 0, false};
+      auto issue_pv = [&]() {
+        if (!pend.valid) return;
+        for (int w = 0; w < 2; ++w) {
+          const int hsel = w * HPW + pend.hsel_hh;
+          const uint32_t pb = pjob & 1;
+          if (pend.j == 0) mbar_wait(B.ofree + 8 * w, (ohead & 1) ^ 1);   // previous O of this warpgroup read out
+          mbar_wait(B.pfull + 8 * (w * 2 + pb), (pjob >> 1) & 1);
+          tc_fence_after();
+          const uint32_t d_o = tmem + w * ATT_WG_COLS + ATT_O_COL, d_s = tmem + w * ATT_WG_COLS + ATT_SUM_COL;
+#pragma unroll
+          for (int k16 = 0; k16 < ATT_NB / 16; ++k16) {
+            const uint64_t a = smem_desc_sw128_kmajor(sP + (w * 2 + pb) * 16384) + (uint64_t)(k16 * 2);
+            const uint64_t bv = smem_desc_sw128_mnmajor(sV + (pend.j * ATT_NB + k16 * 16) * 128 + hsel * HD * 2);
+            const uint64_t b1 = smem_desc_sw128_mnmajor(sOnes + k16 * 16 * 128);
+            const uint32_t acc = (pend.j > 0 || k16 > 0) ? 1u : 0u;
+            umma_f16<1>(d_o, a, bv, idesc_o, acc);
+            umma_f16<1>(d_s, a, b1, idesc_1, acc);
+          }
+          umma_commit(B.pfree + 8 * (w * 2 + pb));
+          if (pend.j == p.nblk - 1) umma_commit(B.ofull + 8 * w);
+        }
+        ++pjob;
+        if (pend.j == p.nblk - 1) ++ohead;
+        if (pend.last_of_item) umma_commit(B.vfree);
+        pend.valid = false;
+      };
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        mbar_wait(bar_kfull, it & 1);
+        mbar_wait(B.kfull, it & 1);
         bool v_ready = false;
         for (int m = 0; m < p.mtiles; ++m, ++qn) {
           const int s = qn & 1;
-          mbar_wait(bar_qfull + 8 * s, (qn >> 1) & 1);
+          mbar_wait(B.qfull + 8 * s, (qn >> 1) & 1);
           tc_fence_after();
           for (int hh = 0; hh < HPW; ++hh) {
-            const int npass = p.nblk > 1 ? 2 : 1;
-            for (int pass = 0; pass < npass; ++pass) {
-              const bool exp_pass = pass == npass - 1;
-              for (int j = 0; j < p.nblk; ++j) {
-                for (int w = 0; w < 2; ++w) {
-                  const int hsel = w * HPW + hh;   // head inside the 64-feature group
-                  mbar_wait(bar_sfree + 8 * w, (n_s[w] & 1) ^ 1);
-                  tc_fence_after();
+            for (int jj = 0; jj < jobs_per_head; ++jj, ++kjob) {
+              const int j = jj % p.nblk;
+              const bool exp_job = resident || jj >= p.nblk;
+              const uint32_t slot = kjob % ATT_RING, use = kjob / ATT_RING;
+              for (int w = 0; w < 2; ++w) {
+                const int hsel = w * HPW + hh;
+                mbar_wait(B.sfree + 8 * (w * 3 + slot), (use & 1) ^ 1);
+                tc_fence_after();
 #pragma unroll
-                  for (int k16 = 0; k16 < HD / 16; ++k16) {
-                    const uint32_t koff = (uint32_t)(hsel * HD * 2 + k16 * 32) >> 4;
-                    const uint64_t a = smem_desc_sw128_kmajor(sQ + s * 16384) + koff;
-                    const uint64_t b = smem_desc_sw128_kmajor(sK + j * p.NB * 128) + koff;
-                    umma_f16<1>(tmem + w * 256, a, b, idesc_s, k16 > 0 ? 1u : 0u);
-                  }
-                  umma_commit(bar_sfull + 8 * w);
-                  ++n_s[w];
-                  // last S MMA of the item: K may be refilled while the last softmax / P V still run
-                  if (w == 1 && exp_pass && j == p.nblk - 1 && hh == HPW - 1 && m == p.mtiles - 1)
-                    umma_commit(bar_kfree);
+                for (int k16 = 0; k16 < HD / 16; ++k16) {
+                  const uint32_t koff = (uint32_t)(hsel * HD * 2 + k16 * 32) >> 4;
+                  const uint64_t a = smem_desc_sw128_kmajor(sQ + s * 16384) + koff;
+                  const uint64_t b = smem_desc_sw128_kmajor(sK + j * ATT_NB * 128) + koff;
+                  umma_f16<1>(tmem + w * ATT_WG_COLS + slot * ATT_NB, a, b, idesc_s, k16 > 0 ? 1u : 0u);
                 }
-                if (exp_pass) {
-                  if (!v_ready) { mbar_wait(bar_vfull, it & 1); v_ready = true; }
-                  for (int w = 0; w < 2; ++w) {
-                    const int hsel = w * HPW + hh;
-                    if (j == 0) {   // first P V of this (m, head): the previous O must have been read out
-                      mbar_wait(bar_ofree + 8 * w, (n_o[w] & 1) ^ 1);
-                    }
-                    mbar_wait(bar_pfull + 8 * w, n_p[w] & 1);
-                    tc_fence_after();
-                    for (int k16 = 0; k16 < p.NB / 16; ++k16) {
-                      const uint64_t a = smem_desc_sw128_kmajor(sP + w * P_BYTES + (k16 >> 2) * 16384) + (uint64_t)((k16 & 3) * 2);
-                      const uint64_t b = smem_desc_sw128_mnmajor(sV + (j * p.NB + k16 * 16) * 128 + hsel * HD * 2);
-                      umma_f16<1>(tmem + w * 256 + ATT_S_COLS, a, b, idesc_o, (j > 0 || k16 > 0) ? 1u : 0u);
-                    }
-                    umma_commit(bar_pfree + 8 * w);
-                    ++n_p[w];
-                    if (j == p.nblk - 1) {
-                      umma_commit(bar_ofull + 8 * w);
-                      ++n_o[w];
-                    }
-                  }
-                }
+                umma_commit(B.sfull + 8 * (w * 3 + slot));
+              }
+              const bool last_s_of_tile = hh == HPW - 1 && jj == jobs_per_head - 1;
+              if (last_s_of_tile) umma_commit(B.qfree + 8 * s);
+              if (last_s_of_tile && m == p.mtiles - 1) umma_commit(B.kfree);
+              // P V of the previous job
+              if (pend.valid && !v_ready && pend.it == it) { mbar_wait(B.vfull, it & 1); v_ready = true; }
+              issue_pv();
+              if (exp_job) {
+                pend.valid = true; pend.j = j; pend.hsel_hh = hh; pend.it = it;
+                pend.last_of_item = last_s_of_tile && m == p.mtiles - 1;
               }
             }
           }
-          umma_commit(bar_qfree + 8 * s);    // every S MMA that reads this Q tile has been issued
         }
-        umma_commit(bar_vfree);              // ... and every P V MMA that reads V of this item
       }
+      if (pend.valid) {
+        const int last_it = it - 1;
+        if (pend.it == last_it) mbar_wait(B.vfull, last_it & 1);   // idempotent if already observed
+      }
+      issue_pv();
     }
     __syncwarp();
   } else {
@@ -271,85 +304,103 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
     const int w = (warp - 2) >> 2;               // warpgroup
     const int q = warp & 3;                      // TMEM lane quadrant of this warp
     const int r = q * 32 + lane;                 // query row inside the 128-row tile
-    const uint32_t t_s = tmem + ((uint32_t)(q * 32) << 16) + w * 256;
-    const uint32_t t_o = t_s + ATT_S_COLS;
-    const uint32_t sPw = sP + w * P_BYTES;
-    uint32_t n_s = 0, n_p = 0, n_o = 0;
+    const uint32_t t_base = tmem + ((uint32_t)(q * 32) << 16) + w * ATT_WG_COLS;
+    uint32_t kjob = 0, pjob = 0, ohead = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int g = item / p.groups, grp = item - g * p.groups;
       for (int m = 0; m < p.mtiles; ++m) {
         const int qi = m * 128 + r;
+        const bool warp_live = m * 128 + q * 32 < p.len;     // warp-uniform: any valid query row in this warp
         for (int hh = 0; hh < HPW; ++hh) {
           const int head = grp * HPT + w * HPW + hh;
-          float mx = -INFINITY, sum = 0.f;
-          const int npass = p.nblk > 1 ? 2 : 1;
-          for (int pass = 0; pass < npass; ++pass) {
-            const bool exp_pass = pass == npass - 1;
-            for (int j = 0; j < p.nblk; ++j) {
-              mbar_wait(bar_sfull + 8 * w, n_s & 1);
-              ++n_s;
-              tc_fence_after();
-              const int kv0 = j * p.NB;
-              if (!exp_pass || p.nblk == 1) {
-                // row maximum over the valid columns of this block
-                for (int c0 = 0; c0 < p.NB; c0 += 16) {
-                  uint32_t v[16];
-                  tmem_ld_32x32b_x16(t_s + c0, v);
-                  tmem_ld_wait();
+          float mx = -INFINITY;
+          // ---- row maximum
+          for (int j = 0; j < p.nblk; ++j) {
+            const uint32_t kk = kjob + j, slot = kk % ATT_RING, use = kk / ATT_RING;
+            mbar_wait(B.sfull + 8 * (w * 3 + slot), use & 1);
+            tc_fence_after();
+            if (warp_live) {
+              const int nv = min(ATT_NB, p.len - j * ATT_NB);
+              for (int c0 = 0; c0 < nv; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(t_base + slot * ATT_NB + c0, v);
+                tmem_ld_wait();
+                if (c0 + 16 <= nv) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                } else {
 #pragma unroll
                   for (int i = 0; i < 16; ++i)
-                    if (kv0 + c0 + i < p.len) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    if (c0 + i < nv) mx = fmaxf(mx, __uint_as_float(v[i]));
                 }
-              }
-              if (exp_pass) {
-                // the P tile of the previous block / head must have been consumed by its P V MMAs
-                mbar_wait(bar_pfree + 8 * w, (n_p & 1) ^ 1);
-                for (int c0 = 0; c0 < p.NB; c0 += 16) {
-                  uint32_t v[16];
-                  tmem_ld_32x32b_x16(t_s + c0, v);
-                  tmem_ld_wait();
-                  uint32_t pk[8];
-#pragma unroll
-                  for (int i = 0; i < 16; i += 2) {
-                    const float e0 = (kv0 + c0 + i < p.len) ? ex2_fast(__uint_as_float(v[i]) - mx) : 0.f;
-                    const float e1 = (kv0 + c0 + i + 1 < p.len) ? ex2_fast(__uint_as_float(v[i + 1]) - mx) : 0.f;
-                    const __half2 h2 = __floats2half2_rn(e0, e1);
-                    // accumulate the ROUNDED probabilities so that numerator and denominator agree
-                    const float2 f2 = __half22float2(h2);
-                    sum += f2.x + f2.y;
-                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-                  }
-                  const uint32_t kb = (uint32_t)c0 >> 6, ch = ((uint32_t)c0 & 63u) >> 3;
-                  const uint32_t a0 = sPw + kb * 16384 + sw128_offset((uint32_t)r, ch);
-                  const uint32_t a1 = sPw + kb * 16384 + sw128_offset((uint32_t)r, ch + 1);
-                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
-                               "r"(pk[3]) : "memory");
-                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]),
-                               "r"(pk[7]) : "memory");
-                }
-              }
-              // S slot drained
-              tc_fence_before();
-              mbar_arrive(bar_sfree + 8 * w);
-              if (exp_pass) {
-                fence_proxy_async();
-                mbar_arrive(bar_pfull + 8 * w);
-                ++n_p;
               }
             }
+            if (!resident) {   // the ring slot is recycled for the exp pass
+              tc_fence_before();
+              mbar_arrive(B.sfree + 8 * (w * 3 + slot));
+            }
           }
-          // O = sum_j P_j V_j complete
-          mbar_wait(bar_ofull + 8 * w, n_o & 1);
-          ++n_o;
+          if (!resident) kjob += p.nblk;
+          // ---- probabilities -> P tiles (fp16, K-major SWIZZLE_128B), consumed by the P V MMAs
+          for (int j = 0; j < p.nblk; ++j, ++kjob, ++pjob) {
+            const uint32_t slot = kjob % ATT_RING, use = kjob / ATT_RING, pb = pjob & 1;
+            if (!resident) {
+              mbar_wait(B.sfull + 8 * (w * 3 + slot), use & 1);
+              tc_fence_after();
+            }
+            mbar_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
+            if (warp_live) {
+              const int nv = min(ATT_NB, p.len - j * ATT_NB);
+              const uint32_t sPw = sP + (w * 2 + pb) * 16384;
+#pragma unroll 1
+              for (int c0 = 0; c0 < ATT_NB; c0 += 16) {
+                uint32_t pk[8];
+                if (c0 < nv) {
+                  uint32_t v[16];
+                  tmem_ld_32x32b_x16(t_base + slot * ATT_NB + c0, v);
+                  tmem_ld_wait();
+                  if (c0 + 16 <= nv) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                      pk[i] = ex2_f16x2(__uint_as_float(v[2 * i]) - mx, __uint_as_float(v[2 * i + 1]) - mx);
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                      const float a = (c0 + 2 * i < nv) ? __uint_as_float(v[2 * i]) - mx : -60000.f;
+                      const float b = (c0 + 2 * i + 1 < nv) ? __uint_as_float(v[2 * i + 1]) - mx : -60000.f;
+                      pk[i] = ex2_f16x2(a, b);   // 2^-60000 flushes to +0
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) pk[i] = 0u;
+                }
+                const uint32_t ch = (uint32_t)c0 >> 3;
+                const uint32_t a0 = sPw + sw128_offset((uint32_t)r, ch), a1 = sPw + sw128_offset((uint32_t)r, ch + 1);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                             "r"(pk[3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]),
+                             "r"(pk[7]) : "memory");
+              }
+            }
+            tc_fence_before();
+            mbar_arrive(B.sfree + 8 * (w * 3 + slot));
+            fence_proxy_async();
+            mbar_arrive(B.pfull + 8 * (w * 2 + pb));
+          }
+          // ---- O = sum_j P_j V_j and the row sums (P x ones) complete
+          mbar_wait(B.ofull + 8 * w, ohead & 1);
+          ++ohead;
           tc_fence_after();
-          uint32_t o[HD];
-          if constexpr (HD == 32) tmem_ld_32x32b_x32(t_o, o);
-          else tmem_ld_32x32b_x16(t_o, o);
+          uint32_t o[HD], sm[16];
+          if constexpr (HD == 32) tmem_ld_32x32b_x32(t_base + ATT_O_COL, o);
+          else tmem_ld_32x32b_x16(t_base + ATT_O_COL, o);
+          tmem_ld_32x32b_x16(t_base + ATT_SUM_COL, sm);
           tmem_ld_wait();
           tc_fence_before();
-          mbar_arrive(bar_ofree + 8 * w);
+          mbar_arrive(B.ofree + 8 * w);
           if (qi < p.len) {
-            const float inv = 1.f / sum;
+            const float inv = 1.f / __uint_as_float(sm[0]);
             uint4* dst = reinterpret_cast<uint4*>(p.out + p.map.row(g, qi) * p.N + head * HD);
 #pragma unroll
             for (int c = 0; c < HD / 8; ++c) {
@@ -378,33 +429,31 @@ static int tc_attention_launch(const __half* qkv, __half* out, SeqMap map, int m
   *handled = false;
   TcAttnArgs a;
   a.mode = mode; a.len = map.len; a.N = N; a.groups = N / 64; a.map = map; a.out = out;
-  a.nblk = (a.len + 223) / 224;
-  a.NB = (((a.len + a.nblk - 1) / a.nblk) + 15) / 16 * 16;
+  a.nblk = (a.len + ATT_NB - 1) / ATT_NB;
   a.mtiles = (a.len + 127) / 128;
-  a.pkb = (a.NB + 63) / 64;
   a.num_items = map.G * a.groups;
-  const size_t smem = 2 * 16384 + 2 * (size_t)a.nblk * a.NB * 128 + 2 * (size_t)a.pkb * 16384 + 256;
-  if (smem > 227 * 1024 || a.NB > 224) return 0;   // not handled: caller falls back
+  const size_t smem = 2 * 16384 + 4 * 16384 + 8192 + 2 * (size_t)a.nblk * ATT_NB * 128 + 512;
+  if (smem > 227 * 1024) return 0;   // not handled: caller falls back
   CUtensorMap tmQ, tmKV;
   const long long tok = (long long)B * S * C;
   if (mode == 0) {
     const uint64_t dims[2] = {(uint64_t)3 * N, (uint64_t)tok};
     const uint64_t str[1] = {(uint64_t)3 * N * 2};
-    const uint32_t boxq[2] = {64, 128}, boxkv[2] = {64, (uint32_t)a.NB};
+    const uint32_t boxq[2] = {64, 128}, boxkv[2] = {64, ATT_NB};
     if (make_tmap_f16(&tmQ, qkv, 2, dims, str, boxq)) return -1;
     if (make_tmap_f16(&tmKV, qkv, 2, dims, str, boxkv)) return -1;
   } else {
     const uint64_t dims[4] = {(uint64_t)3 * N, (uint64_t)C, (uint64_t)S, (uint64_t)B};
     const uint64_t str[3] = {(uint64_t)3 * N * 2, (uint64_t)C * 3 * N * 2, (uint64_t)S * C * 3 * N * 2};
-    const uint32_t boxq[4] = {64, 1, 128, 1}, boxkv[4] = {64, 1, (uint32_t)a.NB, 1};
+    const uint32_t boxq[4] = {64, 1, 128, 1}, boxkv[4] = {64, 1, ATT_NB, 1};
     if (make_tmap_f16(&tmQ, qkv, 4, dims, str, boxq)) return -1;
     if (make_tmap_f16(&tmKV, qkv, 4, dims, str, boxkv)) return -1;
   }
   auto kern = k_tc_attention<HD>;
-  static size_t configured = 0;
-  if (configured < smem) {
+  static bool configured = false;
+  if (!configured) {
     VATSS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    configured = 227 * 1024;
+    configured = true;
   }
   const int grid = a.num_items < num_sms() ? a.num_items : num_sms();
   kern<<<grid, ATT_THREADS, smem, st>>>(tmQ, tmKV, a);

@@ -147,23 +147,27 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
   const uint32_t sQ = base;                        // [2][128 x 128 B]
   const uint32_t sP = sQ + 2 * 16384;              // [2 wg][2][128 x 128 B]
   const uint32_t sOnes = sP + 4 * 16384;           // [64 x 128 B] of fp16 1.0 (B operand of the row-sum MMA)
-  const uint32_t sK = sOnes + 8192;
-  const uint32_t sV = sK + KV_BYTES;
+  const uint32_t sK = sOnes + 8192;                // [2] double buffered across items
+  const uint32_t sV = sK + 2 * KV_BYTES;
   const uint32_t bars = sV + KV_BYTES;
   AttBars B;
-  B.kfull = bars; B.kfree = bars + 8; B.vfull = bars + 16; B.vfree = bars + 24;
-  B.qfull = bars + 32; B.qfree = bars + 48;
-  B.sfull = bars + 64; B.sfree = bars + 112;      // 6 each
-  B.pfull = bars + 160; B.pfree = bars + 192;     // 4 each
-  B.ofull = bars + 224; B.ofree = bars + 240;     // 2 each
-  const uint32_t tmem_slot = bars + 256;
+  B.kfull = bars; B.kfree = bars + 16;             // 2 each
+  B.vfull = bars + 32; B.vfree = bars + 40;
+  B.qfull = bars + 48; B.qfree = bars + 64;        // 2 each
+  B.sfull = bars + 80; B.sfree = bars + 128;       // 6 each
+  B.pfull = bars + 176; B.pfree = bars + 208;      // 4 each
+  B.ofull = bars + 240; B.ofree = bars + 256;      // 2 each
+  const uint32_t tmem_slot = bars + 272;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool resident = p.nblk <= ATT_RING;        // all S blocks of a (tile, head) fit the ring: single S pass
   const int jobs_per_head = resident ? p.nblk : 2 * p.nblk;
 
   if (threadIdx.x == 0) {
-    mbar_init(B.kfull, 1); mbar_init(B.kfree, 1); mbar_init(B.vfull, 1); mbar_init(B.vfree, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(B.qfull + 8 * i, 1); mbar_init(B.qfree + 8 * i, 1); }
+    mbar_init(B.vfull, 1); mbar_init(B.vfree, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(B.kfull + 8 * i, 1); mbar_init(B.kfree + 8 * i, 1);
+      mbar_init(B.qfull + 8 * i, 1); mbar_init(B.qfree + 8 * i, 1);
+    }
     for (int i = 0; i < 6; ++i) { mbar_init(B.sfull + 8 * i, 1); mbar_init(B.sfree + 8 * i, 128); }
     for (int i = 0; i < 4; ++i) { mbar_init(B.pfull + 8 * i, 128); mbar_init(B.pfree + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(B.ofull + 8 * i, 1); mbar_init(B.ofree + 8 * i, 128); }
@@ -198,9 +202,11 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
           if (p.mode == 0) tma_load_2d(dst, tm, bar, col, (int)(row0 + r0));
           else tma_load_4d(dst, tm, bar, col, ck, r0, cb);
         };
-        mbar_wait(B.kfree, (it & 1) ^ 1);
-        mbar_expect_tx(B.kfull, KV_BYTES);
-        for (int j = 0; j < p.nblk; ++j) load_rows(&tmapKV, sK + j * ATT_NB * 128, B.kfull, colk, j * ATT_NB);
+        const int kb = it & 1;
+        mbar_wait(B.kfree + 8 * kb, ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(B.kfull + 8 * kb, KV_BYTES);
+        for (int j = 0; j < p.nblk; ++j)
+          load_rows(&tmapKV, sK + kb * KV_BYTES + j * ATT_NB * 128, B.kfull + 8 * kb, colk, j * ATT_NB);
         for (int m = 0; m < p.mtiles; ++m, ++qn) {
           const int s = qn & 1;
           mbar_wait(B.qfree + 8 * s, ((qn >> 1) & 1) ^ 1);
@@ -221,82 +227,98 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
       const uint32_t idesc_s = idesc_f16(128, ATT_NB, 0);
       const uint32_t idesc_o = idesc_f16(128, HD, 0) | (1u << 16);     // B (= V) is MN-major
       const uint32_t idesc_1 = idesc_f16(128, 16, 0) | (1u << 16);     // row sums: P x ones
-      uint32_t kjob = 0;      // S jobs issued (same sequence for both warpgroups)
-      uint32_t pjob = 0;      // exp jobs whose P V has been issued
-      uint32_t ohead = 0;     // (tile, head) accumulators started
-      int it = 0, qn = 0;
-      // software pipeline: the P V of job k-1 is issued after the S of job k
-      struct { bool valid; int j, hsel_hh, it; bool last_of_item; } pend = {false, 0, 0, 0, false};
-      auto issue_pv = [&]() {
-        if (!pend.valid) return;
+      // a "group" = one (item, query tile, head-of-warpgroup); both warpgroups run the same group sequence
+      struct Cur { int item, it, m, qn, hh; bool valid; };
+      auto advance = [&](Cur& c) {
+        if (++c.hh == HPW) {
+          c.hh = 0; ++c.qn;
+          if (++c.m == p.mtiles) { c.m = 0; c.item += gridDim.x; ++c.it; c.valid = c.item < p.num_items; }
+        }
+      };
+      uint32_t kjob = 0, pjob = 0, ohead = 0;
+      int k_seen = -1, q_seen = -1, v_seen = -1;
+      // S block j of group c into the next ring slot of both warpgroups
+      auto issue_s = [&](const Cur& c, int j, bool last_job_of_group) {
+        if (k_seen != c.it) { mbar_wait(B.kfull + 8 * (c.it & 1), (c.it >> 1) & 1); k_seen = c.it; }
+        if (q_seen != c.qn) { mbar_wait(B.qfull + 8 * (c.qn & 1), (c.qn >> 1) & 1); q_seen = c.qn; }
+        const uint32_t slot = kjob % ATT_RING, use = kjob / ATT_RING;
         for (int w = 0; w < 2; ++w) {
-          const int hsel = w * HPW + pend.hsel_hh;
-          const uint32_t pb = pjob & 1;
-          if (pend.j == 0) mbar_wait(B.ofree + 8 * w, (ohead & 1) ^ 1);   // previous O of this warpgroup read out
+          const int hsel = w * HPW + c.hh;
+          mbar_wait(B.sfree + 8 * (w * 3 + slot), (use & 1) ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k16 = 0; k16 < HD / 16; ++k16) {
+            const uint32_t koff = (uint32_t)(hsel * HD * 2 + k16 * 32) >> 4;
+            const uint64_t a = smem_desc_sw128_kmajor(sQ + (c.qn & 1) * 16384) + koff;
+            const uint64_t b = smem_desc_sw128_kmajor(sK + (c.it & 1) * KV_BYTES + j * ATT_NB * 128) + koff;
+            umma_f16<1>(tmem + w * ATT_WG_COLS + slot * ATT_NB, a, b, idesc_s, k16 > 0 ? 1u : 0u);
+          }
+          umma_commit(B.sfull + 8 * (w * 3 + slot));
+        }
+        ++kjob;
+        if (last_job_of_group && c.hh == HPW - 1) {
+          umma_commit(B.qfree + 8 * (c.qn & 1));                       // last S MMA reading this Q tile
+          if (c.m == p.mtiles - 1) umma_commit(B.kfree + 8 * (c.it & 1));   // ... and this K buffer
+        }
+      };
+      // O += P_j V_j and row sums += P_j 1 for group c, both warpgroups
+      auto issue_pv = [&](const Cur& c, int j) {
+        if (v_seen != c.it) { mbar_wait(B.vfull, c.it & 1); v_seen = c.it; }
+        const uint32_t pb = pjob & 1;
+        for (int w = 0; w < 2; ++w) {
+          const int hsel = w * HPW + c.hh;
+          if (j == 0) mbar_wait(B.ofree + 8 * w, (ohead & 1) ^ 1);     // previous O of this warpgroup read out
           mbar_wait(B.pfull + 8 * (w * 2 + pb), (pjob >> 1) & 1);
           tc_fence_after();
           const uint32_t d_o = tmem + w * ATT_WG_COLS + ATT_O_COL, d_s = tmem + w * ATT_WG_COLS + ATT_SUM_COL;
 #pragma unroll
           for (int k16 = 0; k16 < ATT_NB / 16; ++k16) {
             const uint64_t a = smem_desc_sw128_kmajor(sP + (w * 2 + pb) * 16384) + (uint64_t)(k16 * 2);
-            const uint64_t bv = smem_desc_sw128_mnmajor(sV + (pend.j * ATT_NB + k16 * 16) * 128 + hsel * HD * 2);
+            const uint64_t bv = smem_desc_sw128_mnmajor(sV + (j * ATT_NB + k16 * 16) * 128 + hsel * HD * 2);
             const uint64_t b1 = smem_desc_sw128_mnmajor(sOnes + k16 * 16 * 128);
-            const uint32_t acc = (pend.j > 0 || k16 > 0) ? 1u : 0u;
+            const uint32_t acc = (j > 0 || k16 > 0) ? 1u : 0u;
             umma_f16<1>(d_o, a, bv, idesc_o, acc);
             umma_f16<1>(d_s, a, b1, idesc_1, acc);
           }
           umma_commit(B.pfree + 8 * (w * 2 + pb));
-          if (pend.j == p.nblk - 1) umma_commit(B.ofull + 8 * w);
+          if (j == p.nblk - 1) umma_commit(B.ofull + 8 * w);
         }
         ++pjob;
-        if (pend.j == p.nblk - 1) ++ohead;
-        if (pend.last_of_item) umma_commit(B.vfree);
-        pend.valid = false;
-      };
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        mbar_wait(B.kfull, it & 1);
-        bool v_ready = false;
-        for (int m = 0; m < p.mtiles; ++m, ++qn) {
-          const int s = qn & 1;
-          mbar_wait(B.qfull + 8 * s, (qn >> 1) & 1);
-          tc_fence_after();
-          for (int hh = 0; hh < HPW; ++hh) {
-            for (int jj = 0; jj < jobs_per_head; ++jj, ++kjob) {
-              const int j = jj % p.nblk;
-              const bool exp_job = resident || jj >= p.nblk;
-              const uint32_t slot = kjob % ATT_RING, use = kjob / ATT_RING;
-              for (int w = 0; w < 2; ++w) {
-                const int hsel = w * HPW + hh;
-                mbar_wait(B.sfree + 8 * (w * 3 + slot), (use & 1) ^ 1);
-                tc_fence_after();
-#pragma unroll
-                for (int k16 = 0; k16 < HD / 16; ++k16) {
-                  const uint32_t koff = (uint32_t)(hsel * HD * 2 + k16 * 32) >> 4;
-                  const uint64_t a = smem_desc_sw128_kmajor(sQ + s * 16384) + koff;
-                  const uint64_t b = smem_desc_sw128_kmajor(sK + j * ATT_NB * 128) + koff;
-                  umma_f16<1>(tmem + w * ATT_WG_COLS + slot * ATT_NB, a, b, idesc_s, k16 > 0 ? 1u : 0u);
-                }
-                umma_commit(B.sfull + 8 * (w * 3 + slot));
-              }
-              const bool last_s_of_tile = hh == HPW - 1 && jj == jobs_per_head - 1;
-              if (last_s_of_tile) umma_commit(B.qfree + 8 * s);
-              if (last_s_of_tile && m == p.mtiles - 1) umma_commit(B.kfree);
-              // P V of the previous job
-              if (pend.valid && !v_ready && pend.it == it) { mbar_wait(B.vfull, it & 1); v_ready = true; }
-              issue_pv();
-              if (exp_job) {
-                pend.valid = true; pend.j = j; pend.hsel_hh = hh; pend.it = it;
-                pend.last_of_item = last_s_of_tile && m == p.mtiles - 1;
-              }
-            }
-          }
+        if (j == p.nblk - 1) {
+          ++ohead;
+          if (c.hh == HPW - 1 && c.m == p.mtiles - 1) umma_commit(B.vfree);   // last P V reading this item's V
         }
+      };
+      Cur cur = {(int)blockIdx.x, 0, 0, 0, 0, (int)blockIdx.x < p.num_items};
+      if (resident) {
+        // the softmax needs every S block of a group before it emits P_0: S of group g+1 block j is issued right
+        // after P V of group g block j (whose completion of P_j has freed ring slot j)
+        Cur nxt = cur;
+        if (cur.valid) {
+          for (int j = 0; j < p.nblk; ++j) issue_s(cur, j, j == p.nblk - 1);
+          advance(nxt);
+        }
+        while (cur.valid) {
+          for (int j = 0; j < p.nblk; ++j) {
+            issue_pv(cur, j);
+            if (nxt.valid) issue_s(nxt, j, j == p.nblk - 1);
+          }
+          cur = nxt;
+          if (nxt.valid) advance(nxt);
+        }
+      } else {
+        // two-pass groups: jobs A_0..A_{n-1} (row max) then B_0..B_{n-1} (exp); P V of job k-1 follows S of job k
+        bool pend = false; Cur pc = cur; int pj = 0;
+        while (cur.valid) {
+          for (int jj = 0; jj < 2 * p.nblk; ++jj) {
+            issue_s(cur, jj % p.nblk, jj == 2 * p.nblk - 1);
+            if (pend) { issue_pv(pc, pj); pend = false; }
+            if (jj >= p.nblk) { pend = true; pc = cur; pj = jj - p.nblk; }
+          }
+          advance(cur);
+        }
+        if (pend) issue_pv(pc, pj);
       }
-      if (pend.valid) {
-        const int last_it = it - 1;
-        if (pend.it == last_it) mbar_wait(B.vfull, last_it & 1);   // idempotent if already observed
-      }
-      issue_pv();
     }
     __syncwarp();
   } else {
@@ -432,7 +454,7 @@ static int tc_attention_launch(const __half* qkv, __half* out, SeqMap map, int m
   a.nblk = (a.len + ATT_NB - 1) / ATT_NB;
   a.mtiles = (a.len + 127) / 128;
   a.num_items = map.G * a.groups;
-  const size_t smem = 2 * 16384 + 4 * 16384 + 8192 + 2 * (size_t)a.nblk * ATT_NB * 128 + 512;
+  const size_t smem = 2 * 16384 + 4 * 16384 + 8192 + 3 * (size_t)a.nblk * ATT_NB * 128 + 512;
   if (smem > 227 * 1024) return 0;   // not handled: caller falls back
   CUtensorMap tmQ, tmKV;
   const long long tok = (long long)B * S * C;

@@ -9,8 +9,9 @@
 // SWIZZLE_128B TMA tiles; a head is a 16/32-column K-slice of them.  One persistent CTA per SM:
 //   warp 0        TMA producer (K and V of the item once, Q per 128-query tile, double buffered)
 //   warp 1        MMA issuer: S = Q K^T (M=128, N=kv block, K=hd) and O += P V (M=128, N=hd, K=kv block)
-//   warps 2..5    softmax warpgroup 0  (thread = query row; heads [0, HPT/2) of the group)
-//   warps 6..9    softmax warpgroup 1  (heads [HPT/2, HPT))
+//   warps 2..9    softmax warpgroup 0  (heads [0, HPT/2) of the group): two warps per TMEM lane quadrant, each
+//                 thread owns one query row and one 32-column half of every 64-column S block
+//   warps 10..17  softmax warpgroup 1  (heads [HPT/2, HPT))
 // Each warpgroup owns an S slot and an O accumulator in TMEM and a P tile in shared memory, so the two
 // heads' MMAs and exponentials overlap.  Sequences longer than one kv block use an exact two-pass softmax
 // (pass A: row max over all blocks, pass B: exp / P V accumulation) - no accumulator rescaling.
@@ -103,7 +104,7 @@ struct TcAttnArgs {
   __half* out;    // (tokens, N)
 };
 
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 576;        // producer + MMA warps, 2 warpgroups x 8 softmax warps
 constexpr int ATT_NB = 64;             // kv rows per block = one SWIZZLE_128B k-block of the P tile
 constexpr int ATT_RING = 3;            // S slots per warpgroup in TMEM
 constexpr uint32_t ATT_WG_COLS = 256;  // TMEM columns per warpgroup: 3 x 64 (S ring) + 32 (O) + 16 (row sums)
@@ -158,6 +159,7 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
   B.pfull = bars + 176; B.pfree = bars + 208;      // 4 each
   B.ofull = bars + 240; B.ofree = bars + 256;      // 2 each
   const uint32_t tmem_slot = bars + 272;
+  float* s_mx = reinterpret_cast<float*>(smem + (bars + 288 - base));   // [2 wg][2 sets][128 rows]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool resident = p.nblk <= ATT_RING;        // all S blocks of a (tile, head) fit the ring: single S pass
   const int jobs_per_head = resident ? p.nblk : 2 * p.nblk;
@@ -168,9 +170,9 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
       mbar_init(B.kfull + 8 * i, 1); mbar_init(B.kfree + 8 * i, 1);
       mbar_init(B.qfull + 8 * i, 1); mbar_init(B.qfree + 8 * i, 1);
     }
-    for (int i = 0; i < 6; ++i) { mbar_init(B.sfull + 8 * i, 1); mbar_init(B.sfree + 8 * i, 128); }
-    for (int i = 0; i < 4; ++i) { mbar_init(B.pfull + 8 * i, 128); mbar_init(B.pfree + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(B.ofull + 8 * i, 1); mbar_init(B.ofree + 8 * i, 128); }
+    for (int i = 0; i < 6; ++i) { mbar_init(B.sfull + 8 * i, 1); mbar_init(B.sfree + 8 * i, 256); }
+    for (int i = 0; i < 4; ++i) { mbar_init(B.pfull + 8 * i, 256); mbar_init(B.pfree + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(B.ofull + 8 * i, 1); mbar_init(B.ofree + 8 * i, 256); }
     fence_mbar_init();
     prefetch_tmap(&tmapQ);
     prefetch_tmap(&tmapKV);
@@ -323,38 +325,39 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
     __syncwarp();
   } else {
     // ---------------------------------------------------------------- softmax warpgroups
-    const int w = (warp - 2) >> 2;               // warpgroup
+    const int sw = warp - 2;
+    const int w = sw >> 3;                       // warpgroup
+    const int set = (sw >> 2) & 1;               // which 32-column half of each S block this thread owns
     const int q = warp & 3;                      // TMEM lane quadrant of this warp
     const int r = q * 32 + lane;                 // query row inside the 128-row tile
     const uint32_t t_base = tmem + ((uint32_t)(q * 32) << 16) + w * ATT_WG_COLS;
-    uint32_t kjob = 0, pjob = 0, ohead = 0;
+    const int cb = set * 32;
+    uint32_t kjob = 0, pjob = 0, ohead = 0, gcount = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int g = item / p.groups, grp = item - g * p.groups;
       for (int m = 0; m < p.mtiles; ++m) {
         const int qi = m * 128 + r;
         const bool warp_live = m * 128 + q * 32 < p.len;     // warp-uniform: any valid query row in this warp
-        for (int hh = 0; hh < HPW; ++hh) {
+        for (int hh = 0; hh < HPW; ++hh, ++gcount) {
           const int head = grp * HPT + w * HPW + hh;
           float mx = -INFINITY;
-          // ---- row maximum
+          // ---- row maximum over this thread's columns
           for (int j = 0; j < p.nblk; ++j) {
             const uint32_t kk = kjob + j, slot = kk % ATT_RING, use = kk / ATT_RING;
             mbar_wait(B.sfull + 8 * (w * 3 + slot), use & 1);
             tc_fence_after();
-            if (warp_live) {
-              const int nv = min(ATT_NB, p.len - j * ATT_NB);
-              for (int c0 = 0; c0 < nv; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(t_base + slot * ATT_NB + c0, v);
-                tmem_ld_wait();
-                if (c0 + 16 <= nv) {
+            const int nv = min(ATT_NB, p.len - j * ATT_NB) - cb;   // valid columns of this thread's half
+            if (warp_live && nv > 0) {
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(t_base + slot * ATT_NB + cb, v);
+              tmem_ld_wait();
+              if (nv >= 32) {
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-                } else {
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+              } else {
 #pragma unroll
-                  for (int i = 0; i < 16; ++i)
-                    if (c0 + i < nv) mx = fmaxf(mx, __uint_as_float(v[i]));
-                }
+                for (int i = 0; i < 32; ++i)
+                  if (i < nv) mx = fmaxf(mx, __uint_as_float(v[i]));
               }
             }
             if (!resident) {   // the ring slot is recycled for the exp pass
@@ -363,6 +366,14 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
             }
           }
           if (!resident) kjob += p.nblk;
+          // combine the two column halves of the row through shared memory (named barrier of this warpgroup)
+          {
+            float* ex = s_mx + w * 256;
+            ex[set * 128 + r] = mx;
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
+            mx = fmaxf(mx, ex[(set ^ 1) * 128 + r]);
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");   // both halves read before the next group writes
+          }
           // ---- probabilities -> P tiles (fp16, K-major SWIZZLE_128B), consumed by the P V MMAs
           for (int j = 0; j < p.nblk; ++j, ++kjob, ++pjob) {
             const uint32_t slot = kjob % ATT_RING, use = kjob / ATT_RING, pb = pjob & 1;
@@ -370,62 +381,62 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
               mbar_wait(B.sfull + 8 * (w * 3 + slot), use & 1);
               tc_fence_after();
             }
-            mbar_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
             if (warp_live) {
-              const int nv = min(ATT_NB, p.len - j * ATT_NB);
-              const uint32_t sPw = sP + (w * 2 + pb) * 16384;
-#pragma unroll 1
-              for (int c0 = 0; c0 < ATT_NB; c0 += 16) {
-                uint32_t pk[8];
-                if (c0 < nv) {
-                  uint32_t v[16];
-                  tmem_ld_32x32b_x16(t_base + slot * ATT_NB + c0, v);
-                  tmem_ld_wait();
-                  if (c0 + 16 <= nv) {
+              const int nv = min(ATT_NB, p.len - j * ATT_NB) - cb;
+              uint32_t pk[16];
+              if (nv > 0) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(t_base + slot * ATT_NB + cb, v);
+                tmem_ld_wait();
+                if (nv >= 32) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                      pk[i] = ex2_f16x2(__uint_as_float(v[2 * i]) - mx, __uint_as_float(v[2 * i + 1]) - mx);
-                  } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                      const float a = (c0 + 2 * i < nv) ? __uint_as_float(v[2 * i]) - mx : -60000.f;
-                      const float b = (c0 + 2 * i + 1 < nv) ? __uint_as_float(v[2 * i + 1]) - mx : -60000.f;
-                      pk[i] = ex2_f16x2(a, b);   // 2^-60000 flushes to +0
-                    }
-                  }
+                  for (int i = 0; i < 16; ++i)
+                    pk[i] = ex2_f16x2(__uint_as_float(v[2 * i]) - mx, __uint_as_float(v[2 * i + 1]) - mx);
                 } else {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) pk[i] = 0u;
+                  for (int i = 0; i < 16; ++i) {
+                    const float a = (2 * i < nv) ? __uint_as_float(v[2 * i]) - mx : -60000.f;
+                    const float b = (2 * i + 1 < nv) ? __uint_as_float(v[2 * i + 1]) - mx : -60000.f;
+                    pk[i] = ex2_f16x2(a, b);   // 2^-60000 flushes to +0
+                  }
                 }
-                const uint32_t ch = (uint32_t)c0 >> 3;
-                const uint32_t a0 = sPw + sw128_offset((uint32_t)r, ch), a1 = sPw + sw128_offset((uint32_t)r, ch + 1);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
-                             "r"(pk[3]) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]),
-                             "r"(pk[7]) : "memory");
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = 0u;
               }
+              // the P buffer of two blocks ago must have been consumed by its P V MMAs
+              mbar_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
+              const uint32_t sPw = sP + (w * 2 + pb) * 16384;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint32_t a0 = sPw + sw128_offset((uint32_t)r, (uint32_t)(cb >> 3) + c);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
+                             "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+              }
+            } else {
+              mbar_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
             }
             tc_fence_before();
             mbar_arrive(B.sfree + 8 * (w * 3 + slot));
             fence_proxy_async();
             mbar_arrive(B.pfull + 8 * (w * 2 + pb));
           }
-          // ---- O = sum_j P_j V_j and the row sums (P x ones) complete
+          // ---- O = sum_j P_j V_j and the row sums (P x ones) complete; this thread stores HD/2 features
           mbar_wait(B.ofull + 8 * w, ohead & 1);
           ++ohead;
           tc_fence_after();
-          uint32_t o[HD], sm[16];
-          if constexpr (HD == 32) tmem_ld_32x32b_x32(t_base + ATT_O_COL, o);
-          else tmem_ld_32x32b_x16(t_base + ATT_O_COL, o);
-          tmem_ld_32x32b_x16(t_base + ATT_SUM_COL, sm);
+          uint32_t o[HD / 2], sm[8];
+          if constexpr (HD == 32) tmem_ld_32x32b_x16(t_base + ATT_O_COL + set * 16, o);
+          else tmem_ld_32x32b_x8(t_base + ATT_O_COL + set * 8, o);
+          tmem_ld_32x32b_x8(t_base + ATT_SUM_COL, sm);
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(B.ofree + 8 * w);
           if (qi < p.len) {
             const float inv = 1.f / __uint_as_float(sm[0]);
-            uint4* dst = reinterpret_cast<uint4*>(p.out + p.map.row(g, qi) * p.N + head * HD);
+            uint4* dst = reinterpret_cast<uint4*>(p.out + p.map.row(g, qi) * p.N + head * HD + set * (HD / 2));
 #pragma unroll
-            for (int c = 0; c < HD / 8; ++c) {
+            for (int c = 0; c < HD / 16; ++c) {
               uint32_t wd[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -454,7 +465,7 @@ static int tc_attention_launch(const __half* qkv, __half* out, SeqMap map, int m
   a.nblk = (a.len + ATT_NB - 1) / ATT_NB;
   a.mtiles = (a.len + 127) / 128;
   a.num_items = map.G * a.groups;
-  const size_t smem = 2 * 16384 + 4 * 16384 + 8192 + 3 * (size_t)a.nblk * ATT_NB * 128 + 512;
+  const size_t smem = 2 * 16384 + 4 * 16384 + 8192 + 3 * (size_t)a.nblk * ATT_NB * 128 + 512 + 2048;
   if (smem > 227 * 1024) return 0;   // not handled: caller falls back
   CUtensorMap tmQ, tmKV;
   const long long tok = (long long)B * S * C;

@@ -106,9 +106,9 @@ struct TcAttnArgs {
 
 constexpr int ATT_THREADS = 576;        // producer + MMA warps, 2 warpgroups x 8 softmax warps
 constexpr int ATT_NB = 64;             // kv rows per block = one SWIZZLE_128B k-block of the P tile
-constexpr int ATT_RING = 3;            // S slots per warpgroup in TMEM
-constexpr uint32_t ATT_WG_COLS = 256;  // TMEM columns per warpgroup: 3 x 64 (S ring) + 32 (O) + 16 (row sums)
-constexpr uint32_t ATT_O_COL = 192, ATT_SUM_COL = 224;
+constexpr int ATT_SUPER = 3;           // 64-row kv blocks per S job: one N <= 192 MMA fills the whole S region
+constexpr uint32_t ATT_WG_COLS = 256;  // TMEM columns per warpgroup: 192 (S region) + 32 (O)
+constexpr uint32_t ATT_O_COL = 192;
 
 // MN-major (N contiguous) B operand with 128-byte rows, SWIZZLE_128B: 8-row (K) groups 1024 B apart
 __device__ __forceinline__ uint64_t smem_desc_sw128_mnmajor(uint32_t smem_addr) {
@@ -121,6 +121,11 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_mnmajor(uint32_t smem_addr) 
   return d;
 }
 
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // p = 2^(a), 2^(b) as packed fp16 (one MUFU op for the pair)
 __device__ __forceinline__ uint32_t ex2_f16x2(float a, float b) {
   uint32_t packed, y;
@@ -130,8 +135,8 @@ __device__ __forceinline__ uint32_t ex2_f16x2(float a, float b) {
 }
 
 struct AttBars {
-  uint32_t kfull, kfree, vfull, vfree, qfull, qfree;   // qfull/qfree: [2]
-  uint32_t sfull, sfree;                               // [2 wg][3 slots]
+  uint32_t kfull, kfree, vfull, vfree, qfull, qfree;   // kfull/kfree/qfull/qfree: [2]
+  uint32_t sfull, sfree;                               // [2 wg]
   uint32_t pfull, pfree;                               // [2 wg][2 buffers]
   uint32_t ofull, ofree;                               // [2 wg]
 };
@@ -147,8 +152,7 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
   const uint32_t KV_BYTES = (uint32_t)p.nblk * ATT_NB * 128u;
   const uint32_t sQ = base;                        // [2][128 x 128 B]
   const uint32_t sP = sQ + 2 * 16384;              // [2 wg][2][128 x 128 B]
-  const uint32_t sOnes = sP + 4 * 16384;           // [64 x 128 B] of fp16 1.0 (B operand of the row-sum MMA)
-  const uint32_t sK = sOnes + 8192;                // [2] double buffered across items
+  const uint32_t sK = sP + 4 * 16384;              // [2] double buffered across items
   const uint32_t sV = sK + 2 * KV_BYTES;
   const uint32_t bars = sV + KV_BYTES;
   AttBars B;
@@ -161,8 +165,8 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
   const uint32_t tmem_slot = bars + 272;
   float* s_mx = reinterpret_cast<float*>(smem + (bars + 288 - base));   // [2 wg][2 sets][128 rows]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool resident = p.nblk <= ATT_RING;        // all S blocks of a (tile, head) fit the ring: single S pass
-  const int jobs_per_head = resident ? p.nblk : 2 * p.nblk;
+  const bool resident = p.nblk <= ATT_SUPER;       // all of S of a (tile, head) fits the S region: single S pass
+  const int nsuper = (p.nblk + ATT_SUPER - 1) / ATT_SUPER;
 
   if (threadIdx.x == 0) {
     mbar_init(B.vfull, 1); mbar_init(B.vfree, 1);
@@ -170,16 +174,13 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
       mbar_init(B.kfull + 8 * i, 1); mbar_init(B.kfree + 8 * i, 1);
       mbar_init(B.qfull + 8 * i, 1); mbar_init(B.qfree + 8 * i, 1);
     }
-    for (int i = 0; i < 6; ++i) { mbar_init(B.sfull + 8 * i, 1); mbar_init(B.sfree + 8 * i, 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(B.sfull + 8 * i, 1); mbar_init(B.sfree + 8 * i, 256); }
     for (int i = 0; i < 4; ++i) { mbar_init(B.pfull + 8 * i, 256); mbar_init(B.pfree + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(B.ofull + 8 * i, 1); mbar_init(B.ofree + 8 * i, 256); }
     fence_mbar_init();
     prefetch_tmap(&tmapQ);
     prefetch_tmap(&tmapKV);
   }
-  for (int i = threadIdx.x; i < 8192 / 4; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(smem + (sOnes - base))[i] = 0x3C003C00u;
-  fence_proxy_async();
   if (warp == 1) {
     tmem_alloc<1>(tmem_slot, 512);
     tmem_relinquish<1>();
@@ -225,10 +226,10 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
+    // Small tcgen05.mma instructions cost a fixed ~100+ cycles each, so the instruction count is what matters:
+    // S uses one N = 64..192 MMA per 16-wide K step for a whole super-block, P V needs kv/16 MMAs of N = hd.
     if (lane == 0) {
-      const uint32_t idesc_s = idesc_f16(128, ATT_NB, 0);
       const uint32_t idesc_o = idesc_f16(128, HD, 0) | (1u << 16);     // B (= V) is MN-major
-      const uint32_t idesc_1 = idesc_f16(128, 16, 0) | (1u << 16);     // row sums: P x ones
       // a "group" = one (item, query tile, head-of-warpgroup); both warpgroups run the same group sequence
       struct Cur { int item, it, m, qn, hh; bool valid; };
       auto advance = [&](Cur& c) {
@@ -237,33 +238,34 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
           if (++c.m == p.mtiles) { c.m = 0; c.item += gridDim.x; ++c.it; c.valid = c.item < p.num_items; }
         }
       };
-      uint32_t kjob = 0, pjob = 0, ohead = 0;
+      uint32_t sjob = 0, pjob = 0, ohead = 0;
       int k_seen = -1, q_seen = -1, v_seen = -1;
-      // S block j of group c into the next ring slot of both warpgroups
-      auto issue_s = [&](const Cur& c, int j, bool last_job_of_group) {
+      // S super-block sb (kv blocks [3 sb, 3 sb + nb)) of group c into the S region of both warpgroups
+      auto issue_s = [&](const Cur& c, int sb, bool last_job_of_group) {
         if (k_seen != c.it) { mbar_wait(B.kfull + 8 * (c.it & 1), (c.it >> 1) & 1); k_seen = c.it; }
         if (q_seen != c.qn) { mbar_wait(B.qfull + 8 * (c.qn & 1), (c.qn >> 1) & 1); q_seen = c.qn; }
-        const uint32_t slot = kjob % ATT_RING, use = kjob / ATT_RING;
+        const int nb = min(ATT_SUPER, p.nblk - sb * ATT_SUPER);
+        const uint32_t idesc_s = idesc_f16(128, nb * ATT_NB, 0);
         for (int w = 0; w < 2; ++w) {
           const int hsel = w * HPW + c.hh;
-          mbar_wait(B.sfree + 8 * (w * 3 + slot), (use & 1) ^ 1);
+          mbar_wait(B.sfree + 8 * w, (sjob & 1) ^ 1);
           tc_fence_after();
 #pragma unroll
           for (int k16 = 0; k16 < HD / 16; ++k16) {
             const uint32_t koff = (uint32_t)(hsel * HD * 2 + k16 * 32) >> 4;
             const uint64_t a = smem_desc_sw128_kmajor(sQ + (c.qn & 1) * 16384) + koff;
-            const uint64_t b = smem_desc_sw128_kmajor(sK + (c.it & 1) * KV_BYTES + j * ATT_NB * 128) + koff;
-            umma_f16<1>(tmem + w * ATT_WG_COLS + slot * ATT_NB, a, b, idesc_s, k16 > 0 ? 1u : 0u);
+            const uint64_t b = smem_desc_sw128_kmajor(sK + (c.it & 1) * KV_BYTES + sb * ATT_SUPER * ATT_NB * 128) + koff;
+            umma_f16<1>(tmem + w * ATT_WG_COLS, a, b, idesc_s, k16 > 0 ? 1u : 0u);
           }
-          umma_commit(B.sfull + 8 * (w * 3 + slot));
+          umma_commit(B.sfull + 8 * w);
         }
-        ++kjob;
+        ++sjob;
         if (last_job_of_group && c.hh == HPW - 1) {
           umma_commit(B.qfree + 8 * (c.qn & 1));                       // last S MMA reading this Q tile
           if (c.m == p.mtiles - 1) umma_commit(B.kfree + 8 * (c.it & 1));   // ... and this K buffer
         }
       };
-      // O += P_j V_j and row sums += P_j 1 for group c, both warpgroups
+      // O += P_j V_j for group c, both warpgroups
       auto issue_pv = [&](const Cur& c, int j) {
         if (v_seen != c.it) { mbar_wait(B.vfull, c.it & 1); v_seen = c.it; }
         const uint32_t pb = pjob & 1;
@@ -272,15 +274,12 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
           if (j == 0) mbar_wait(B.ofree + 8 * w, (ohead & 1) ^ 1);     // previous O of this warpgroup read out
           mbar_wait(B.pfull + 8 * (w * 2 + pb), (pjob >> 1) & 1);
           tc_fence_after();
-          const uint32_t d_o = tmem + w * ATT_WG_COLS + ATT_O_COL, d_s = tmem + w * ATT_WG_COLS + ATT_SUM_COL;
+          const uint32_t d_o = tmem + w * ATT_WG_COLS + ATT_O_COL;
 #pragma unroll
           for (int k16 = 0; k16 < ATT_NB / 16; ++k16) {
             const uint64_t a = smem_desc_sw128_kmajor(sP + (w * 2 + pb) * 16384) + (uint64_t)(k16 * 2);
             const uint64_t bv = smem_desc_sw128_mnmajor(sV + (j * ATT_NB + k16 * 16) * 128 + hsel * HD * 2);
-            const uint64_t b1 = smem_desc_sw128_mnmajor(sOnes + k16 * 16 * 128);
-            const uint32_t acc = (j > 0 || k16 > 0) ? 1u : 0u;
-            umma_f16<1>(d_o, a, bv, idesc_o, acc);
-            umma_f16<1>(d_s, a, b1, idesc_1, acc);
+            umma_f16<1>(d_o, a, bv, idesc_o, (j > 0 || k16 > 0) ? 1u : 0u);
           }
           umma_commit(B.pfree + 8 * (w * 2 + pb));
           if (j == p.nblk - 1) umma_commit(B.ofull + 8 * w);
@@ -292,34 +291,19 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
         }
       };
       Cur cur = {(int)blockIdx.x, 0, 0, 0, 0, (int)blockIdx.x < p.num_items};
-      if (resident) {
-        // the softmax needs every S block of a group before it emits P_0: S of group g+1 block j is issued right
-        // after P V of group g block j (whose completion of P_j has freed ring slot j)
-        Cur nxt = cur;
-        if (cur.valid) {
-          for (int j = 0; j < p.nblk; ++j) issue_s(cur, j, j == p.nblk - 1);
-          advance(nxt);
-        }
-        while (cur.valid) {
-          for (int j = 0; j < p.nblk; ++j) {
-            issue_pv(cur, j);
-            if (nxt.valid) issue_s(nxt, j, j == p.nblk - 1);
+      while (cur.valid) {
+        if (resident) {
+          issue_s(cur, 0, true);
+          for (int j = 0; j < p.nblk; ++j) issue_pv(cur, j);
+        } else {
+          for (int sb = 0; sb < nsuper; ++sb) issue_s(cur, sb, false);             // pass A: row maxima
+          for (int sb = 0; sb < nsuper; ++sb) {                                    // pass B: exp, P V
+            issue_s(cur, sb, sb == nsuper - 1);
+            const int j1 = min(p.nblk, (sb + 1) * ATT_SUPER);
+            for (int j = sb * ATT_SUPER; j < j1; ++j) issue_pv(cur, j);
           }
-          cur = nxt;
-          if (nxt.valid) advance(nxt);
         }
-      } else {
-        // two-pass groups: jobs A_0..A_{n-1} (row max) then B_0..B_{n-1} (exp); P V of job k-1 follows S of job k
-        bool pend = false; Cur pc = cur; int pj = 0;
-        while (cur.valid) {
-          for (int jj = 0; jj < 2 * p.nblk; ++jj) {
-            issue_s(cur, jj % p.nblk, jj == 2 * p.nblk - 1);
-            if (pend) { issue_pv(pc, pj); pend = false; }
-            if (jj >= p.nblk) { pend = true; pc = cur; pj = jj - p.nblk; }
-          }
-          advance(cur);
-        }
-        if (pend) issue_pv(pc, pj);
+        advance(cur);
       }
     }
     __syncwarp();
@@ -327,113 +311,124 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
     // ---------------------------------------------------------------- softmax warpgroups
     const int sw = warp - 2;
     const int w = sw >> 3;                       // warpgroup
-    const int set = (sw >> 2) & 1;               // which 32-column half of each S block this thread owns
+    const int set = (sw >> 2) & 1;               // which 32-column half of each 64-column kv block this thread owns
     const int q = warp & 3;                      // TMEM lane quadrant of this warp
     const int r = q * 32 + lane;                 // query row inside the 128-row tile
     const uint32_t t_base = tmem + ((uint32_t)(q * 32) << 16) + w * ATT_WG_COLS;
     const int cb = set * 32;
-    uint32_t kjob = 0, pjob = 0, ohead = 0, gcount = 0;
+    float* ex = s_mx + w * 256;
+    uint32_t sjob = 0, pjob = 0, ohead = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int g = item / p.groups, grp = item - g * p.groups;
       for (int m = 0; m < p.mtiles; ++m) {
         const int qi = m * 128 + r;
         const bool warp_live = m * 128 + q * 32 < p.len;     // warp-uniform: any valid query row in this warp
-        for (int hh = 0; hh < HPW; ++hh, ++gcount) {
+        for (int hh = 0; hh < HPW; ++hh) {
           const int head = grp * HPT + w * HPW + hh;
           float mx = -INFINITY;
           // ---- row maximum over this thread's columns
-          for (int j = 0; j < p.nblk; ++j) {
-            const uint32_t kk = kjob + j, slot = kk % ATT_RING, use = kk / ATT_RING;
-            mbar_wait(B.sfull + 8 * (w * 3 + slot), use & 1);
+          for (int sb = 0; sb < nsuper; ++sb) {
+            mbar_wait(B.sfull + 8 * w, (sjob + sb) & 1);
             tc_fence_after();
-            const int nv = min(ATT_NB, p.len - j * ATT_NB) - cb;   // valid columns of this thread's half
-            if (warp_live && nv > 0) {
-              uint32_t v[32];
-              tmem_ld_32x32b_x32(t_base + slot * ATT_NB + cb, v);
-              tmem_ld_wait();
-              if (nv >= 32) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (i < nv) mx = fmaxf(mx, __uint_as_float(v[i]));
-              }
-            }
-            if (!resident) {   // the ring slot is recycled for the exp pass
-              tc_fence_before();
-              mbar_arrive(B.sfree + 8 * (w * 3 + slot));
-            }
-          }
-          if (!resident) kjob += p.nblk;
-          // combine the two column halves of the row through shared memory (named barrier of this warpgroup)
-          {
-            float* ex = s_mx + w * 256;
-            ex[set * 128 + r] = mx;
-            asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
-            mx = fmaxf(mx, ex[(set ^ 1) * 128 + r]);
-            asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");   // both halves read before the next group writes
-          }
-          // ---- probabilities -> P tiles (fp16, K-major SWIZZLE_128B), consumed by the P V MMAs
-          for (int j = 0; j < p.nblk; ++j, ++kjob, ++pjob) {
-            const uint32_t slot = kjob % ATT_RING, use = kjob / ATT_RING, pb = pjob & 1;
-            if (!resident) {
-              mbar_wait(B.sfull + 8 * (w * 3 + slot), use & 1);
-              tc_fence_after();
-            }
+            const int j1 = min(p.nblk, (sb + 1) * ATT_SUPER);
             if (warp_live) {
-              const int nv = min(ATT_NB, p.len - j * ATT_NB) - cb;
-              uint32_t pk[16];
-              if (nv > 0) {
+              for (int j = sb * ATT_SUPER; j < j1; ++j) {
+                const int nv = min(ATT_NB, p.len - j * ATT_NB) - cb;   // valid columns of this thread's half
+                if (nv <= 0) continue;
                 uint32_t v[32];
-                tmem_ld_32x32b_x32(t_base + slot * ATT_NB + cb, v);
+                tmem_ld_32x32b_x32(t_base + (j - sb * ATT_SUPER) * ATT_NB + cb, v);
                 tmem_ld_wait();
                 if (nv >= 32) {
 #pragma unroll
-                  for (int i = 0; i < 16; ++i)
-                    pk[i] = ex2_f16x2(__uint_as_float(v[2 * i]) - mx, __uint_as_float(v[2 * i + 1]) - mx);
+                  for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
                 } else {
 #pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if (i < nv) mx = fmaxf(mx, __uint_as_float(v[i]));
+                }
+              }
+            }
+            if (!resident) {   // the S region is recycled for the next super-block
+              tc_fence_before();
+              mbar_arrive(B.sfree + 8 * w);
+            }
+          }
+          if (!resident) sjob += nsuper;
+          // combine the two column halves of the row through shared memory (named barrier of this warpgroup)
+          ex[set * 128 + r] = mx;
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
+          mx = fmaxf(mx, ex[(set ^ 1) * 128 + r]);
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");   // both halves read before the buffer is reused
+          // ---- probabilities -> P tiles (fp16, K-major SWIZZLE_128B), consumed by the P V MMAs
+          float sum = 0.f;
+          for (int sb = 0; sb < nsuper; ++sb, ++sjob) {
+            if (!resident) {
+              mbar_wait(B.sfull + 8 * w, sjob & 1);
+              tc_fence_after();
+            }
+            const int j1 = min(p.nblk, (sb + 1) * ATT_SUPER);
+            for (int j = sb * ATT_SUPER; j < j1; ++j, ++pjob) {
+              const uint32_t pb = pjob & 1;
+              if (warp_live) {
+                const int nv = min(ATT_NB, p.len - j * ATT_NB) - cb;
+                uint32_t pk[16];
+                if (nv > 0) {
+                  uint32_t v[32];
+                  tmem_ld_32x32b_x32(t_base + (j - sb * ATT_SUPER) * ATT_NB + cb, v);
+                  tmem_ld_wait();
+#pragma unroll
                   for (int i = 0; i < 16; ++i) {
-                    const float a = (2 * i < nv) ? __uint_as_float(v[2 * i]) - mx : -60000.f;
-                    const float b = (2 * i + 1 < nv) ? __uint_as_float(v[2 * i + 1]) - mx : -60000.f;
-                    pk[i] = ex2_f16x2(a, b);   // 2^-60000 flushes to +0
+                    float e0 = ex2_fast(__uint_as_float(v[2 * i]) - mx);
+                    float e1 = ex2_fast(__uint_as_float(v[2 * i + 1]) - mx);
+                    if (nv < 32) {
+                      e0 = (2 * i < nv) ? e0 : 0.f;
+                      e1 = (2 * i + 1 < nv) ? e1 : 0.f;
+                    }
+                    sum += e0 + e1;
+                    const __half2 h2 = __floats2half2_rn(e0, e1);
+                    pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
                   }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                }
+                // the P buffer of two blocks ago must have been consumed by its P V MMAs
+                mbar_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
+                const uint32_t sPw = sP + (w * 2 + pb) * 16384;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const uint32_t a0 = sPw + sw128_offset((uint32_t)r, (uint32_t)(cb >> 3) + c);
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
+                               "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
                 }
               } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                mbar_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
               }
-              // the P buffer of two blocks ago must have been consumed by its P V MMAs
-              mbar_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
-              const uint32_t sPw = sP + (w * 2 + pb) * 16384;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const uint32_t a0 = sPw + sw128_offset((uint32_t)r, (uint32_t)(cb >> 3) + c);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
-                             "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+              if (j == j1 - 1) {   // last block of the super-block: the S region may be overwritten
+                tc_fence_before();
+                mbar_arrive(B.sfree + 8 * w);
               }
-            } else {
-              mbar_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
+              fence_proxy_async();
+              mbar_arrive(B.pfull + 8 * (w * 2 + pb));
             }
-            tc_fence_before();
-            mbar_arrive(B.sfree + 8 * (w * 3 + slot));
-            fence_proxy_async();
-            mbar_arrive(B.pfull + 8 * (w * 2 + pb));
           }
-          // ---- O = sum_j P_j V_j and the row sums (P x ones) complete; this thread stores HD/2 features
+          // row sums: combine the two column halves
+          ex[set * 128 + r] = sum;
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
+          sum += ex[(set ^ 1) * 128 + r];
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
+          // ---- O = sum_j P_j V_j complete; this thread stores HD/2 features of its row
           mbar_wait(B.ofull + 8 * w, ohead & 1);
           ++ohead;
           tc_fence_after();
-          uint32_t o[HD / 2], sm[8];
+          uint32_t o[HD / 2];
           if constexpr (HD == 32) tmem_ld_32x32b_x16(t_base + ATT_O_COL + set * 16, o);
           else tmem_ld_32x32b_x8(t_base + ATT_O_COL + set * 8, o);
-          tmem_ld_32x32b_x8(t_base + ATT_SUM_COL, sm);
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(B.ofree + 8 * w);
           if (qi < p.len) {
-            const float inv = 1.f / __uint_as_float(sm[0]);
+            const float inv = 1.f / sum;
             uint4* dst = reinterpret_cast<uint4*>(p.out + p.map.row(g, qi) * p.N + head * HD + set * (HD / 2));
 #pragma unroll
             for (int c = 0; c < HD / 16; ++c) {
@@ -465,7 +460,7 @@ static int tc_attention_launch(const __half* qkv, __half* out, SeqMap map, int m
   a.nblk = (a.len + ATT_NB - 1) / ATT_NB;
   a.mtiles = (a.len + 127) / 128;
   a.num_items = map.G * a.groups;
-  const size_t smem = 2 * 16384 + 4 * 16384 + 8192 + 3 * (size_t)a.nblk * ATT_NB * 128 + 512 + 2048;
+  const size_t smem = 2 * 16384 + 4 * 16384 + 3 * (size_t)a.nblk * ATT_NB * 128 + 512 + 2048;
   if (smem > 227 * 1024) return 0;   // not handled: caller falls back
   CUtensorMap tmQ, tmKV;
   const long long tok = (long long)B * S * C;

@@ -8,10 +8,11 @@
 // Work item = (sequence, 64-feature head group): the Q/K/V tiles of a head group are 128-byte rows, i.e. plain
 // SWIZZLE_128B TMA tiles; a head is a 16/32-column K-slice of them.  One persistent CTA per SM:
 //   warp 0        TMA producer (K and V of the item once, Q per 128-query tile, double buffered)
-//   warp 1        MMA issuer: S = Q K^T (M=128, N=kv block, K=hd) and O += P V (M=128, N=hd, K=kv block)
-//   warps 2..9    softmax warpgroup 0  (heads [0, HPT/2) of the group): two warps per TMEM lane quadrant, each
+//   warps 1,2     MMA issuers, one per softmax warpgroup (decoupled pipelines): S = Q K^T (M=128, N<=192, K=hd)
+//                 and O += P V (M=128, N=hd, K=64 per kv block)
+//   warps 3..10   softmax warpgroup 0  (heads [0, HPT/2) of the group): two warps per TMEM lane quadrant, each
 //                 thread owns one query row and one 32-column half of every 64-column S block
-//   warps 10..17  softmax warpgroup 1  (heads [HPT/2, HPT))
+//   warps 11..18  softmax warpgroup 1  (heads [HPT/2, HPT))
 // Each warpgroup owns an S slot and an O accumulator in TMEM and a P tile in shared memory, so the two
 // heads' MMAs and exponentials overlap.  Sequences longer than one kv block use an exact two-pass softmax
 // (pass A: row max over all blocks, pass B: exp / P V accumulation) - no accumulator rescaling.
@@ -104,7 +105,7 @@ struct TcAttnArgs {
   __half* out;    // (tokens, N)
 };
 
-constexpr int ATT_THREADS = 576;        // producer + MMA warps, 2 warpgroups x 8 softmax warps
+constexpr int ATT_THREADS = 608;        // producer warp, 2 MMA warps (one per warpgroup), 2 x 8 softmax warps
 constexpr int ATT_NB = 64;             // kv rows per block = one SWIZZLE_128B k-block of the P tile
 constexpr int ATT_SUPER = 3;           // 64-row kv blocks per S job: one N <= 192 MMA fills the whole S region
 constexpr uint32_t ATT_WG_COLS = 256;  // TMEM columns per warpgroup: 192 (S region) + 32 (O)
@@ -169,10 +170,10 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
   const int nsuper = (p.nblk + ATT_SUPER - 1) / ATT_SUPER;
 
   if (threadIdx.x == 0) {
-    mbar_init(B.vfull, 1); mbar_init(B.vfree, 1);
+    mbar_init(B.vfull, 1); mbar_init(B.vfree, 2);      // "free" barriers: one commit from each MMA warp
     for (int i = 0; i < 2; ++i) {
-      mbar_init(B.kfull + 8 * i, 1); mbar_init(B.kfree + 8 * i, 1);
-      mbar_init(B.qfull + 8 * i, 1); mbar_init(B.qfree + 8 * i, 1);
+      mbar_init(B.kfull + 8 * i, 1); mbar_init(B.kfree + 8 * i, 2);
+      mbar_init(B.qfull + 8 * i, 1); mbar_init(B.qfree + 8 * i, 2);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(B.sfull + 8 * i, 1); mbar_init(B.sfree + 8 * i, 256); }
     for (int i = 0; i < 4; ++i) { mbar_init(B.pfull + 8 * i, 256); mbar_init(B.pfree + 8 * i, 1); }
@@ -224,11 +225,12 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
+  } else if (warp == 1 || warp == 2) {
+    // ---------------------------------------------------------------- MMA issuer (warp 1 -> warpgroup 0, warp 2 -> 1)
     // Small tcgen05.mma instructions cost a fixed ~100+ cycles each, so the instruction count is what matters:
     // S uses one N = 64..192 MMA per 16-wide K step for a whole super-block, P V needs kv/16 MMAs of N = hd.
     if (lane == 0) {
+      const int w = warp - 1;
       const uint32_t idesc_o = idesc_f16(128, HD, 0) | (1u << 16);     // B (= V) is MN-major
       // a "group" = one (item, query tile, head-of-warpgroup); both warpgroups run the same group sequence
       struct Cur { int item, it, m, qn, hh; bool valid; };
@@ -246,7 +248,7 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
         if (q_seen != c.qn) { mbar_wait(B.qfull + 8 * (c.qn & 1), (c.qn >> 1) & 1); q_seen = c.qn; }
         const int nb = min(ATT_SUPER, p.nblk - sb * ATT_SUPER);
         const uint32_t idesc_s = idesc_f16(128, nb * ATT_NB, 0);
-        for (int w = 0; w < 2; ++w) {
+        {
           const int hsel = w * HPW + c.hh;
           mbar_wait(B.sfree + 8 * w, (sjob & 1) ^ 1);
           tc_fence_after();
@@ -269,7 +271,7 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
       auto issue_pv = [&](const Cur& c, int j) {
         if (v_seen != c.it) { mbar_wait(B.vfull, c.it & 1); v_seen = c.it; }
         const uint32_t pb = pjob & 1;
-        for (int w = 0; w < 2; ++w) {
+        {
           const int hsel = w * HPW + c.hh;
           if (j == 0) mbar_wait(B.ofree + 8 * w, (ohead & 1) ^ 1);     // previous O of this warpgroup read out
           mbar_wait(B.pfull + 8 * (w * 2 + pb), (pjob >> 1) & 1);
@@ -309,7 +311,7 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
     __syncwarp();
   } else {
     // ---------------------------------------------------------------- softmax warpgroups
-    const int sw = warp - 2;
+    const int sw = warp - 3;
     const int w = sw >> 3;                       // warpgroup
     const int set = (sw >> 2) & 1;               // which 32-column half of each 64-column kv block this thread owns
     const int q = warp & 3;                      // TMEM lane quadrant of this warp

@@ -67,7 +67,7 @@ __device__ __forceinline__ float tanh_fast(float x) {
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
 template <int NFEAT>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(104)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
 k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapW, TcLstmArgs p) {
   using L = TcLstmSmem<NFEAT>;
   extern __shared__ __align__(1024) unsigned char smem[];

@@ -14,8 +14,8 @@
 // The 512 gate columns are processed as 4 chunks of 128 columns = 32 hidden units x (i,f,g,o), so that
 // the gate math of chunk c overlaps the MMAs of the other chunks and the x-part of step t+1.
 //
-// Warp roles (576 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA) + TMEM allocator,
-// warps 2..17 gate math (four warps per TMEM lane quadrant; thread = sequence row x 8 hidden units per chunk).
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA) + TMEM allocator,
+// warps 2..9 gate math (thread = sequence row, 16 hidden units per chunk).
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tc_kernels.cuh"
@@ -25,7 +25,7 @@ namespace vatss {
 using namespace ptx;
 
 constexpr int LSTM_H = 128;
-constexpr int LSTM_THREADS = 576;      // producer + MMA warps, 16 gate-math warps
+constexpr int LSTM_THREADS = 320;
 constexpr int LSTM_CHUNKS = 4;          // 4 x (32 units x 4 gates) = 512 accumulator columns
 constexpr int LSTM_UNITS_PER_CHUNK = 32;
 
@@ -101,17 +101,14 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
     }
     for (int c = 0; c < LSTM_CHUNKS; ++c) {
       mbar_init(bar_accfull + 8 * c, 1);
-      mbar_init(bar_accempty + 8 * c, 32);  // 16 gate warps x 2 CTAs
+      mbar_init(bar_accempty + 8 * c, 2);   // one arrival per CTA (gate warps first meet at a named barrier)
     }
-    mbar_init(bar_hfull, 32);
+    mbar_init(bar_hfull, 2);
     fence_mbar_init();
     prefetch_tmap(&tmapX);
     prefetch_tmap(&tmapW);
   }
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
-    const int gate = (i & 127) >> 5;   // column order inside a chunk: i, f, g, o x 32 units
-    sBias[i] = p.bias[dir * 512 + i] * (gate == 2 ? 1.f : 0.5f);
-  }
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) sBias[i] = p.bias[dir * 512 + i];
   // clean operand buffers: rows that no TMA box covers must not hold NaN bit patterns
   for (int i = threadIdx.x; i < (2 * L::X_STAGE + L::H_BYTES) / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(smem + L::OFF_X)[i] = make_uint4(0, 0, 0, 0);
@@ -230,7 +227,7 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
     // ------------------------------------------------------------------ gate math
     const int gw = warp - 2;
     const int q = warp & 3;            // TMEM lane quadrant this warp may touch
-    const int quarter = gw >> 2;       // which 8 of the chunk's 32 units
+    const int half = gw >> 2;          // which 16 of the chunk's 32 units
     const int r = q * 32 + lane;       // sequence row inside the tile
     // global output row of this sequence at time t: row_base + t * row_tstride (or invalid)
     long long row_base = 0, row_tstride = 0;
@@ -247,81 +244,81 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
       row_tstride = p.C;
     }
     const int ldo = p.ndir * LSTM_H;
-    float cst[LSTM_CHUNKS][8];
+    float cst[LSTM_CHUNKS][16];
 #pragma unroll
     for (int c = 0; c < LSTM_CHUNKS; ++c)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) cst[c][j] = 0.f;
+      for (int j = 0; j < 16; ++j) cst[c][j] = 0.f;
     uint32_t accempty_leader[LSTM_CHUNKS], hfull_leader;
 #pragma unroll
     for (int c = 0; c < LSTM_CHUNKS; ++c)
       asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(accempty_leader[c]) : "r"(bar_accempty + 8 * c));
     asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(hfull_leader) : "r"(bar_hfull));
+
     for (int step = 0; step < len; ++step) {
       const int t = dir == 0 ? step : len - 1 - step;
-      uint32_t hp[LSTM_CHUNKS][4];   // packed fp16 h of this step (kept until all h-part MMAs have read sH)
-      __half* orow = p.out + (row_base + (long long)t * row_tstride) * ldo + dir * LSTM_H + quarter * 8;
+      uint32_t hp[LSTM_CHUNKS][8];   // packed fp16 h of this step (kept until all h-part MMAs have read sH)
 #pragma unroll
       for (int c = 0; c < LSTM_CHUNKS; ++c) {
         mbar_wait(bar_accfull + 8 * c, step & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + c * 128 + quarter * 8;
-        uint32_t gi[8], gf[8], gg[8], go[8];
-        tmem_ld_32x32b_x8(taddr + 0, gi);
-        tmem_ld_32x32b_x8(taddr + 32, gf);
-        tmem_ld_32x32b_x8(taddr + 64, gg);
-        tmem_ld_32x32b_x8(taddr + 96, go);
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + c * 128 + half * 16;
+        uint32_t gi[16], gf[16], gg[16], go[16];
+        tmem_ld_32x32b_x16(taddr + 0, gi);
+        tmem_ld_32x32b_x16(taddr + 32, gf);
+        tmem_ld_32x32b_x16(taddr + 64, gg);
+        tmem_ld_32x32b_x16(taddr + 96, go);
         tmem_ld_wait();
         // accumulator chunk drained -> the MMA warp may start the next step's x-part into it
         tc_fence_before();
-        __syncwarp();
-        if (lane == 0)
+        // remote mbarrier arrivals are expensive: the 8 gate warps meet at a CTA-local named barrier and one
+        // thread signals the leader
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (gw == 0 && lane == 0)
           asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(accempty_leader[c]) : "memory");
-        // biases: broadcast float4 reads from shared memory (pre-halved for the sigmoid gates at load time)
-        float bi[8], bf[8], bg[8], bo[8];
-        {
-          const float4* b4 = reinterpret_cast<const float4*>(sBias + c * 128 + quarter * 8);
-          const float4 i0 = b4[0], i1 = b4[1], f0 = b4[8], f1 = b4[9], g0 = b4[16], g1 = b4[17], o0 = b4[24], o1 = b4[25];
-          bi[0] = i0.x; bi[1] = i0.y; bi[2] = i0.z; bi[3] = i0.w; bi[4] = i1.x; bi[5] = i1.y; bi[6] = i1.z; bi[7] = i1.w;
-          bf[0] = f0.x; bf[1] = f0.y; bf[2] = f0.z; bf[3] = f0.w; bf[4] = f1.x; bf[5] = f1.y; bf[6] = f1.z; bf[7] = f1.w;
-          bg[0] = g0.x; bg[1] = g0.y; bg[2] = g0.z; bg[3] = g0.w; bg[4] = g1.x; bg[5] = g1.y; bg[6] = g1.z; bg[7] = g1.w;
-          bo[0] = o0.x; bo[1] = o0.y; bo[2] = o0.z; bo[3] = o0.w; bo[4] = o1.x; bo[5] = o1.y; bo[6] = o1.z; bo[7] = o1.w;
-        }
-        float hv[8];
+        const float* bc = sBias + c * 128 + half * 16;
+        float hv[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          // sigmoid(x) = 0.5 tanh(0.5 x) + 0.5 with the halved bias folded in
-          const float ig = fmaf(0.5f, tanh_fast(fmaf(0.5f, __uint_as_float(gi[j]), bi[j])), 0.5f);
-          const float fg = fmaf(0.5f, tanh_fast(fmaf(0.5f, __uint_as_float(gf[j]), bf[j])), 0.5f);
-          const float g_ = tanh_fast(__uint_as_float(gg[j]) + bg[j]);
-          const float og = fmaf(0.5f, tanh_fast(fmaf(0.5f, __uint_as_float(go[j]), bo[j])), 0.5f);
+        for (int j = 0; j < 16; ++j) {
+          const float ig = sigmoid_fast(__uint_as_float(gi[j]) + bc[j]);
+          const float fg = sigmoid_fast(__uint_as_float(gf[j]) + bc[32 + j]);
+          const float g_ = tanh_fast(__uint_as_float(gg[j]) + bc[64 + j]);
+          const float og = sigmoid_fast(__uint_as_float(go[j]) + bc[96 + j]);
           const float cc = fmaf(fg, cst[c][j], ig * g_);
           cst[c][j] = cc;
           hv[j] = og * tanh_fast(cc);
         }
-        uint32_t ho[4];
+        uint32_t ho[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const __half2 a = __floats2half2_rn(hv[2 * j], hv[2 * j + 1]);
           hp[c][j] = *reinterpret_cast<const uint32_t*>(&a);
           const __half2 o = p.act ? __floats2half2_rn(fmaxf(hv[2 * j], 0.f), fmaxf(hv[2 * j + 1], 0.f)) : a;
           ho[j] = *reinterpret_cast<const uint32_t*>(&o);
         }
-        if (valid) *reinterpret_cast<uint4*>(orow + c * LSTM_UNITS_PER_CHUNK) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (row_base + (long long)t * row_tstride) * ldo + dir * LSTM_H +
+                                                c * LSTM_UNITS_PER_CHUNK + half * 16);
+          dst[0] = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+          dst[1] = make_uint4(ho[4], ho[5], ho[6], ho[7]);
+        }
       }
       // acc_full of the last chunk implies every h-part MMA of this step has finished reading sH
       if (step + 1 < len) {
 #pragma unroll
         for (int c = 0; c < LSTM_CHUNKS; ++c) {
-          const int k = c * LSTM_UNITS_PER_CHUNK + quarter * 8;   // hidden-unit index = K index of the h operand
+          const int k = c * LSTM_UNITS_PER_CHUNK + half * 16;   // hidden-unit index = K index of the h operand
           const int kb = k >> 6, ch = (k & 63) >> 3;
           const uint32_t a0 = sH + kb * 16384 + sw128_offset((uint32_t)r, (uint32_t)ch);
+          const uint32_t a1 = sH + kb * 16384 + sw128_offset((uint32_t)r, (uint32_t)ch + 1);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(hp[c][0]), "r"(hp[c][1]),
                        "r"(hp[c][2]), "r"(hp[c][3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(hp[c][4]), "r"(hp[c][5]),
+                       "r"(hp[c][6]), "r"(hp[c][7]) : "memory");
         }
         fence_proxy_async();
-        __syncwarp();
-        if (lane == 0)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (gw == 0 && lane == 0)
           asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(hfull_leader) : "memory");
       }
     }

@@ -101,9 +101,9 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
     }
     for (int c = 0; c < LSTM_CHUNKS; ++c) {
       mbar_init(bar_accfull + 8 * c, 1);
-      mbar_init(bar_accempty + 8 * c, 2);   // one arrival per CTA (gate warps first meet at a named barrier)
+      mbar_init(bar_accempty + 8 * c, 16);  // 8 gate warps x 2 CTAs
     }
-    mbar_init(bar_hfull, 2);
+    mbar_init(bar_hfull, 16);
     fence_mbar_init();
     prefetch_tmap(&tmapX);
     prefetch_tmap(&tmapW);
@@ -271,10 +271,8 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
         tmem_ld_wait();
         // accumulator chunk drained -> the MMA warp may start the next step's x-part into it
         tc_fence_before();
-        // remote mbarrier arrivals are expensive: the 8 gate warps meet at a CTA-local named barrier and one
-        // thread signals the leader
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (gw == 0 && lane == 0)
+        __syncwarp();
+        if (lane == 0)
           asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(accempty_leader[c]) : "memory");
         const float* bc = sBias + c * 128 + half * 16;
         float hv[16];
@@ -317,8 +315,8 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
                        "r"(hp[c][6]), "r"(hp[c][7]) : "memory");
         }
         fence_proxy_async();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (gw == 0 && lane == 0)
+        __syncwarp();
+        if (lane == 0)
           asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(hfull_leader) : "memory");
       }
     }

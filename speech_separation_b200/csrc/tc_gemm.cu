@@ -5,7 +5,8 @@
 // Persistent kernel, one CTA per SM, warp-specialised:
 //   warp 0      TMA producer   (W once, then a 2-stage ring of 128-row A tiles)
 //   warp 1      MMA issuer     (one thread; tcgen05.mma kind::f16, M=128, N<=256, fp32 accum in TMEM)
-//   warps 2..5  epilogue       (tcgen05.ld, thread = output row; bias / residual / LayerNorm / casts)
+//   warps 2..9  epilogue       (tcgen05.ld; thread = output row x half of the columns, the two halves of a row
+//                               combine their LayerNorm statistics through shared memory)
 // K is only 64..256 here, so a whole K extent of A and all of W fit in shared memory: no K pipeline,
 // W is read from HBM/L2 once per CTA and A exactly once per forward.  These GEMMs are HBM-bound
 // (AI ~ 96 flop/B < ridge ~ 255), hence everything that can be folded into the epilogue is.
@@ -89,7 +90,7 @@ struct TcGemmArgs {
   const float* prelu_a;
 };
 
-constexpr int TCG_THREADS = 192;
+constexpr int TCG_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
 
 template <int NOUT, int KDIM>
 struct TcGemmSmem {
@@ -100,7 +101,8 @@ struct TcGemmSmem {
   static constexpr int OFF_A = OFF_W + W_BYTES;
   static constexpr int OFF_PAR = OFF_A + 2 * A_STAGE_BYTES;  // bias, ln_w, ln_b
   static constexpr int OFF_BAR = OFF_PAR + 3 * NOUT * 4;
-  static constexpr int TOTAL = OFF_BAR + 128 + 1024;  // + alignment slack
+  static constexpr int OFF_EX = OFF_BAR + 128;           // LayerNorm statistics exchange: [2 halves][128 rows] float2
+  static constexpr int TOTAL = OFF_EX + 2048 + 1024;  // + alignment slack
   static constexpr int ACC_STAGES = (2 * NOUT <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = (ACC_STAGES * NOUT <= 32)    ? 32
                                    : (ACC_STAGES * NOUT <= 64)  ? 64
@@ -134,7 +136,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
       mbar_init(bar_afull + 8 * s, 1);
       mbar_init(bar_aempty + 8 * s, 1);
       mbar_init(bar_accfull + 8 * s, 1);
-      mbar_init(bar_accempty + 8 * s, 128);
+      mbar_init(bar_accempty + 8 * s, 256);
     }
     fence_mbar_init();
     prefetch_tmap(&tmapA);
@@ -199,29 +201,34 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (thread = row)
+    // ------------------------------------------------------------------ epilogue (thread = row x column half)
+    constexpr int NH = NOUT / 2;                 // columns per thread
+    static_assert(NH % 32 == 0, "column half must be a multiple of the 32-column TMEM load");
     const int q = warp & 3;
-    const float* sBias = sPar;
-    const float* sLw = sPar + NOUT;
-    const float* sLb = sPar + 2 * NOUT;
+    const int half = (warp - 2) >> 2;
+    const int cl = half * NH;
+    const float* sBias = sPar + cl;
+    const float* sLw = sPar + NOUT + cl;
+    const float* sLb = sPar + 2 * NOUT + cl;
+    float2* sEx = reinterpret_cast<float2*>(gen + L::OFF_EX);
     const float slope = (p.act16 == 2 && p.prelu_a) ? p.prelu_a[0] : 0.f;
     int i = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
       const int as = i % L::ACC_STAGES, aph = (i / L::ACC_STAGES) & 1;
-      mbar_wait(bar_accfull + 8 * as, aph);
-      tc_fence_after();
       const long long row = (long long)tile * 128 + q * 32 + lane;
       const bool live = row < p.M;
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + as * NOUT;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + as * NOUT + cl;
       if constexpr (EPI == TC_EPI_F16 || EPI == TC_EPI_F32) {
+        mbar_wait(bar_accfull + 8 * as, aph);
+        tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < NOUT; c0 += 32) {
+        for (int c0 = 0; c0 < NH; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c0, r);
           tmem_ld_wait();
           if (live) {
             if constexpr (EPI == TC_EPI_F16) {
-              uint4* dst = reinterpret_cast<uint4*>(p.out16 + row * p.ldo16 + c0);
+              uint4* dst = reinterpret_cast<uint4*>(p.out16 + row * p.ldo16 + cl + c0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint32_t w[4];
@@ -235,8 +242,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
                 dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
               }
             } else {
-              float4* dst = reinterpret_cast<float4*>(p.out32 + row * p.ldo32 + c0);
-              const float4* rs = p.res ? reinterpret_cast<const float4*>(p.res + row * p.ldr + c0) : nullptr;
+              float4* dst = reinterpret_cast<float4*>(p.out32 + row * p.ldo32 + cl + c0);
+              const float4* rs = p.res ? reinterpret_cast<const float4*>(p.res + row * p.ldr + cl + c0) : nullptr;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 float4 v;
@@ -254,52 +261,68 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
           }
         }
       } else {
-        // LayerNorm over the whole row held in registers
-        float v[NOUT];
+        // LayerNorm: this thread holds NH columns of its row; the residual is fetched before the accumulator
+        // is waited for (it does not depend on the MMA)
+        float v[NH];
+        const float4* rs = reinterpret_cast<const float4*>(p.res + (live ? row : 0) * p.ldr + cl);
+        if constexpr (EPI == TC_EPI_LN) {
 #pragma unroll
-        for (int c0 = 0; c0 < NOUT; c0 += 32) {
+          for (int j = 0; j < NH / 4; ++j) {
+            const float4 x = rs[j];
+            v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+          }
+        }
+        mbar_wait(bar_accfull + 8 * as, aph);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < NH; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c0, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[c0 + j] = __uint_as_float(r[j]) + sBias[c0 + j];
+          for (int j = 0; j < 32; ++j) {
+            const float a = __uint_as_float(r[j]) + sBias[c0 + j];
+            if constexpr (EPI == TC_EPI_LN) v[c0 + j] += a;   // LN(. + res)
+            else v[c0 + j] = a;                               // LN(.) + res: residual added after the norm
+          }
         }
+        float sum = 0.f;
+        // local statistics over NH columns, then Chan's combination with the other half of the row
+#pragma unroll
+        for (int j = 0; j < NH; ++j) sum += v[j];
+        const float m_loc = sum * (1.f / NH);
+        float m2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NH; ++j) {
+          const float d = v[j] - m_loc;
+          m2 = fmaf(d, d, m2);
+        }
+        const int rr = q * 32 + lane;
+        sEx[half * 128 + rr] = make_float2(m_loc, m2);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float2 o = sEx[(half ^ 1) * 128 + rr];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float mean = 0.5f * (m_loc + o.x);
+        const float dm = m_loc - o.x;
+        const float var = (m2 + o.y + dm * dm * (0.5f * NH)) * (1.f / NOUT);
+        const float rstd = rsqrtf(var + 1e-5f);
         if (live) {
-          const float4* rs = reinterpret_cast<const float4*>(p.res + row * p.ldr);
-          if constexpr (EPI == TC_EPI_LN) {
 #pragma unroll
-            for (int j = 0; j < NOUT / 4; ++j) {
-              const float4 x = rs[j];
-              v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
-            }
-          }
-          float sum = 0.f;
-#pragma unroll
-          for (int j = 0; j < NOUT; ++j) sum += v[j];
-          const float mean = sum * (1.f / NOUT);
-          float sq = 0.f;
-#pragma unroll
-          for (int j = 0; j < NOUT; ++j) {
-            const float d = v[j] - mean;
-            sq = fmaf(d, d, sq);
-          }
-          const float rstd = rsqrtf(sq * (1.f / NOUT) + 1e-5f);
-#pragma unroll
-          for (int j = 0; j < NOUT; ++j) v[j] = (v[j] - mean) * rstd * sLw[j] + sLb[j];
+          for (int j = 0; j < NH; ++j) v[j] = (v[j] - mean) * rstd * sLw[j] + sLb[j];
           if constexpr (EPI == TC_EPI_LN_POST) {
 #pragma unroll
-            for (int j = 0; j < NOUT / 4; ++j) {
+            for (int j = 0; j < NH / 4; ++j) {
               const float4 x = rs[j];
               v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
             }
           }
-          float4* d32 = reinterpret_cast<float4*>(p.out32 + row * p.ldo32);
+          float4* d32 = reinterpret_cast<float4*>(p.out32 + row * p.ldo32 + cl);
 #pragma unroll
-          for (int j = 0; j < NOUT / 4; ++j) d32[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < NH / 4; ++j) d32[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           if (p.out16) {
-            uint4* d16 = reinterpret_cast<uint4*>(p.out16 + row * p.ldo16);
+            uint4* d16 = reinterpret_cast<uint4*>(p.out16 + row * p.ldo16 + cl);
 #pragma unroll
-            for (int j = 0; j < NOUT / 8; ++j) {
+            for (int j = 0; j < NH / 8; ++j) {
               uint32_t w[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {

@@ -5,8 +5,8 @@
 // Persistent kernel, one CTA per SM, warp-specialised:
 //   warp 0      TMA producer   (W once, then a 2-stage ring of 128-row A tiles)
 //   warp 1      MMA issuer     (one thread; tcgen05.mma kind::f16, M=128, N<=256, fp32 accum in TMEM)
-//   warps 2..9  epilogue       (tcgen05.ld; thread = output row x half of the columns, the two halves of a row
-//                               combine their LayerNorm statistics through shared memory)
+//   warps 2..5  epilogue       (tcgen05.ld, thread = output row; all global traffic is staged through a
+//                               per-warp shared-memory tile so that every warp instruction touches whole lines)
 // K is only 64..256 here, so a whole K extent of A and all of W fit in shared memory: no K pipeline,
 // W is read from HBM/L2 once per CTA and A exactly once per forward.  These GEMMs are HBM-bound
 // (AI ~ 96 flop/B < ridge ~ 255), hence everything that can be folded into the epilogue is.
@@ -90,7 +90,7 @@ struct TcGemmArgs {
   const float* prelu_a;
 };
 
-constexpr int TCG_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
+constexpr int TCG_THREADS = 192;   // TMA warp, MMA warp, 4 epilogue warps
 
 template <int NOUT, int KDIM>
 struct TcGemmSmem {
@@ -101,8 +101,8 @@ struct TcGemmSmem {
   static constexpr int OFF_A = OFF_W + W_BYTES;
   static constexpr int OFF_PAR = OFF_A + 2 * A_STAGE_BYTES;  // bias, ln_w, ln_b
   static constexpr int OFF_BAR = OFF_PAR + 3 * NOUT * 4;
-  static constexpr int OFF_EX = OFF_BAR + 128;           // LayerNorm statistics exchange: [2 halves][128 rows] float2
-  static constexpr int TOTAL = OFF_EX + 2048 + 1024;  // + alignment slack
+  static constexpr int OFF_STAGE = OFF_BAR + 128;        // per epilogue warp: [32 rows][36 floats] transpose tile
+  static constexpr int TOTAL = OFF_STAGE + 4 * 32 * 36 * 4 + 1024;  // + alignment slack
   static constexpr int ACC_STAGES = (2 * NOUT <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = (ACC_STAGES * NOUT <= 32)    ? 32
                                    : (ACC_STAGES * NOUT <= 64)  ? 64
@@ -110,6 +110,62 @@ struct TcGemmSmem {
                                    : (ACC_STAGES * NOUT <= 256) ? 256
                                                                 : 512;
 };
+
+// ---- warp-level staged global access: a warp owns 32 consecutive rows; thread = row in registers, but every
+// global instruction is row-contiguous (8 rows x 128 B for fp32 chunks of 32 columns).
+constexpr int STG_LD = 36;   // padded row pitch (floats) of the staging tile: conflict-free for both access patterns
+
+// v[32] += / = g[row lane][0..31]
+template <bool ACCUM>
+__device__ __forceinline__ void staged_load_f32(const float* __restrict__ g, long long ld, int rows_valid, float* stage,
+                                                int lane, float* v) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 3);
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows_valid) x = *reinterpret_cast<const float4*>(g + (long long)r * ld + (lane & 7) * 4);
+    *reinterpret_cast<float4*>(stage + r * STG_LD + (lane & 7) * 4) = x;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 x = *reinterpret_cast<const float4*>(stage + lane * STG_LD + 4 * j);
+    if (ACCUM) { v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w; }
+    else { v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w; }
+  }
+  __syncwarp();
+}
+// g[row lane][0..31] = v[32]
+__device__ __forceinline__ void staged_store_f32(float* __restrict__ g, long long ld, int rows_valid, float* stage, int lane,
+                                                 const float* v) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stage + lane * STG_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 3);
+    const float4 x = *reinterpret_cast<const float4*>(stage + r * STG_LD + (lane & 7) * 4);
+    if (r < rows_valid) *reinterpret_cast<float4*>(g + (long long)r * ld + (lane & 7) * 4) = x;
+  }
+  __syncwarp();
+}
+// g16[row lane][0..31] = half(pk) where pk[16] holds the row's 32 values as packed half2 (64 B per row)
+__device__ __forceinline__ void staged_store_f16(__half* __restrict__ g, long long ld, int rows_valid, float* stage, int lane,
+                                                 const uint32_t* pk) {
+  uint32_t* st = reinterpret_cast<uint32_t*>(stage);   // row pitch 20 words
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(st + lane * 20 + 4 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    const uint4 x = *reinterpret_cast<const uint4*>(st + r * 20 + (lane & 3) * 4);
+    if (r < rows_valid) *reinterpret_cast<uint4*>(g + (long long)r * ld + (lane & 3) * 8) = x;
+  }
+  __syncwarp();
+}
 
 template <int NOUT, int KDIM, int EPI>
 __global__ void __launch_bounds__(TCG_THREADS, 1)
@@ -136,7 +192,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
       mbar_init(bar_afull + 8 * s, 1);
       mbar_init(bar_aempty + 8 * s, 1);
       mbar_init(bar_accfull + 8 * s, 1);
-      mbar_init(bar_accempty + 8 * s, 256);
+      mbar_init(bar_accempty + 8 * s, 128);
     }
     fence_mbar_init();
     prefetch_tmap(&tmapA);
@@ -201,139 +257,97 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (thread = row x column half)
-    constexpr int NH = NOUT / 2;                 // columns per thread
-    static_assert(NH % 32 == 0, "column half must be a multiple of the 32-column TMEM load");
+    // ------------------------------------------------------------------ epilogue (thread = row)
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int cl = half * NH;
-    const float* sBias = sPar + cl;
-    const float* sLw = sPar + NOUT + cl;
-    const float* sLb = sPar + 2 * NOUT + cl;
-    float2* sEx = reinterpret_cast<float2*>(gen + L::OFF_EX);
+    const float* sBias = sPar;
+    const float* sLw = sPar + NOUT;
+    const float* sLb = sPar + 2 * NOUT;
+    float* stage = reinterpret_cast<float*>(gen + L::OFF_STAGE) + (warp - 2) * 32 * STG_LD;
     const float slope = (p.act16 == 2 && p.prelu_a) ? p.prelu_a[0] : 0.f;
     int i = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
       const int as = i % L::ACC_STAGES, aph = (i / L::ACC_STAGES) & 1;
-      const long long row = (long long)tile * 128 + q * 32 + lane;
-      const bool live = row < p.M;
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + as * NOUT + cl;
+      const long long row0 = (long long)tile * 128 + q * 32;          // first row of this warp
+      const long long left = p.M - row0;
+      const int rows_valid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + as * NOUT;
       if constexpr (EPI == TC_EPI_F16 || EPI == TC_EPI_F32) {
         mbar_wait(bar_accfull + 8 * as, aph);
         tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < NH; c0 += 32) {
+        for (int c0 = 0; c0 < NOUT; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c0, r);
           tmem_ld_wait();
-          if (live) {
-            if constexpr (EPI == TC_EPI_F16) {
-              uint4* dst = reinterpret_cast<uint4*>(p.out16 + row * p.ldo16 + cl + c0);
+          if constexpr (EPI == TC_EPI_F16) {
+            uint32_t pk[16];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint32_t w[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int c = j * 8 + e * 2;
-                  const __half2 h = __floats2half2_rn(__uint_as_float(r[c]) + sBias[c0 + c],
-                                                      __uint_as_float(r[c + 1]) + sBias[c0 + c + 1]);
-                  w[e] = *reinterpret_cast<const uint32_t*>(&h);
-                }
-                dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
-              }
-            } else {
-              float4* dst = reinterpret_cast<float4*>(p.out32 + row * p.ldo32 + cl + c0);
-              const float4* rs = p.res ? reinterpret_cast<const float4*>(p.res + row * p.ldr + cl + c0) : nullptr;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 v;
-                v.x = __uint_as_float(r[4 * j + 0]) + sBias[c0 + 4 * j + 0];
-                v.y = __uint_as_float(r[4 * j + 1]) + sBias[c0 + 4 * j + 1];
-                v.z = __uint_as_float(r[4 * j + 2]) + sBias[c0 + 4 * j + 2];
-                v.w = __uint_as_float(r[4 * j + 3]) + sBias[c0 + 4 * j + 3];
-                if (rs) {
-                  const float4 x = rs[j];
-                  v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
-                }
-                dst[j] = v;
-              }
+            for (int j = 0; j < 16; ++j) {
+              const __half2 h = __floats2half2_rn(__uint_as_float(r[2 * j]) + sBias[c0 + 2 * j],
+                                                  __uint_as_float(r[2 * j + 1]) + sBias[c0 + 2 * j + 1]);
+              pk[j] = *reinterpret_cast<const uint32_t*>(&h);
             }
+            staged_store_f16(p.out16 + row0 * p.ldo16 + c0, p.ldo16, rows_valid, stage, lane, pk);
+          } else {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sBias[c0 + j];
+            if (p.res) staged_load_f32<true>(p.res + row0 * p.ldr + c0, p.ldr, rows_valid, stage, lane, v);
+            staged_store_f32(p.out32 + row0 * p.ldo32 + c0, p.ldo32, rows_valid, stage, lane, v);
           }
         }
       } else {
-        // LayerNorm: this thread holds NH columns of its row; the residual is fetched before the accumulator
-        // is waited for (it does not depend on the MMA)
-        float v[NH];
-        const float4* rs = reinterpret_cast<const float4*>(p.res + (live ? row : 0) * p.ldr + cl);
+        // LayerNorm over the whole row held in registers
+        float v[NOUT];
         if constexpr (EPI == TC_EPI_LN) {
+          // the residual does not depend on the MMA: fetch it before waiting for the accumulator
 #pragma unroll
-          for (int j = 0; j < NH / 4; ++j) {
-            const float4 x = rs[j];
-            v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
-          }
+          for (int c0 = 0; c0 < NOUT; c0 += 32)
+            staged_load_f32<false>(p.res + row0 * p.ldr + c0, p.ldr, rows_valid, stage, lane, v + c0);
         }
         mbar_wait(bar_accfull + 8 * as, aph);
         tc_fence_after();
 #pragma unroll
-        for (int c0 = 0; c0 < NH; c0 += 32) {
+        for (int c0 = 0; c0 < NOUT; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c0, r);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float a = __uint_as_float(r[j]) + sBias[c0 + j];
-            if constexpr (EPI == TC_EPI_LN) v[c0 + j] += a;   // LN(. + res)
-            else v[c0 + j] = a;                               // LN(.) + res: residual added after the norm
+            if constexpr (EPI == TC_EPI_LN) v[c0 + j] += a;
+            else v[c0 + j] = a;
           }
         }
         float sum = 0.f;
-        // local statistics over NH columns, then Chan's combination with the other half of the row
 #pragma unroll
-        for (int j = 0; j < NH; ++j) sum += v[j];
-        const float m_loc = sum * (1.f / NH);
-        float m2 = 0.f;
+        for (int j = 0; j < NOUT; ++j) sum += v[j];
+        const float mean = sum * (1.f / NOUT);
+        float sq = 0.f;
 #pragma unroll
-        for (int j = 0; j < NH; ++j) {
-          const float d = v[j] - m_loc;
-          m2 = fmaf(d, d, m2);
+        for (int j = 0; j < NOUT; ++j) {
+          const float d = v[j] - mean;
+          sq = fmaf(d, d, sq);
         }
-        const int rr = q * 32 + lane;
-        sEx[half * 128 + rr] = make_float2(m_loc, m2);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float2 o = sEx[(half ^ 1) * 128 + rr];
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float mean = 0.5f * (m_loc + o.x);
-        const float dm = m_loc - o.x;
-        const float var = (m2 + o.y + dm * dm * (0.5f * NH)) * (1.f / NOUT);
-        const float rstd = rsqrtf(var + 1e-5f);
-        if (live) {
+        const float rstd = rsqrtf(sq * (1.f / NOUT) + 1e-5f);
 #pragma unroll
-          for (int j = 0; j < NH; ++j) v[j] = (v[j] - mean) * rstd * sLw[j] + sLb[j];
-          if constexpr (EPI == TC_EPI_LN_POST) {
+        for (int j = 0; j < NOUT; ++j) v[j] = (v[j] - mean) * rstd * sLw[j] + sLb[j];
 #pragma unroll
-            for (int j = 0; j < NH / 4; ++j) {
-              const float4 x = rs[j];
-              v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
-            }
-          }
-          float4* d32 = reinterpret_cast<float4*>(p.out32 + row * p.ldo32 + cl);
-#pragma unroll
-          for (int j = 0; j < NH / 4; ++j) d32[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int c0 = 0; c0 < NOUT; c0 += 32) {
+          if constexpr (EPI == TC_EPI_LN_POST)
+            staged_load_f32<true>(p.res + row0 * p.ldr + c0, p.ldr, rows_valid, stage, lane, v + c0);
+          staged_store_f32(p.out32 + row0 * p.ldo32 + c0, p.ldo32, rows_valid, stage, lane, v + c0);
           if (p.out16) {
-            uint4* d16 = reinterpret_cast<uint4*>(p.out16 + row * p.ldo16 + cl);
+            uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < NH / 8; ++j) {
-              uint32_t w[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
-                if (p.act16 == 1) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                else if (p.act16 == 2) { a = a >= 0.f ? a : slope * a; b = b >= 0.f ? b : slope * b; }
-                const __half2 h = __floats2half2_rn(a, b);
-                w[e] = *reinterpret_cast<const uint32_t*>(&h);
-              }
-              d16[j] = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int j = 0; j < 16; ++j) {
+              float a = v[c0 + 2 * j], b = v[c0 + 2 * j + 1];
+              if (p.act16 == 1) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+              else if (p.act16 == 2) { a = a >= 0.f ? a : slope * a; b = b >= 0.f ? b : slope * b; }
+              const __half2 h = __floats2half2_rn(a, b);
+              pk[j] = *reinterpret_cast<const uint32_t*>(&h);
             }
+            staged_store_f16(p.out16 + row0 * p.ldo16 + c0, p.ldo16, rows_valid, stage, lane, pk);
           }
         }
       }

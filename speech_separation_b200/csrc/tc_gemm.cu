@@ -112,7 +112,7 @@ struct TcGemmSmem {
 };
 
 // ---- warp-level staged global access: a warp owns 32 consecutive rows; thread = row in registers, but every
-// global instruction is row-contiguous (8 rows x 128 B for fp32 chunks of 32 columns).
+// global instruction is row-contiguous (4 rows x 128 B for fp32 chunks of 32 columns, 8 rows x 64 B for fp16).
 constexpr int STG_LD = 36;   // padded row pitch (floats) of the staging tile: conflict-free for both access patterns
 
 // v[32] += / = g[row lane][0..31]
@@ -120,8 +120,8 @@ template <bool ACCUM>
 __device__ __forceinline__ void staged_load_f32(const float* __restrict__ g, long long ld, int rows_valid, float* stage,
                                                 int lane, float* v) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = i * 8 + (lane >> 3);
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3);   // 8 lanes x 16 B = one 128-byte row segment, 4 rows per instruction
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < rows_valid) x = *reinterpret_cast<const float4*>(g + (long long)r * ld + (lane & 7) * 4);
     *reinterpret_cast<float4*>(stage + r * STG_LD + (lane & 7) * 4) = x;
@@ -143,8 +143,8 @@ __device__ __forceinline__ void staged_store_f32(float* __restrict__ g, long lon
     *reinterpret_cast<float4*>(stage + lane * STG_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   __syncwarp();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = i * 8 + (lane >> 3);
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3);
     const float4 x = *reinterpret_cast<const float4*>(stage + r * STG_LD + (lane & 7) * 4);
     if (r < rows_valid) *reinterpret_cast<float4*>(g + (long long)r * ld + (lane & 7) * 4) = x;
   }

@@ -307,5 +307,8 @@ __host__ __device__ constexpr uint32_t sw128_offset(uint32_t r, uint32_t c) {
 // dims/strides innermost first; strides in BYTES for dims 1.. (dim 0 is contiguous).
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
+// same for fp32 tensors (inner box = 32 floats = 128 B)
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
 
 }  // namespace vatss

@@ -41,8 +41,20 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+static int make_tmap_any(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box);
+
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box) {
+  return make_tmap_any(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, rank, dims, strides_bytes, box);
+}
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  return make_tmap_any(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
+}
+
+static int make_tmap_any(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box) {
   PFN_encodeTiled enc = get_encode();
   VATSS_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[5], gstr[5];
@@ -53,7 +65,7 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     es[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+  CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VATSS_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d (rank %d)", (int)r, rank);
@@ -92,14 +104,18 @@ struct TcGemmArgs {
 
 constexpr int TCG_THREADS = 192;   // TMA warp, MMA warp, 4 epilogue warps
 
-template <int NOUT, int KDIM>
+template <int NOUT, int KDIM, bool RES_TMA = false>
 struct TcGemmSmem {
   static constexpr int KB = KDIM / 64;
   static constexpr int W_BYTES = KB * NOUT * 128;
   static constexpr int A_STAGE_BYTES = KB * 128 * 128;
+  // residual tile [128 rows x NOUT fp32] as NOUT/32 column blocks of 128-byte rows (SWIZZLE_128B), TMA-prefetched
+  static constexpr int RES_BYTES = RES_TMA ? 128 * NOUT * 4 : 0;
+  static constexpr int A_STAGES = (W_BYTES + 2 * A_STAGE_BYTES + RES_BYTES + 24 * 1024 <= 227 * 1024) ? 2 : 1;
   static constexpr int OFF_W = 0;
   static constexpr int OFF_A = OFF_W + W_BYTES;
-  static constexpr int OFF_PAR = OFF_A + 2 * A_STAGE_BYTES;  // bias, ln_w, ln_b
+  static constexpr int OFF_RES = OFF_A + A_STAGES * A_STAGE_BYTES;
+  static constexpr int OFF_PAR = OFF_RES + RES_BYTES;  // bias, ln_w, ln_b
   static constexpr int OFF_BAR = OFF_PAR + 3 * NOUT * 4;
   static constexpr int OFF_STAGE = OFF_BAR + 128;        // per epilogue warp: [32 rows][36 floats] transpose tile
   static constexpr int TOTAL = OFF_STAGE + 4 * 32 * 36 * 4 + 1024;  // + alignment slack
@@ -169,8 +185,10 @@ __device__ __forceinline__ void staged_store_f16(__half* __restrict__ g, long lo
 
 template <int NOUT, int KDIM, int EPI>
 __global__ void __launch_bounds__(TCG_THREADS, 1)
-k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapW, TcGemmArgs p) {
-  using L = TcGemmSmem<NOUT, KDIM>;
+k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapW,
+          const __grid_constant__ CUtensorMap tmapR, TcGemmArgs p) {
+  constexpr bool RES_TMA = (EPI == TC_EPI_LN || EPI == TC_EPI_LN_POST);   // residual tile prefetched by TMA
+  using L = TcGemmSmem<NOUT, KDIM, RES_TMA>;
   static_assert(NOUT % 16 == 0 && NOUT <= 512 && KDIM % 64 == 0, "shape");
   static_assert(EPI != TC_EPI_LN && EPI != TC_EPI_LN_POST || NOUT <= 128, "LayerNorm epilogue needs the row in regs");
   extern __shared__ unsigned char smem_raw[];
@@ -181,7 +199,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
   float* sPar = reinterpret_cast<float*>(gen + L::OFF_PAR);
   const uint32_t bars = base + L::OFF_BAR;
   const uint32_t bar_w = bars, bar_afull = bars + 8, bar_aempty = bars + 24, bar_accfull = bars + 40,
-                 bar_accempty = bars + 56;
+                 bar_accempty = bars + 56, bar_rfull = bars + 72, bar_rempty = bars + 80;
+  const uint32_t sR = base + L::OFF_RES;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + L::OFF_BAR + 96);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -194,9 +213,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
       mbar_init(bar_accfull + 8 * s, 1);
       mbar_init(bar_accempty + 8 * s, 128);
     }
+    mbar_init(bar_rfull, 1);
+    mbar_init(bar_rempty, 128);
     fence_mbar_init();
     prefetch_tmap(&tmapA);
     prefetch_tmap(&tmapW);
+    if (RES_TMA) prefetch_tmap(&tmapR);
   }
   for (int i = threadIdx.x; i < NOUT; i += blockDim.x) {
     sPar[i] = p.bias ? p.bias[i] : 0.f;
@@ -220,11 +242,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
         for (int n0 = 0; n0 < NOUT; n0 += 64) tma_load_2d(sW + kb * NOUT * 128 + n0 * 128, &tmapW, bar_w, kb * 64, n0);
       int i = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
-        const int s = i & 1, ph = (i >> 1) & 1;
+        const int s = i % L::A_STAGES, ph = (i / L::A_STAGES) & 1;
         mbar_wait(bar_aempty + 8 * s, ph ^ 1);
         mbar_expect_tx(bar_afull + 8 * s, L::A_STAGE_BYTES);
         for (int kb = 0; kb < L::KB; ++kb)
           tma_load_2d(sA + s * L::A_STAGE_BYTES + kb * 16384, &tmapA, bar_afull + 8 * s, kb * 64, tile * 128);
+        if constexpr (RES_TMA) {
+          mbar_wait(bar_rempty, (i & 1) ^ 1);
+          mbar_expect_tx(bar_rfull, L::RES_BYTES);
+          for (int cbk = 0; cbk < NOUT / 32; ++cbk) tma_load_2d(sR + cbk * 16384, &tmapR, bar_rfull, cbk * 32, tile * 128);
+        }
       }
     }
     __syncwarp();
@@ -234,7 +261,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
       mbar_wait(bar_w, 0);
       int i = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
-        const int s = i & 1, ph = (i >> 1) & 1;
+        const int s = i % L::A_STAGES, ph = (i / L::A_STAGES) & 1;
         const int as = i % L::ACC_STAGES, aph = (i / L::ACC_STAGES) & 1;
         mbar_wait(bar_accempty + 8 * as, aph ^ 1);
         mbar_wait(bar_afull + 8 * s, ph);
@@ -297,14 +324,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
           }
         }
       } else {
-        // LayerNorm over the whole row held in registers
+        // LayerNorm over the whole row held in registers; the residual tile was prefetched into shared memory by TMA
         float v[NOUT];
-        if constexpr (EPI == TC_EPI_LN) {
-          // the residual does not depend on the MMA: fetch it before waiting for the accumulator
-#pragma unroll
-          for (int c0 = 0; c0 < NOUT; c0 += 32)
-            staged_load_f32<false>(p.res + row0 * p.ldr + c0, p.ldr, rows_valid, stage, lane, v + c0);
-        }
+        const int rr = q * 32 + lane;
+        mbar_wait(bar_rfull, i & 1);
         mbar_wait(bar_accfull + 8 * as, aph);
         tc_fence_after();
 #pragma unroll
@@ -313,10 +336,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
           tmem_ld_32x32b_x32(taddr + c0, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float a = __uint_as_float(r[j]) + sBias[c0 + j];
-            if constexpr (EPI == TC_EPI_LN) v[c0 + j] += a;
-            else v[c0 + j] = a;
+          for (int j = 0; j < 32; ++j) v[c0 + j] = __uint_as_float(r[j]) + sBias[c0 + j];
+          if constexpr (EPI == TC_EPI_LN) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 x = *reinterpret_cast<const float4*>(gen + L::OFF_RES + (c0 / 32) * 16384 +
+                                                                sw128_offset((uint32_t)rr, (uint32_t)c));
+              v[c0 + 4 * c] += x.x; v[c0 + 4 * c + 1] += x.y; v[c0 + 4 * c + 2] += x.z; v[c0 + 4 * c + 3] += x.w;
+            }
           }
         }
         float sum = 0.f;
@@ -334,8 +361,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
         for (int j = 0; j < NOUT; ++j) v[j] = (v[j] - mean) * rstd * sLw[j] + sLb[j];
 #pragma unroll
         for (int c0 = 0; c0 < NOUT; c0 += 32) {
-          if constexpr (EPI == TC_EPI_LN_POST)
-            staged_load_f32<true>(p.res + row0 * p.ldr + c0, p.ldr, rows_valid, stage, lane, v + c0);
+          if constexpr (EPI == TC_EPI_LN_POST) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 x = *reinterpret_cast<const float4*>(gen + L::OFF_RES + (c0 / 32) * 16384 +
+                                                                sw128_offset((uint32_t)rr, (uint32_t)c));
+              v[c0 + 4 * c] += x.x; v[c0 + 4 * c + 1] += x.y; v[c0 + 4 * c + 2] += x.z; v[c0 + 4 * c + 3] += x.w;
+            }
+          }
           staged_store_f32(p.out32 + row0 * p.ldo32 + c0, p.ldo32, rows_valid, stage, lane, v + c0);
           if (p.out16) {
             uint32_t pk[16];
@@ -351,6 +384,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
           }
         }
       }
+      if constexpr (RES_TMA) mbar_arrive(bar_rempty);
       tc_fence_before();
       mbar_arrive(bar_accempty + 8 * as);
     }
@@ -362,9 +396,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
 
 template <int NOUT, int KDIM, int EPI>
 static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const TcGemmArgs& args, cudaStream_t st) {
-  using L = TcGemmSmem<NOUT, KDIM>;
+  constexpr bool RES_TMA = (EPI == TC_EPI_LN || EPI == TC_EPI_LN_POST);
+  using L = TcGemmSmem<NOUT, KDIM, RES_TMA>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmW, tmR;
+  tmR = CUtensorMap();
+  if (RES_TMA) {
+    const uint64_t dims[2] = {(uint64_t)NOUT, (uint64_t)args.M};
+    const uint64_t str[1] = {(uint64_t)args.ldr * 4};
+    const uint32_t box[2] = {32, 128};
+    if (make_tmap_f32(&tmR, args.res, 2, dims, str, box)) return -1;
+  }
   {
     const uint64_t dims[2] = {(uint64_t)KDIM, (uint64_t)args.M};
     const uint64_t str[1] = {(uint64_t)lda * 2};
@@ -384,7 +426,7 @@ static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const
     configured = true;
   }
   const int grid = args.num_tiles < num_sms() ? args.num_tiles : num_sms();
-  kern<<<grid, TCG_THREADS, L::TOTAL, st>>>(tmA, tmW, args);
+  kern<<<grid, TCG_THREADS, L::TOTAL, st>>>(tmA, tmW, tmR, args);
   VATSS_LAUNCH_OK();
   return 0;
 }

@@ -101,7 +101,8 @@ k_sisnr_finalize(const double* __restrict__ scratch, int B, int T, int chunks, i
       if (q < 4) {
         // reference loss form, no eps: signal = dot^2/gg, noise = pp - dot^2/gg
         const double s = pm.dot * pm.dot / pm.gg;
-        const double n = pm.pp - s;
+        double n = pm.pp - s;
+        if (n < 0.0) n = 0.0;   // perfect estimate: rounding may push the residual power below zero
         rows_loss[b * 4 + q] = -20.0 * log10(s / n);
       }
     }

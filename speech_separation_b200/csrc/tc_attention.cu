@@ -167,10 +167,10 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
       mbar_init(b_kfull + 8 * i, 1); mbar_init(b_kfree + 8 * i, 1);
       mbar_init(b_vfull + 8 * i, 1); mbar_init(b_vfree + 8 * i, 1);
       mbar_init(b_qfull + 8 * i, 1); mbar_init(b_qfree + 8 * i, 1);
-      mbar_init(b_sfull + 8 * i, 1); mbar_init(b_sfree + 8 * i, 512);
-      mbar_init(b_ofull + 8 * i, 1); mbar_init(b_ofree + 8 * i, 512);
+      mbar_init(b_sfull + 8 * i, 1); mbar_init(b_sfree + 8 * i, 16);   // one elected arrival per softmax warp
+      mbar_init(b_ofull + 8 * i, 1); mbar_init(b_ofree + 8 * i, 16);
     }
-    for (int i = 0; i < ATT_PRING; ++i) { mbar_init(b_pfull + 8 * i, 512); mbar_init(b_pfree + 8 * i, 1); }
+    for (int i = 0; i < ATT_PRING; ++i) { mbar_init(b_pfull + 8 * i, 16); mbar_init(b_pfree + 8 * i, 1); }
     fence_mbar_init();
     prefetch_tmap(&tmapQ);
     prefetch_tmap(&tmapKV);
@@ -322,7 +322,8 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
       else tmem_ld_32x32b_x4(t_lane + oreg_prev * ATT_REGION + ATT_O_COL + cq * OC, o);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(b_ofree + 8 * oreg_prev);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_ofree + 8 * oreg_prev);   // 512 same-address arrivals would serialise
       if (orow_prev >= 0) {
         uint32_t wd[OC / 2];
 #pragma unroll
@@ -367,7 +368,8 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
         }
         if (!resident) {   // the S region is recycled
           tc_fence_before();
-          mbar_arrive(b_sfree + 8 * reg);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_sfree + 8 * reg);
         }
       }
       if (!resident) sjob += nsuper;
@@ -417,12 +419,13 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
           } else {
             mbar_wait(b_pfree + 8 * pb, ((pjob / ATT_PRING) & 1) ^ 1);
           }
-          if (j == j1 - 1) {   // last block of the S job: the region may be overwritten
-            tc_fence_before();
-            mbar_arrive(b_sfree + 8 * reg);
-          }
           fence_proxy_async();
-          mbar_arrive(b_pfull + 8 * pb);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (j == j1 - 1) mbar_arrive(b_sfree + 8 * reg);   // last block of the S job: region may be overwritten
+            mbar_arrive(b_pfull + 8 * pb);
+          }
         }
       }
       // row sums: combine the four column quarters

@@ -6,16 +6,15 @@
 // probabilities are exp2(s - rowmax).
 //
 // Work item = (sequence, 64-feature head group): the Q/K/V tiles of a head group are 128-byte rows, i.e. plain
-// SWIZZLE_128B TMA tiles; a head is a 16/32-column K-slice of them (start-address offset inside the swizzle atom) and
-// V is consumed as an MN-major B operand (no transpose).  One persistent CTA per SM, 576 threads:
-//   warp 0        TMA producer (K, V of the item, double buffered; Q per 128-query tile, double buffered)
-//   warp 1        MMA issuer: S = Q K^T (M=128, N<=192 per MMA, K=hd) and O += P V (M=128, N=hd, K=64 per kv block)
-//   warps 2..17   softmax: thread = one query row x one 16-column quarter of every 64-column kv block
-// The unit of work is a group = (item, query tile, head).  S and O are double buffered in TMEM (two regions of
-// 192 + 32 columns) and P is a 4-deep ring in shared memory, so S of group g+1 and P V of group g run on the tensor
-// pipe while the softmax warps work on group g, and the O read-out of group g is deferred until after the softmax of
-// group g+1: in steady state the softmax warps never wait for an MMA.  Row maxima / sums of the four column
-// quarters are combined through shared memory.  Sequences longer than 192 use an exact two-pass softmax
+// SWIZZLE_128B TMA tiles; a head is a 16/32-column K-slice of them.  One persistent CTA per SM:
+//   warp 0        TMA producer (K and V of the item once, Q per 128-query tile, double buffered)
+//   warps 1,2     MMA issuers, one per softmax warpgroup (decoupled pipelines): S = Q K^T (M=128, N<=192, K=hd)
+//                 and O += P V (M=128, N=hd, K=64 per kv block)
+//   warps 3..10   softmax warpgroup 0  (heads [0, HPT/2) of the group): two warps per TMEM lane quadrant, each
+//                 thread owns one query row and one 32-column half of every 64-column S block
+//   warps 11..18  softmax warpgroup 1  (heads [HPT/2, HPT))
+// Each warpgroup owns an S slot and an O accumulator in TMEM and a P tile in shared memory, so the two
+// heads' MMAs and exponentials overlap.  Sequences longer than one kv block use an exact two-pass softmax
 // (pass A: row max over all blocks, pass B: exp / P V accumulation) - no accumulator rescaling.
 //
 // k_attention_f16_simt is the shape-agnostic fallback (sequence too long for the shared-memory plan).
@@ -101,17 +100,15 @@ struct TcAttnArgs {
   int groups;     // 64-feature head groups per sequence (N / 64)
   int nblk;       // 64-row kv blocks per sequence
   int mtiles;     // 128-query tiles per sequence
-  int vbufs;      // V buffers (2 when shared memory allows)
   int num_items;  // sequences * groups
   SeqMap map;
   __half* out;    // (tokens, N)
 };
 
-constexpr int ATT_THREADS = 576;       // producer warp, MMA warp, 16 softmax warps
+constexpr int ATT_THREADS = 608;        // producer warp, 2 MMA warps (one per warpgroup), 2 x 8 softmax warps
 constexpr int ATT_NB = 64;             // kv rows per block = one SWIZZLE_128B k-block of the P tile
-constexpr int ATT_SUPER = 3;           // kv blocks per S job: one N <= 192 MMA per 16-wide K step
-constexpr int ATT_PRING = 4;           // P tiles in flight
-constexpr uint32_t ATT_REGION = 256;   // TMEM columns per pipeline region: 192 (S) + 32 (O)
+constexpr int ATT_SUPER = 3;           // 64-row kv blocks per S job: one N <= 192 MMA fills the whole S region
+constexpr uint32_t ATT_WG_COLS = 256;  // TMEM columns per warpgroup: 192 (S region) + 32 (O)
 constexpr uint32_t ATT_O_COL = 192;
 
 // MN-major (N contiguous) B operand with 128-byte rows, SWIZZLE_128B: 8-row (K) groups 1024 B apart
@@ -130,47 +127,57 @@ __device__ __forceinline__ float ex2_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// p = 2^(a), 2^(b) as packed fp16 (one MUFU op for the pair)
+__device__ __forceinline__ uint32_t ex2_f16x2(float a, float b) {
+  uint32_t packed, y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(packed) : "f"(b), "f"(a));   // low half = a, high half = b
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(packed));
+  return y;
+}
 
-// One (item, query tile, head) unit of work; every role enumerates the same sequence.
-struct AttGroup {
-  int item, it, m, qn, h;
-  bool valid;
+struct AttBars {
+  uint32_t kfull, kfree, vfull, vfree, qfull, qfree;   // kfull/kfree/qfull/qfree: [2]
+  uint32_t sfull, sfree;                               // [2 wg]
+  uint32_t pfull, pfree;                               // [2 wg][2 buffers]
+  uint32_t ofull, ofree;                               // [2 wg]
 };
 
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CUtensorMap tmapKV, TcAttnArgs p) {
   constexpr int HPT = 64 / HD;       // heads per 64-feature group
-  constexpr int OC = HD / 4;         // output features per softmax thread
+  constexpr int HPW = HPT / 2;       // heads per warpgroup
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t base = smem_u32(smem);
   if ((base & 1023u) != 0) __trap();
   const uint32_t KV_BYTES = (uint32_t)p.nblk * ATT_NB * 128u;
-  const uint32_t sQ = base;                                   // [2][128 x 128 B]
-  const uint32_t sP = sQ + 2 * 16384;                         // [ATT_PRING][128 x 128 B]
-  const uint32_t sK = sP + ATT_PRING * 16384;                 // [2]
-  const uint32_t sV = sK + 2 * KV_BYTES;                      // [vbufs]
-  const uint32_t bars = sV + p.vbufs * KV_BYTES;
-  // barrier map, 8 bytes each: k/v/q full+free [2 each], s full/free [2], p full/free [4], o full/free [2]
-  const uint32_t b_kfull = bars, b_kfree = bars + 16, b_vfull = bars + 32, b_vfree = bars + 48;
-  const uint32_t b_qfull = bars + 64, b_qfree = bars + 80, b_sfull = bars + 96, b_sfree = bars + 112;
-  const uint32_t b_pfull = bars + 128, b_pfree = bars + 160, b_ofull = bars + 192, b_ofree = bars + 208;
-  const uint32_t tmem_slot = bars + 224;
-  float* s_ex = reinterpret_cast<float*>(smem + (bars + 256 - base));   // [2 kinds][2 parity][4 quarters][128 rows]
+  const uint32_t sQ = base;                        // [2][128 x 128 B]
+  const uint32_t sP = sQ + 2 * 16384;              // [2 wg][2][128 x 128 B]
+  const uint32_t sK = sP + 4 * 16384;              // [2] double buffered across items
+  const uint32_t sV = sK + 2 * KV_BYTES;
+  const uint32_t bars = sV + KV_BYTES;
+  AttBars B;
+  B.kfull = bars; B.kfree = bars + 16;             // 2 each
+  B.vfull = bars + 32; B.vfree = bars + 40;
+  B.qfull = bars + 48; B.qfree = bars + 64;        // 2 each
+  B.sfull = bars + 80; B.sfree = bars + 128;       // 6 each
+  B.pfull = bars + 176; B.pfree = bars + 208;      // 4 each
+  B.ofull = bars + 240; B.ofree = bars + 256;      // 2 each
+  const uint32_t tmem_slot = bars + 272;
+  float* s_mx = reinterpret_cast<float*>(smem + (bars + 288 - base));   // [2 wg][2 sets][128 rows]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool resident = p.nblk <= ATT_SUPER;       // all of S of a (tile, head) fits one region: single S pass
+  const bool resident = p.nblk <= ATT_SUPER;       // all of S of a (tile, head) fits the S region: single S pass
   const int nsuper = (p.nblk + ATT_SUPER - 1) / ATT_SUPER;
-  const int jobs_per_group = resident ? 1 : 2 * nsuper;
 
   if (threadIdx.x == 0) {
+    mbar_init(B.vfull, 1); mbar_init(B.vfree, 2);      // "free" barriers: one commit from each MMA warp
     for (int i = 0; i < 2; ++i) {
-      mbar_init(b_kfull + 8 * i, 1); mbar_init(b_kfree + 8 * i, 1);
-      mbar_init(b_vfull + 8 * i, 1); mbar_init(b_vfree + 8 * i, 1);
-      mbar_init(b_qfull + 8 * i, 1); mbar_init(b_qfree + 8 * i, 1);
-      mbar_init(b_sfull + 8 * i, 1); mbar_init(b_sfree + 8 * i, 16);   // one elected arrival per softmax warp
-      mbar_init(b_ofull + 8 * i, 1); mbar_init(b_ofree + 8 * i, 16);
+      mbar_init(B.kfull + 8 * i, 1); mbar_init(B.kfree + 8 * i, 2);
+      mbar_init(B.qfull + 8 * i, 1); mbar_init(B.qfree + 8 * i, 2);
     }
-    for (int i = 0; i < ATT_PRING; ++i) { mbar_init(b_pfull + 8 * i, 16); mbar_init(b_pfree + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(B.sfull + 8 * i, 1); mbar_init(B.sfree + 8 * i, 256); }
+    for (int i = 0; i < 4; ++i) { mbar_init(B.pfull + 8 * i, 256); mbar_init(B.pfree + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(B.ofull + 8 * i, 1); mbar_init(B.ofree + 8 * i, 256); }
     fence_mbar_init();
     prefetch_tmap(&tmapQ);
     prefetch_tmap(&tmapKV);
@@ -183,14 +190,6 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
-
-  auto advance = [&](AttGroup& c) {
-    if (++c.h == HPT) {
-      c.h = 0; ++c.qn;
-      if (++c.m == p.mtiles) { c.m = 0; c.item += gridDim.x; ++c.it; c.valid = c.item < p.num_items; }
-    }
-  };
-  const AttGroup first = {(int)blockIdx.x, 0, 0, 0, 0, (int)blockIdx.x < p.num_items};
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -208,239 +207,246 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
           else tma_load_4d(dst, tm, bar, col, ck, r0, cb);
         };
         const int kb = it & 1;
-        mbar_wait(b_kfree + 8 * kb, ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(b_kfull + 8 * kb, KV_BYTES);
+        mbar_wait(B.kfree + 8 * kb, ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(B.kfull + 8 * kb, KV_BYTES);
         for (int j = 0; j < p.nblk; ++j)
-          load_rows(&tmapKV, sK + kb * KV_BYTES + j * ATT_NB * 128, b_kfull + 8 * kb, colk, j * ATT_NB);
+          load_rows(&tmapKV, sK + kb * KV_BYTES + j * ATT_NB * 128, B.kfull + 8 * kb, colk, j * ATT_NB);
         for (int m = 0; m < p.mtiles; ++m, ++qn) {
           const int s = qn & 1;
-          mbar_wait(b_qfree + 8 * s, ((qn >> 1) & 1) ^ 1);
-          mbar_expect_tx(b_qfull + 8 * s, 16384);
-          load_rows(&tmapQ, sQ + s * 16384, b_qfull + 8 * s, colq, m * 128);
+          mbar_wait(B.qfree + 8 * s, ((qn >> 1) & 1) ^ 1);
+          mbar_expect_tx(B.qfull + 8 * s, 16384);
+          load_rows(&tmapQ, sQ + s * 16384, B.qfull + 8 * s, colq, m * 128);
           if (m == 0) {
-            const int vb = it % p.vbufs, vuse = it / p.vbufs;
-            mbar_wait(b_vfree + 8 * vb, (vuse & 1) ^ 1);
-            mbar_expect_tx(b_vfull + 8 * vb, KV_BYTES);
-            for (int j = 0; j < p.nblk; ++j)
-              load_rows(&tmapKV, sV + vb * KV_BYTES + j * ATT_NB * 128, b_vfull + 8 * vb, colv, j * ATT_NB);
+            mbar_wait(B.vfree, (it & 1) ^ 1);
+            mbar_expect_tx(B.vfull, KV_BYTES);
+            for (int j = 0; j < p.nblk; ++j) load_rows(&tmapKV, sV + j * ATT_NB * 128, B.vfull, colv, j * ATT_NB);
           }
         }
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    // S jobs run one job ahead of the softmax (two S regions in TMEM); P V MMAs follow the P tiles; O is double
-    // buffered as well, so the softmax warps never wait for the tensor pipe in steady state.
+  } else if (warp == 1 || warp == 2) {
+    // ---------------------------------------------------------------- MMA issuer (warp 1 -> warpgroup 0, warp 2 -> 1)
+    // Small tcgen05.mma instructions cost a fixed ~100+ cycles each, so the instruction count is what matters:
+    // S uses one N = 64..192 MMA per 16-wide K step for a whole super-block, P V needs kv/16 MMAs of N = hd.
     if (lane == 0) {
+      const int w = warp - 1;
       const uint32_t idesc_o = idesc_f16(128, HD, 0) | (1u << 16);     // B (= V) is MN-major
-      uint32_t sjob = 0, pjob = 0, ogrp = 0;
+      // a "group" = one (item, query tile, head-of-warpgroup); both warpgroups run the same group sequence
+      struct Cur { int item, it, m, qn, hh; bool valid; };
+      auto advance = [&](Cur& c) {
+        if (++c.hh == HPW) {
+          c.hh = 0; ++c.qn;
+          if (++c.m == p.mtiles) { c.m = 0; c.item += gridDim.x; ++c.it; c.valid = c.item < p.num_items; }
+        }
+      };
+      uint32_t sjob = 0, pjob = 0, ohead = 0;
       int k_seen = -1, q_seen = -1, v_seen = -1;
-      // job cursor: (group, job index inside the group)
-      AttGroup jg = first; int jj = 0;        // next S job to issue
-      AttGroup cg = first; int cj = 0;        // job whose P V MMAs come next
-      auto issue_s = [&]() {
-        const AttGroup& c = jg;
-        if (k_seen != c.it) { mbar_wait(b_kfull + 8 * (c.it & 1), (c.it >> 1) & 1); k_seen = c.it; }
-        if (q_seen != c.qn) { mbar_wait(b_qfull + 8 * (c.qn & 1), (c.qn >> 1) & 1); q_seen = c.qn; }
-        const int sb = resident ? 0 : jj % nsuper;
+      // S super-block sb (kv blocks [3 sb, 3 sb + nb)) of group c into the S region of both warpgroups
+      auto issue_s = [&](const Cur& c, int sb, bool last_job_of_group) {
+        if (k_seen != c.it) { mbar_wait(B.kfull + 8 * (c.it & 1), (c.it >> 1) & 1); k_seen = c.it; }
+        if (q_seen != c.qn) { mbar_wait(B.qfull + 8 * (c.qn & 1), (c.qn >> 1) & 1); q_seen = c.qn; }
         const int nb = min(ATT_SUPER, p.nblk - sb * ATT_SUPER);
         const uint32_t idesc_s = idesc_f16(128, nb * ATT_NB, 0);
-        const uint32_t reg = sjob & 1;
-        mbar_wait(b_sfree + 8 * reg, ((sjob >> 1) & 1) ^ 1);
-        tc_fence_after();
+        {
+          const int hsel = w * HPW + c.hh;
+          mbar_wait(B.sfree + 8 * w, (sjob & 1) ^ 1);
+          tc_fence_after();
 #pragma unroll
-        for (int k16 = 0; k16 < HD / 16; ++k16) {
-          const uint32_t koff = (uint32_t)(c.h * HD * 2 + k16 * 32) >> 4;
-          const uint64_t a = smem_desc_sw128_kmajor(sQ + (c.qn & 1) * 16384) + koff;
-          const uint64_t b = smem_desc_sw128_kmajor(sK + (c.it & 1) * KV_BYTES + sb * ATT_SUPER * ATT_NB * 128) + koff;
-          umma_f16<1>(tmem + reg * ATT_REGION, a, b, idesc_s, k16 > 0 ? 1u : 0u);
+          for (int k16 = 0; k16 < HD / 16; ++k16) {
+            const uint32_t koff = (uint32_t)(hsel * HD * 2 + k16 * 32) >> 4;
+            const uint64_t a = smem_desc_sw128_kmajor(sQ + (c.qn & 1) * 16384) + koff;
+            const uint64_t b = smem_desc_sw128_kmajor(sK + (c.it & 1) * KV_BYTES + sb * ATT_SUPER * ATT_NB * 128) + koff;
+            umma_f16<1>(tmem + w * ATT_WG_COLS, a, b, idesc_s, k16 > 0 ? 1u : 0u);
+          }
+          umma_commit(B.sfull + 8 * w);
         }
-        umma_commit(b_sfull + 8 * reg);
         ++sjob;
-        const bool last_job = jj == jobs_per_group - 1;
-        if (last_job && c.h == HPT - 1) {
-          umma_commit(b_qfree + 8 * (c.qn & 1));                          // last S MMA reading this Q tile
-          if (c.m == p.mtiles - 1) umma_commit(b_kfree + 8 * (c.it & 1));  // ... and this K buffer
+        if (last_job_of_group && c.hh == HPW - 1) {
+          umma_commit(B.qfree + 8 * (c.qn & 1));                       // last S MMA reading this Q tile
+          if (c.m == p.mtiles - 1) umma_commit(B.kfree + 8 * (c.it & 1));   // ... and this K buffer
         }
-        if (++jj == jobs_per_group) { jj = 0; advance(jg); }
       };
-      auto issue_pv_job = [&]() {
-        const AttGroup& c = cg;
-        const bool exp_job = resident || cj >= nsuper;
-        if (exp_job) {
-          const int sb = resident ? 0 : cj - nsuper;
-          const int j1 = min(p.nblk, (sb + 1) * ATT_SUPER);
-          const int vb = c.it % p.vbufs;
-          if (v_seen != c.it) { mbar_wait(b_vfull + 8 * vb, (c.it / p.vbufs) & 1); v_seen = c.it; }
-          const uint32_t oreg = ogrp & 1;
-          for (int j = sb * ATT_SUPER; j < j1; ++j, ++pjob) {
-            const uint32_t pb = pjob % ATT_PRING;
-            if (j == 0) mbar_wait(b_ofree + 8 * oreg, ((ogrp >> 1) & 1) ^ 1);   // O region read out two groups ago
-            mbar_wait(b_pfull + 8 * pb, (pjob / ATT_PRING) & 1);
-            tc_fence_after();
-            const uint32_t d_o = tmem + oreg * ATT_REGION + ATT_O_COL;
+      // O += P_j V_j for group c, both warpgroups
+      auto issue_pv = [&](const Cur& c, int j) {
+        if (v_seen != c.it) { mbar_wait(B.vfull, c.it & 1); v_seen = c.it; }
+        const uint32_t pb = pjob & 1;
+        {
+          const int hsel = w * HPW + c.hh;
+          if (j == 0) mbar_wait(B.ofree + 8 * w, (ohead & 1) ^ 1);     // previous O of this warpgroup read out
+          mbar_wait(B.pfull + 8 * (w * 2 + pb), (pjob >> 1) & 1);
+          tc_fence_after();
+          const uint32_t d_o = tmem + w * ATT_WG_COLS + ATT_O_COL;
 #pragma unroll
-            for (int k16 = 0; k16 < ATT_NB / 16; ++k16) {
-              const uint64_t a = smem_desc_sw128_kmajor(sP + pb * 16384) + (uint64_t)(k16 * 2);
-              const uint64_t bv = smem_desc_sw128_mnmajor(sV + vb * KV_BYTES + (j * ATT_NB + k16 * 16) * 128 + c.h * HD * 2);
-              umma_f16<1>(d_o, a, bv, idesc_o, (j > 0 || k16 > 0) ? 1u : 0u);
-            }
-            umma_commit(b_pfree + 8 * pb);
+          for (int k16 = 0; k16 < ATT_NB / 16; ++k16) {
+            const uint64_t a = smem_desc_sw128_kmajor(sP + (w * 2 + pb) * 16384) + (uint64_t)(k16 * 2);
+            const uint64_t bv = smem_desc_sw128_mnmajor(sV + (j * ATT_NB + k16 * 16) * 128 + hsel * HD * 2);
+            umma_f16<1>(d_o, a, bv, idesc_o, (j > 0 || k16 > 0) ? 1u : 0u);
           }
-          if (j1 == p.nblk) {
-            umma_commit(b_ofull + 8 * oreg);
-            ++ogrp;
-            if (c.h == HPT - 1 && c.m == p.mtiles - 1) umma_commit(b_vfree + 8 * vb);   // last P V reading this V
+          umma_commit(B.pfree + 8 * (w * 2 + pb));
+          if (j == p.nblk - 1) umma_commit(B.ofull + 8 * w);
+        }
+        ++pjob;
+        if (j == p.nblk - 1) {
+          ++ohead;
+          if (c.hh == HPW - 1 && c.m == p.mtiles - 1) umma_commit(B.vfree);   // last P V reading this item's V
+        }
+      };
+      Cur cur = {(int)blockIdx.x, 0, 0, 0, 0, (int)blockIdx.x < p.num_items};
+      while (cur.valid) {
+        if (resident) {
+          issue_s(cur, 0, true);
+          for (int j = 0; j < p.nblk; ++j) issue_pv(cur, j);
+        } else {
+          for (int sb = 0; sb < nsuper; ++sb) issue_s(cur, sb, false);             // pass A: row maxima
+          for (int sb = 0; sb < nsuper; ++sb) {                                    // pass B: exp, P V
+            issue_s(cur, sb, sb == nsuper - 1);
+            const int j1 = min(p.nblk, (sb + 1) * ATT_SUPER);
+            for (int j = sb * ATT_SUPER; j < j1; ++j) issue_pv(cur, j);
           }
         }
-        if (++cj == jobs_per_group) { cj = 0; advance(cg); }
-      };
-      if (jg.valid) issue_s();
-      while (cg.valid) {
-        if (jg.valid) issue_s();      // keep S one job ahead
-        issue_pv_job();
+        advance(cur);
       }
     }
     __syncwarp();
   } else {
-    // ---------------------------------------------------------------- softmax warps (16): thread = row x column quarter
-    const int sw = warp - 2;
+    // ---------------------------------------------------------------- softmax warpgroups
+    const int sw = warp - 3;
+    const int w = sw >> 3;                       // warpgroup
+    const int set = (sw >> 2) & 1;               // which 32-column half of each 64-column kv block this thread owns
     const int q = warp & 3;                      // TMEM lane quadrant of this warp
-    const int cq = sw >> 2;                      // which 16 columns of each 64-column kv block
     const int r = q * 32 + lane;                 // query row inside the 128-row tile
-    const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
-    const int cb = cq * 16;
-    uint32_t sjob = 0, pjob = 0, gcount = 0;
-    // deferred epilogue of the previous group (its O accumulates while this group's softmax runs)
-    bool have_prev = false; float inv_prev = 0.f; long long orow_prev = -1; int ocol_prev = 0; uint32_t oreg_prev = 0;
-    auto epilogue = [&]() {
-      mbar_wait(b_ofull + 8 * oreg_prev, ((gcount - 1) >> 1) & 1);
-      tc_fence_after();
-      uint32_t o[OC];
-      if constexpr (OC == 8) tmem_ld_32x32b_x8(t_lane + oreg_prev * ATT_REGION + ATT_O_COL + cq * OC, o);
-      else tmem_ld_32x32b_x4(t_lane + oreg_prev * ATT_REGION + ATT_O_COL + cq * OC, o);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(b_ofree + 8 * oreg_prev);   // 512 same-address arrivals would serialise
-      if (orow_prev >= 0) {
-        uint32_t wd[OC / 2];
+    const uint32_t t_base = tmem + ((uint32_t)(q * 32) << 16) + w * ATT_WG_COLS;
+    const int cb = set * 32;
+    float* ex = s_mx + w * 256;
+    uint32_t sjob = 0, pjob = 0, ohead = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int g = item / p.groups, grp = item - g * p.groups;
+      for (int m = 0; m < p.mtiles; ++m) {
+        const int qi = m * 128 + r;
+        const bool warp_live = m * 128 + q * 32 < p.len;     // warp-uniform: any valid query row in this warp
+        for (int hh = 0; hh < HPW; ++hh) {
+          const int head = grp * HPT + w * HPW + hh;
+          float mx = -INFINITY;
+          // ---- row maximum over this thread's columns
+          for (int sb = 0; sb < nsuper; ++sb) {
+            mbar_wait(B.sfull + 8 * w, (sjob + sb) & 1);
+            tc_fence_after();
+            const int j1 = min(p.nblk, (sb + 1) * ATT_SUPER);
+            if (warp_live) {
+              for (int j = sb * ATT_SUPER; j < j1; ++j) {
+                const int nv = min(ATT_NB, p.len - j * ATT_NB) - cb;   // valid columns of this thread's half
+                if (nv <= 0) continue;
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(t_base + (j - sb * ATT_SUPER) * ATT_NB + cb, v);
+                tmem_ld_wait();
+                if (nv >= 32) {
 #pragma unroll
-        for (int e = 0; e < OC / 2; ++e) {
-          const __half2 h2 = __floats2half2_rn(__uint_as_float(o[2 * e]) * inv_prev, __uint_as_float(o[2 * e + 1]) * inv_prev);
-          wd[e] = *reinterpret_cast<const uint32_t*>(&h2);
-        }
-        __half* dst = p.out + orow_prev * p.N + ocol_prev;
-        if constexpr (OC == 8) *reinterpret_cast<uint4*>(dst) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-        else *reinterpret_cast<uint2*>(dst) = make_uint2(wd[0], wd[1]);
-      }
-    };
-    for (AttGroup c = first; c.valid; advance(c), ++gcount) {
-      const int g = c.item / p.groups, grp = c.item - g * p.groups;
-      const int qi = c.m * 128 + r;
-      const bool warp_live = c.m * 128 + q * 32 < p.len;     // warp-uniform: any valid query row in this warp
-      float* exm = s_ex + ((gcount & 1) * 4) * 128;          // row-max exchange  [4 quarters][128]
-      float* exs = s_ex + (8 + (gcount & 1) * 4) * 128;      // row-sum exchange
-      float mx = -INFINITY;
-      // ---- row maximum over this thread's columns
-      for (int sb = 0; sb < nsuper; ++sb) {
-        const uint32_t reg = (sjob + sb) & 1;
-        mbar_wait(b_sfull + 8 * reg, ((sjob + sb) >> 1) & 1);
-        tc_fence_after();
-        const int j1 = min(p.nblk, (sb + 1) * ATT_SUPER);
-        if (warp_live) {
-          for (int j = sb * ATT_SUPER; j < j1; ++j) {
-            const int nv = min(ATT_NB, p.len - j * ATT_NB) - cb;   // valid columns of this thread's quarter
-            if (nv <= 0) continue;
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(t_lane + reg * ATT_REGION + (j - sb * ATT_SUPER) * ATT_NB + cb, v);
-            tmem_ld_wait();
-            if (nv >= 16) {
+                  for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < nv) mx = fmaxf(mx, __uint_as_float(v[i]));
-            }
-          }
-        }
-        if (!resident) {   // the S region is recycled
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(b_sfree + 8 * reg);
-        }
-      }
-      if (!resident) sjob += nsuper;
-      exm[cq * 128 + r] = mx;
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      mx = fmaxf(fmaxf(exm[r], exm[128 + r]), fmaxf(exm[256 + r], exm[384 + r]));
-      // ---- probabilities -> P tiles (fp16, K-major SWIZZLE_128B), consumed by the P V MMAs
-      float sum = 0.f;
-      for (int sb = 0; sb < nsuper; ++sb, ++sjob) {
-        const uint32_t reg = sjob & 1;
-        if (!resident) {
-          mbar_wait(b_sfull + 8 * reg, (sjob >> 1) & 1);
-          tc_fence_after();
-        }
-        const int j1 = min(p.nblk, (sb + 1) * ATT_SUPER);
-        for (int j = sb * ATT_SUPER; j < j1; ++j, ++pjob) {
-          const uint32_t pb = pjob % ATT_PRING;
-          if (warp_live) {
-            const int nv = min(ATT_NB, p.len - j * ATT_NB) - cb;
-            uint32_t pk[8];
-            if (nv > 0) {
-              uint32_t v[16];
-              tmem_ld_32x32b_x16(t_lane + reg * ATT_REGION + (j - sb * ATT_SUPER) * ATT_NB + cb, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float e0 = ex2_fast(__uint_as_float(v[2 * i]) - mx);
-                float e1 = ex2_fast(__uint_as_float(v[2 * i + 1]) - mx);
-                if (nv < 16) {
-                  e0 = (2 * i < nv) ? e0 : 0.f;
-                  e1 = (2 * i + 1 < nv) ? e1 : 0.f;
+                  for (int i = 0; i < 32; ++i)
+                    if (i < nv) mx = fmaxf(mx, __uint_as_float(v[i]));
                 }
-                sum += e0 + e1;
-                const __half2 h2 = __floats2half2_rn(e0, e1);
-                pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
               }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) pk[i] = 0u;
             }
-            mbar_wait(b_pfree + 8 * pb, ((pjob / ATT_PRING) & 1) ^ 1);   // P tile consumed by its P V MMAs
-            const uint32_t sPw = sP + pb * 16384;
-            const uint32_t a0 = sPw + sw128_offset((uint32_t)r, (uint32_t)(cb >> 3));
-            const uint32_t a1 = sPw + sw128_offset((uint32_t)r, (uint32_t)(cb >> 3) + 1);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
-          } else {
-            mbar_wait(b_pfree + 8 * pb, ((pjob / ATT_PRING) & 1) ^ 1);
+            if (!resident) {   // the S region is recycled for the next super-block
+              tc_fence_before();
+              mbar_arrive(B.sfree + 8 * w);
+            }
           }
-          fence_proxy_async();
+          if (!resident) sjob += nsuper;
+          // combine the two column halves of the row through shared memory (named barrier of this warpgroup)
+          ex[set * 128 + r] = mx;
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
+          mx = fmaxf(mx, ex[(set ^ 1) * 128 + r]);
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");   // both halves read before the buffer is reused
+          // ---- probabilities -> P tiles (fp16, K-major SWIZZLE_128B), consumed by the P V MMAs
+          float sum = 0.f;
+          for (int sb = 0; sb < nsuper; ++sb, ++sjob) {
+            if (!resident) {
+              mbar_wait(B.sfull + 8 * w, sjob & 1);
+              tc_fence_after();
+            }
+            const int j1 = min(p.nblk, (sb + 1) * ATT_SUPER);
+            for (int j = sb * ATT_SUPER; j < j1; ++j, ++pjob) {
+              const uint32_t pb = pjob & 1;
+              if (warp_live) {
+                const int nv = min(ATT_NB, p.len - j * ATT_NB) - cb;
+                uint32_t pk[16];
+                if (nv > 0) {
+                  uint32_t v[32];
+                  tmem_ld_32x32b_x32(t_base + (j - sb * ATT_SUPER) * ATT_NB + cb, v);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    float e0 = ex2_fast(__uint_as_float(v[2 * i]) - mx);
+                    float e1 = ex2_fast(__uint_as_float(v[2 * i + 1]) - mx);
+                    if (nv < 32) {
+                      e0 = (2 * i < nv) ? e0 : 0.f;
+                      e1 = (2 * i + 1 < nv) ? e1 : 0.f;
+                    }
+                    sum += e0 + e1;
+                    const __half2 h2 = __floats2half2_rn(e0, e1);
+                    pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                }
+                // the P buffer of two blocks ago must have been consumed by its P V MMAs
+                mbar_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
+                const uint32_t sPw = sP + (w * 2 + pb) * 16384;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const uint32_t a0 = sPw + sw128_offset((uint32_t)r, (uint32_t)(cb >> 3) + c);
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
+                               "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+                }
+              } else {
+                mbar_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
+              }
+              if (j == j1 - 1) {   // last block of the super-block: the S region may be overwritten
+                tc_fence_before();
+                mbar_arrive(B.sfree + 8 * w);
+              }
+              fence_proxy_async();
+              mbar_arrive(B.pfull + 8 * (w * 2 + pb));
+            }
+          }
+          // row sums: combine the two column halves
+          ex[set * 128 + r] = sum;
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
+          sum += ex[(set ^ 1) * 128 + r];
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
+          // ---- O = sum_j P_j V_j complete; this thread stores HD/2 features of its row
+          mbar_wait(B.ofull + 8 * w, ohead & 1);
+          ++ohead;
+          tc_fence_after();
+          uint32_t o[HD / 2];
+          if constexpr (HD == 32) tmem_ld_32x32b_x16(t_base + ATT_O_COL + set * 16, o);
+          else tmem_ld_32x32b_x8(t_base + ATT_O_COL + set * 8, o);
+          tmem_ld_wait();
           tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (j == j1 - 1) mbar_arrive(b_sfree + 8 * reg);   // last block of the S job: region may be overwritten
-            mbar_arrive(b_pfull + 8 * pb);
+          mbar_arrive(B.ofree + 8 * w);
+          if (qi < p.len) {
+            const float inv = 1.f / sum;
+            uint4* dst = reinterpret_cast<uint4*>(p.out + p.map.row(g, qi) * p.N + head * HD + set * (HD / 2));
+#pragma unroll
+            for (int c = 0; c < HD / 16; ++c) {
+              uint32_t wd[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __half2 h2 = __floats2half2_rn(__uint_as_float(o[c * 8 + 2 * e]) * inv,
+                                                     __uint_as_float(o[c * 8 + 2 * e + 1]) * inv);
+                wd[e] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+              dst[c] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            }
           }
         }
       }
-      // row sums: combine the four column quarters
-      exs[cq * 128 + r] = sum;
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      sum = (exs[r] + exs[128 + r]) + (exs[256 + r] + exs[384 + r]);
-      // ---- epilogue of the previous group, then remember this one
-      if (have_prev) epilogue();
-      have_prev = true;
-      inv_prev = 1.f / sum;
-      orow_prev = qi < p.len ? p.map.row(g, qi) : -1;
-      ocol_prev = (grp * HPT + c.h) * HD + cq * OC;
-      oreg_prev = gcount & 1;
     }
-    if (have_prev) { epilogue(); }
   }
   tc_fence_before();
   __syncthreads();
@@ -456,10 +462,7 @@ static int tc_attention_launch(const __half* qkv, __half* out, SeqMap map, int m
   a.nblk = (a.len + ATT_NB - 1) / ATT_NB;
   a.mtiles = (a.len + 127) / 128;
   a.num_items = map.G * a.groups;
-  const size_t kv = (size_t)a.nblk * ATT_NB * 128;
-  const size_t fixed = 2 * 16384 + ATT_PRING * 16384 + 256 + 16 * 128 * 4 + 256;
-  a.vbufs = (fixed + 4 * kv <= 227 * 1024) ? 2 : 1;
-  const size_t smem = fixed + (2 + a.vbufs) * kv;
+  const size_t smem = 2 * 16384 + 4 * 16384 + 3 * (size_t)a.nblk * ATT_NB * 128 + 512 + 2048;
   if (smem > 227 * 1024) return 0;   // not handled: caller falls back
   CUtensorMap tmQ, tmKV;
   const long long tok = (long long)B * S * C;

@@ -192,6 +192,8 @@ int vatss_tc_attention(const void* qkv16, void* out16, int mode, int B, int S, i
 #define VATSS_STAGE_COUNT 9
 /* 0 frontend 1 qkv 2 attention 3 outproj+ln1 4 lstm-input 5 lstm-recurrent 6 ffn+ln2 7 tail 8 sisnr */
 unsigned long long vatss_launch_count(void);
+/* debug: device buffer (>= 128 int64) receiving a clock64 trace of CTA 0 of vatss_tc_lstm; NULL disables */
+void vatss_debug_lstm_trace(void* dev_buffer);
 int vatss_profile_begin(void);
 int vatss_profile_end(float* ms_per_stage, int* launches_per_stage, int n_stages);
 

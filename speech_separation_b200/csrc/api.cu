@@ -408,6 +408,8 @@ int vatss_tc_attention(const void* qkv16, void* out16, int mode, int B, int S, i
                               (cudaStream_t)stream);
 }
 
+void vatss_debug_lstm_trace(void* dev_buffer) { vatss::g_lstm_trace = (long long*)dev_buffer; }
+
 unsigned long long vatss_launch_count(void) { return g_launches.load(); }
 
 int vatss_profile_begin(void) {

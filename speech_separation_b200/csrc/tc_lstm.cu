@@ -41,6 +41,7 @@ struct TcLstmArgs {
   int act;         // 1: store relu(h) (DPTN feeds the LSTM output through ReLU only), 0: store h
   const float* bias;   // [ndir][512] b_ih + b_hh in accumulator-column order
   __half* out;         // [tokens, ndir*128]
+  long long* trace;    // optional clock64 trace of CTA 0 (debug), NULL in production
 };
 
 template <int NFEAT>
@@ -197,9 +198,13 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
         umma_commit_cg2(bar_accfull + 8 * c, 3);
       }
       umma_commit_cg2(bar_xempty, 3);
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
       for (int step = 1; step < len; ++step) {
         const int s = step & 1;
+        long long* T = (tr && step >= 8 && step < 12) ? p.trace + (step - 8) * 32 : nullptr;
+        if (T) T[0] = clock64();
         mbar_wait(bar_xfull + 8 * s, (step >> 1) & 1);
+        if (T) T[1] = clock64();
         tc_fence_after();
         // x-part of this step for chunks 0..2 as soon as the gate warps have drained them (step-1)
         for (int c = 0; c < LSTM_CHUNKS - 1; ++c) {
@@ -208,18 +213,23 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
           issue_x(c, s);
         }
         // h_{step-1} complete in both CTAs
+        if (T) T[2] = clock64();
         mbar_wait(bar_hfull, (step - 1) & 1);
+        if (T) T[3] = clock64();
         tc_fence_after();
         for (int c = 0; c < LSTM_CHUNKS - 1; ++c) {
           issue_h(c);
           umma_commit_cg2(bar_accfull + 8 * c, 3);
         }
+        if (T) T[4] = clock64();
         mbar_wait(bar_accempty + 8 * (LSTM_CHUNKS - 1), (step - 1) & 1);
+        if (T) T[5] = clock64();
         tc_fence_after();
         issue_x(LSTM_CHUNKS - 1, s);
         umma_commit_cg2(bar_xempty + 8 * s, 3);
         issue_h(LSTM_CHUNKS - 1);
         umma_commit_cg2(bar_accfull + 8 * (LSTM_CHUNKS - 1), 3);
+        if (T) T[6] = clock64();
       }
     }
     __syncwarp();
@@ -255,12 +265,16 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
       asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(accempty_leader[c]) : "r"(bar_accempty + 8 * c));
     asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(hfull_leader) : "r"(bar_hfull));
 
+    const bool trg = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && gw == 0 && lane == 0;
     for (int step = 0; step < len; ++step) {
       const int t = dir == 0 ? step : len - 1 - step;
+      long long* T = (trg && step >= 8 && step < 12) ? p.trace + (step - 8) * 32 + 8 : nullptr;
       uint32_t hp[LSTM_CHUNKS][8];   // packed fp16 h of this step (kept until all h-part MMAs have read sH)
 #pragma unroll
       for (int c = 0; c < LSTM_CHUNKS; ++c) {
+        if (T) T[3 * c] = clock64();
         mbar_wait(bar_accfull + 8 * c, step & 1);
+        if (T) T[3 * c + 1] = clock64();
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + c * 128 + half * 16;
         uint32_t gi[16], gf[16], gg[16], go[16];
@@ -300,6 +314,7 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
           dst[0] = make_uint4(ho[0], ho[1], ho[2], ho[3]);
           dst[1] = make_uint4(ho[4], ho[5], ho[6], ho[7]);
         }
+        if (T) T[3 * c + 2] = clock64();
       }
       // acc_full of the last chunk implies every h-part MMA of this step has finished reading sH
       if (step + 1 < len) {
@@ -318,6 +333,7 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
         __syncwarp();
         if (lane == 0)
           asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(hfull_leader) : "memory");
+        if (T) T[12] = clock64();
       }
     }
   }
@@ -377,11 +393,14 @@ static void pick_inter_tile(int C, int B, int* Kc, int* Bc) {
   }
 }
 
+long long* g_lstm_trace = nullptr;   // debug: set through vatss_debug_lstm_trace
+
 int launch_tc_lstm(const __half* x16, const __half* Wpack, const float* bias_pack, __half* out16, int mode, int B,
                    int S, int C, int NFEAT, int ndir, int act, cudaStream_t st) {
   TcLstmArgs a;
   a.mode = mode; a.ndir = ndir; a.B = B; a.S = S; a.C = C; a.act = act; a.bias = bias_pack; a.out = out16;
   a.Kc = 0; a.Bc = 0; a.kblocks = 1; a.G = 0;
+  a.trace = g_lstm_trace;
   if (mode == 0) {
     a.len = C;
     a.G = B * S;

@@ -19,6 +19,24 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def separate_in_micro_batches(net, mix, s1_embedding=None, s2_embedding=None, micro_batch=32):
+    """Run `net` over a large shard in micro-batches (bounded workspace: ~0.22 GB per 4-s utterance).
+
+    cfg-3 of BASELINE.json gives every rank 128..512 ten-second utterances; the activations of one micro-batch of
+    32 x 10 s are ~17 GB, so the shard is streamed through the same workspace.  Returns the concatenated predictions.
+    """
+    outs1, outs2 = [], []
+    for lo in range(0, mix.shape[0], micro_batch):
+        hi = min(mix.shape[0], lo + micro_batch)
+        kw = {"mix": mix[lo:hi]}
+        if s1_embedding is not None:
+            kw["s1_embedding"], kw["s2_embedding"] = s1_embedding[lo:hi], s2_embedding[lo:hi]
+        out = net(**kw)
+        outs1.append(out["s1_pred"])
+        outs2.append(out["s2_pred"])
+    return {"s1_pred": torch.cat(outs1), "s2_pred": torch.cat(outs2)}
+
+
 def sisnr_sums(rows, rows_loss=None):
     """Local sums to be reduced: six per-pair SI-SNR sums, per-utterance-PIT SI-SNRi sum, count, loss sums x4."""
     rows = rows.double()

@@ -13,34 +13,54 @@ namespace vatss {
 // visual compression: vis[b,t,j] = sum_e emb_{j/(N/2)}[b,e,t] * Wv[j%(N/2),e] + bv[j%(N/2)]
 // (nn.Linear(E, N/2) applied to both lip-embedding streams, then concat; dptn_wav.py:173-179)
 // ----------------------------------------------------------------------------------------
-__global__ void k_visual_compress(const float* __restrict__ emb1, const float* __restrict__ emb2,
-                                  const float* __restrict__ Wv, const float* __restrict__ bv, int E, int Tv,
-                                  int N, float* __restrict__ vis) {
-  extern __shared__ float s_emb[];  // [2][E]
-  const int t = blockIdx.x, b = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) {
-    const float* src = (i < E) ? emb1 : emb2;
-    int e = (i < E) ? i : i - E;
-    s_emb[i] = src[((size_t)b * E + e) * Tv + t];
-  }
-  __syncthreads();
-  const int half = N / 2;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    const int which = j / half, jj = j % half;
-    const float* w = Wv + (size_t)jj * E;
-    const float* x = s_emb + which * E;
-    float acc = 0.f;
-    for (int e = 0; e < E; ++e) acc = fmaf(w[e], x[e], acc);
-    vis[((size_t)b * Tv + t) * N + j] = acc + bv[jj];
+// One CTA = (utterance b, stream, 32 video frames): the (E x 32) slab of the embedding is read with frames
+// contiguous (coalesced), W in 64-column slabs; each thread accumulates 8 outputs of one frame.
+constexpr int VC_T = 32, VC_E = 64;
+__global__ void __launch_bounds__(256)
+k_visual_compress(const float* __restrict__ emb1, const float* __restrict__ emb2, const float* __restrict__ Wv,
+                  const float* __restrict__ bv, int E, int Tv, int N, float* __restrict__ vis) {
+  __shared__ float sE[VC_E][VC_T + 1];
+  __shared__ float sW[64][VC_E + 1];
+  const int half = N / 2;                    // outputs per stream (<= 64 per pass)
+  const int t0 = blockIdx.x * VC_T, which = blockIdx.y, b = blockIdx.z;
+  const float* emb = (which == 0 ? emb1 : emb2) + (size_t)b * E * Tv;
+  const int tl = threadIdx.x & 31, jg = threadIdx.x >> 5;   // frame, group of 8 outputs
+  for (int j0 = 0; j0 < half; j0 += 64) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int e0 = 0; e0 < E; e0 += VC_E) {
+      for (int i = threadIdx.x; i < VC_E * VC_T; i += blockDim.x) {
+        const int e = i / VC_T, t = i - e * VC_T;
+        sE[e][t] = (e0 + e < E && t0 + t < Tv) ? emb[(size_t)(e0 + e) * Tv + t0 + t] : 0.f;
+      }
+      for (int i = threadIdx.x; i < 64 * VC_E; i += blockDim.x) {
+        const int j = i / VC_E, e = i - j * VC_E;
+        sW[j][e] = (j0 + j < half && e0 + e < E) ? Wv[(size_t)(j0 + j) * E + e0 + e] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int e = 0; e < VC_E; ++e) {
+        const float x = sE[e][tl];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(sW[jg * 8 + i][e], x, acc[i]);
+      }
+      __syncthreads();
+    }
+    if (t0 + tl < Tv) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = j0 + jg * 8 + i;
+        if (j < half) vis[((size_t)b * Tv + t0 + tl) * N + which * half + j] = acc[i] + bv[j];
+      }
+    }
   }
 }
 
 int launch_visual_compress(const float* emb1, const float* emb2, const float* Wv, const float* bv, int B,
                            int E, int Tv, int N, float* vis, cudaStream_t st) {
-  dim3 grid(Tv, B);
-  int threads = ((N + 31) / 32) * 32;
-  if (threads > 256) threads = 256;
-  k_visual_compress<<<grid, threads, 2 * E * sizeof(float), st>>>(emb1, emb2, Wv, bv, E, Tv, N, vis);
+  dim3 grid(ceil_div(Tv, VC_T), 2, B);
+  k_visual_compress<<<grid, 256, 0, st>>>(emb1, emb2, Wv, bv, E, Tv, N, vis);
   VATSS_LAUNCH_OK();
   return 0;
 }

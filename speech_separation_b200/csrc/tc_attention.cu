@@ -101,6 +101,7 @@ struct TcAttnArgs {
   int nblk;       // 64-row kv blocks per sequence
   int mtiles;     // 128-query tiles per sequence
   int num_items;  // sequences * groups
+  int stream;     // 1: K / V super-blocks stream through a shared-memory ring (sequence too long to keep resident)
   SeqMap map;
   __half* out;    // (tokens, N)
 };
@@ -110,6 +111,8 @@ constexpr int ATT_NB = 64;             // kv rows per block = one SWIZZLE_128B k
 constexpr int ATT_SUPER = 3;           // 64-row kv blocks per S job: one N <= 192 MMA fills the whole S region
 constexpr uint32_t ATT_WG_COLS = 256;  // TMEM columns per warpgroup: 192 (S region) + 32 (O)
 constexpr uint32_t ATT_O_COL = 192;
+constexpr int ATT_RING = 4;            // streaming mode: ring stages of one super-block (3 x 64 rows x 128 B = 24 KB)
+constexpr uint32_t ATT_STAGE_BYTES = ATT_SUPER * ATT_NB * 128;
 
 // MN-major (N contiguous) B operand with 128-byte rows, SWIZZLE_128B: 8-row (K) groups 1024 B apart
 __device__ __forceinline__ uint64_t smem_desc_sw128_mnmajor(uint32_t smem_addr) {
@@ -153,9 +156,11 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
   const uint32_t KV_BYTES = (uint32_t)p.nblk * ATT_NB * 128u;
   const uint32_t sQ = base;                        // [2][128 x 128 B]
   const uint32_t sP = sQ + 2 * 16384;              // [2 wg][2][128 x 128 B]
-  const uint32_t sK = sP + 4 * 16384;              // [2] double buffered across items
+  const uint32_t sK = sP + 4 * 16384;              // [2] double buffered across items   (resident mode)
   const uint32_t sV = sK + 2 * KV_BYTES;
-  const uint32_t bars = sV + KV_BYTES;
+  const uint32_t sRing = sP + 4 * 16384;           // [ATT_RING] K / V super-blocks      (streaming mode)
+  const bool stream = p.stream != 0;
+  const uint32_t bars = stream ? sRing + ATT_RING * ATT_STAGE_BYTES : sV + KV_BYTES;
   AttBars B;
   B.kfull = bars; B.kfree = bars + 16;             // 2 each
   B.vfull = bars + 32; B.vfree = bars + 40;
@@ -164,6 +169,7 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
   B.pfull = bars + 176; B.pfree = bars + 208;      // 4 each
   B.ofull = bars + 240; B.ofree = bars + 256;      // 2 each
   const uint32_t tmem_slot = bars + 272;
+  const uint32_t b_rfull = bars + 2336, b_rfree = bars + 2336 + 8 * ATT_RING;   // after the 2 KB exchange buffer
   float* s_mx = reinterpret_cast<float*>(smem + (bars + 288 - base));   // [2 wg][2 sets][128 rows]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool resident = p.nblk <= ATT_SUPER;       // all of S of a (tile, head) fits the S region: single S pass
@@ -178,6 +184,7 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
     for (int i = 0; i < 2; ++i) { mbar_init(B.sfull + 8 * i, 1); mbar_init(B.sfree + 8 * i, 256); }
     for (int i = 0; i < 4; ++i) { mbar_init(B.pfull + 8 * i, 256); mbar_init(B.pfree + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(B.ofull + 8 * i, 1); mbar_init(B.ofree + 8 * i, 256); }
+    for (int i = 0; i < ATT_RING; ++i) { mbar_init(b_rfull + 8 * i, 1); mbar_init(b_rfree + 8 * i, 2); }
     fence_mbar_init();
     prefetch_tmap(&tmapQ);
     prefetch_tmap(&tmapKV);
@@ -195,6 +202,7 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
       int it = 0, qn = 0;
+      uint32_t rseq = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
         const int g = item / p.groups, grp = item - g * p.groups;
         const int colq = grp * 64, colk = p.N + grp * 64, colv = 2 * p.N + grp * 64;
@@ -206,20 +214,40 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
           if (p.mode == 0) tma_load_2d(dst, tm, bar, col, (int)(row0 + r0));
           else tma_load_4d(dst, tm, bar, col, ck, r0, cb);
         };
-        const int kb = it & 1;
-        mbar_wait(B.kfree + 8 * kb, ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(B.kfull + 8 * kb, KV_BYTES);
-        for (int j = 0; j < p.nblk; ++j)
-          load_rows(&tmapKV, sK + kb * KV_BYTES + j * ATT_NB * 128, B.kfull + 8 * kb, colk, j * ATT_NB);
+        if (!stream) {
+          const int kb = it & 1;
+          mbar_wait(B.kfree + 8 * kb, ((it >> 1) & 1) ^ 1);
+          mbar_expect_tx(B.kfull + 8 * kb, KV_BYTES);
+          for (int j = 0; j < p.nblk; ++j)
+            load_rows(&tmapKV, sK + kb * KV_BYTES + j * ATT_NB * 128, B.kfull + 8 * kb, colk, j * ATT_NB);
+        }
         for (int m = 0; m < p.mtiles; ++m, ++qn) {
           const int s = qn & 1;
           mbar_wait(B.qfree + 8 * s, ((qn >> 1) & 1) ^ 1);
           mbar_expect_tx(B.qfull + 8 * s, 16384);
           load_rows(&tmapQ, sQ + s * 16384, B.qfull + 8 * s, colq, m * 128);
-          if (m == 0) {
-            mbar_wait(B.vfree, (it & 1) ^ 1);
-            mbar_expect_tx(B.vfull, KV_BYTES);
-            for (int j = 0; j < p.nblk; ++j) load_rows(&tmapKV, sV + j * ATT_NB * 128, B.vfull, colv, j * ATT_NB);
+          if (!stream) {
+            if (m == 0) {
+              mbar_wait(B.vfree, (it & 1) ^ 1);
+              mbar_expect_tx(B.vfull, KV_BYTES);
+              for (int j = 0; j < p.nblk; ++j) load_rows(&tmapKV, sV + j * ATT_NB * 128, B.vfull, colv, j * ATT_NB);
+            }
+          } else {
+            // ring order = consumption order of the MMA warps: per head slot, pass A: K_0..K_{n-1}; pass B: K_0,V_0,K_1,V_1,...
+            auto push = [&](int col, int sb) {
+              const uint32_t st = rseq % ATT_RING;
+              mbar_wait(b_rfree + 8 * st, ((rseq / ATT_RING) & 1) ^ 1);
+              const int nb = min(ATT_SUPER, p.nblk - sb * ATT_SUPER);
+              mbar_expect_tx(b_rfull + 8 * st, nb * ATT_NB * 128);
+              for (int j = 0; j < nb; ++j)
+                load_rows(&tmapKV, sRing + st * ATT_STAGE_BYTES + j * ATT_NB * 128, b_rfull + 8 * st, col,
+                          (sb * ATT_SUPER + j) * ATT_NB);
+              ++rseq;
+            };
+            for (int hh = 0; hh < HPW; ++hh) {
+              for (int sb = 0; sb < nsuper; ++sb) push(colk, sb);
+              for (int sb = 0; sb < nsuper; ++sb) { push(colk, sb); push(colv, sb); }
+            }
           }
         }
       }
@@ -240,11 +268,20 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
           if (++c.m == p.mtiles) { c.m = 0; c.item += gridDim.x; ++c.it; c.valid = c.item < p.num_items; }
         }
       };
-      uint32_t sjob = 0, pjob = 0, ohead = 0;
+      uint32_t sjob = 0, pjob = 0, ohead = 0, rseq = 0, v_stage = 0;
       int k_seen = -1, q_seen = -1, v_seen = -1;
       // S super-block sb (kv blocks [3 sb, 3 sb + nb)) of group c into the S region of both warpgroups
       auto issue_s = [&](const Cur& c, int sb, bool last_job_of_group) {
-        if (k_seen != c.it) { mbar_wait(B.kfull + 8 * (c.it & 1), (c.it >> 1) & 1); k_seen = c.it; }
+        uint32_t kbase, rst = 0;
+        if (!stream) {
+          if (k_seen != c.it) { mbar_wait(B.kfull + 8 * (c.it & 1), (c.it >> 1) & 1); k_seen = c.it; }
+          kbase = sK + (c.it & 1) * KV_BYTES + sb * ATT_SUPER * ATT_NB * 128;
+        } else {
+          rst = rseq % ATT_RING;
+          mbar_wait(b_rfull + 8 * rst, (rseq / ATT_RING) & 1);
+          kbase = sRing + rst * ATT_STAGE_BYTES;
+          ++rseq;
+        }
         if (q_seen != c.qn) { mbar_wait(B.qfull + 8 * (c.qn & 1), (c.qn >> 1) & 1); q_seen = c.qn; }
         const int nb = min(ATT_SUPER, p.nblk - sb * ATT_SUPER);
         const uint32_t idesc_s = idesc_f16(128, nb * ATT_NB, 0);
@@ -256,20 +293,32 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
           for (int k16 = 0; k16 < HD / 16; ++k16) {
             const uint32_t koff = (uint32_t)(hsel * HD * 2 + k16 * 32) >> 4;
             const uint64_t a = smem_desc_sw128_kmajor(sQ + (c.qn & 1) * 16384) + koff;
-            const uint64_t b = smem_desc_sw128_kmajor(sK + (c.it & 1) * KV_BYTES + sb * ATT_SUPER * ATT_NB * 128) + koff;
+            const uint64_t b = smem_desc_sw128_kmajor(kbase) + koff;
             umma_f16<1>(tmem + w * ATT_WG_COLS, a, b, idesc_s, k16 > 0 ? 1u : 0u);
           }
           umma_commit(B.sfull + 8 * w);
+          if (stream) umma_commit(b_rfree + 8 * rst);   // this warp's S MMAs were the last readers of the K stage
         }
         ++sjob;
         if (last_job_of_group && c.hh == HPW - 1) {
           umma_commit(B.qfree + 8 * (c.qn & 1));                       // last S MMA reading this Q tile
-          if (c.m == p.mtiles - 1) umma_commit(B.kfree + 8 * (c.it & 1));   // ... and this K buffer
+          if (!stream && c.m == p.mtiles - 1) umma_commit(B.kfree + 8 * (c.it & 1));   // ... and this K buffer
         }
       };
       // O += P_j V_j for group c, both warpgroups
       auto issue_pv = [&](const Cur& c, int j) {
-        if (v_seen != c.it) { mbar_wait(B.vfull, c.it & 1); v_seen = c.it; }
+        uint32_t vbase;
+        if (!stream) {
+          if (v_seen != c.it) { mbar_wait(B.vfull, c.it & 1); v_seen = c.it; }
+          vbase = sV + j * ATT_NB * 128;
+        } else {
+          if (j % ATT_SUPER == 0) {   // first block of a V super-block: next ring stage
+            v_stage = rseq % ATT_RING;
+            mbar_wait(b_rfull + 8 * v_stage, (rseq / ATT_RING) & 1);
+            ++rseq;
+          }
+          vbase = sRing + v_stage * ATT_STAGE_BYTES + (j % ATT_SUPER) * ATT_NB * 128;
+        }
         const uint32_t pb = pjob & 1;
         {
           const int hsel = w * HPW + c.hh;
@@ -280,16 +329,17 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
 #pragma unroll
           for (int k16 = 0; k16 < ATT_NB / 16; ++k16) {
             const uint64_t a = smem_desc_sw128_kmajor(sP + (w * 2 + pb) * 16384) + (uint64_t)(k16 * 2);
-            const uint64_t bv = smem_desc_sw128_mnmajor(sV + (j * ATT_NB + k16 * 16) * 128 + hsel * HD * 2);
+            const uint64_t bv = smem_desc_sw128_mnmajor(vbase + k16 * 16 * 128 + hsel * HD * 2);
             umma_f16<1>(d_o, a, bv, idesc_o, (j > 0 || k16 > 0) ? 1u : 0u);
           }
           umma_commit(B.pfree + 8 * (w * 2 + pb));
           if (j == p.nblk - 1) umma_commit(B.ofull + 8 * w);
+          if (stream && (j % ATT_SUPER == ATT_SUPER - 1 || j == p.nblk - 1)) umma_commit(b_rfree + 8 * v_stage);
         }
         ++pjob;
         if (j == p.nblk - 1) {
           ++ohead;
-          if (c.hh == HPW - 1 && c.m == p.mtiles - 1) umma_commit(B.vfree);   // last P V reading this item's V
+          if (!stream && c.hh == HPW - 1 && c.m == p.mtiles - 1) umma_commit(B.vfree);   // last P V reading this item's V
         }
       };
       Cur cur = {(int)blockIdx.x, 0, 0, 0, 0, (int)blockIdx.x < p.num_items};
@@ -462,8 +512,13 @@ static int tc_attention_launch(const __half* qkv, __half* out, SeqMap map, int m
   a.nblk = (a.len + ATT_NB - 1) / ATT_NB;
   a.mtiles = (a.len + 127) / 128;
   a.num_items = map.G * a.groups;
-  const size_t smem = 2 * 16384 + 4 * 16384 + 3 * (size_t)a.nblk * ATT_NB * 128 + 512 + 2048;
-  if (smem > 227 * 1024) return 0;   // not handled: caller falls back
+  const size_t fixed = 2 * 16384 + 4 * 16384 + 512 + 2048 + 128;
+  size_t smem = fixed + 3 * (size_t)a.nblk * ATT_NB * 128;
+  a.stream = 0;
+  if (smem > 227 * 1024) {   // K / V do not fit: stream them through the ring (two-pass softmax re-reads K)
+    a.stream = 1;
+    smem = fixed + (size_t)ATT_RING * ATT_STAGE_BYTES;
+  }
   CUtensorMap tmQ, tmKV;
   const long long tok = (long long)B * S * C;
   if (mode == 0) {

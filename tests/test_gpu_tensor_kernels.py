@@ -149,6 +149,8 @@ ATT_CASES = [
     (0, 2, 3, 150, 64, 4),       # N = 64: head dim 16, one group of four heads
     (1, 2, 283, 3, 64, 4),
     (0, 1, 2, 250, 128, 4),      # longer chunk: two kv blocks of 128
+    (1, 1, 710, 3, 128, 4),      # inter 10 s: K / V streamed through the shared-memory ring
+    (1, 2, 400, 2, 64, 4),
 ]
 
 

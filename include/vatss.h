@@ -174,8 +174,10 @@ int vatss_tc_gemm(int epi, const void* A16, long long lda, const void* W16, cons
 /* vatss_tc_lstm: nn.LSTM(N->128) recurrence (src/model/dptn.py:23-29,49) on a CTA pair, input and recurrent
  * contractions fused per time step.  x16 (B,S,C,N) fp16 token-major; params: fp32 nn.LSTM tensors of the
  * forward (and reverse, if ndir=2) direction; out16 (B*S*C, ndir*128) fp16, relu(h) if act=1.
- * mode 0 = intra-chunk sequences, 1 = inter-chunk.  wpack: ndir*512*(N+128) halfs, bias_pack: ndir*512 floats. */
-int vatss_tc_lstm(const void* x16, const float* const* lstm_params /* [8]: Wih,Whh,bih,bhh fwd then rev */,
+ * mode 0 = intra-chunk sequences, 1 = inter-chunk.  wpack: ndir*512*(N+128) halfs (ndir*512*(2N+128) with x16lo),
+ * bias_pack: ndir*512 floats. */
+int vatss_tc_lstm(const void* x16, const void* x16lo /* NULL, or half(x - half(x)): hi/lo split variant, N = 64 */,
+                  const float* const* lstm_params /* [8]: Wih,Whh,bih,bhh fwd then rev */,
                   void* out16, int mode, int B, int S, int C, int N, int ndir, int act, void* wpack,
                   float* bias_pack, void* stream);
 

@@ -98,7 +98,8 @@ int launch_visual_compress(const float* emb1, const float* emb2, const float* Wv
                            int B, int E, int Tv, int N, float* vis, cudaStream_t st);
 int launch_encoder(const float* mix, const float* Wenc, const float* vis, const float* gate,
                    const float* vln_w, const float* vln_b, int B, int T, int Tv, int N, int K, int L,
-                   int S, int C, int P, float* enc, float* seg, __half* seg16, cudaStream_t st);
+                   int S, int C, int P, float* enc, float* seg, __half* seg16, cudaStream_t st,
+                   __half* seg16lo = nullptr);
 int launch_segment_cm(const float* x, int B, int N, int L, int C, int P, float* out, cudaStream_t st);
 int launch_overlap_add_cm(const float* y, int B, int N, int S, int C, int P, float* out, cudaStream_t st);
 

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256)
 k_encoder(const float* __restrict__ mix, const float* __restrict__ Wenc, const float* __restrict__ vis,
           const float* __restrict__ gate, const float* __restrict__ vln_w, const float* __restrict__ vln_b,
           int T, int Tv, int N, int K, int L, int S, int C, int P, float* __restrict__ enc,
-          float* __restrict__ seg, __half* __restrict__ seg16) {
+          float* __restrict__ seg, __half* __restrict__ seg16, __half* __restrict__ seg16lo) {
   extern __shared__ float smem[];
   const int st = K / 2;
   const int b = blockIdx.y;
@@ -173,7 +173,11 @@ k_encoder(const float* __restrict__ mix, const float* __restrict__ Wenc, const f
           const int n = lane + 32 * i;
           if (i < NI && n < N) {
             if (seg) seg[row * N + n] = e[i];
-            if (seg16) seg16[row * N + n] = __float2half_rn(e[i]);
+            if (seg16) {
+              const __half hi = __float2half_rn(e[i]);
+              seg16[row * N + n] = hi;
+              if (seg16lo) seg16lo[row * N + n] = __float2half_rn(e[i] - __half2float(hi));
+            }
           }
         }
       }
@@ -183,12 +187,12 @@ k_encoder(const float* __restrict__ mix, const float* __restrict__ Wenc, const f
 
 int launch_encoder(const float* mix, const float* Wenc, const float* vis, const float* gate,
                    const float* vln_w, const float* vln_b, int B, int T, int Tv, int N, int K, int L, int S,
-                   int C, int P, float* enc, float* seg, __half* seg16, cudaStream_t st) {
+                   int C, int P, float* enc, float* seg, __half* seg16, cudaStream_t st, __half* seg16lo) {
   VATSS_CHECK_ARG(N <= 32 * ENC_MAX_NI, "encoder: num_features %d > %d unsupported", N, 32 * ENC_MAX_NI);
   dim3 grid(ceil_div(L, ENC_FRAMES_PER_BLOCK), B);
   size_t smem = ((size_t)K * N + (size_t)(ENC_FRAMES_PER_BLOCK - 1) * (K / 2) + K) * sizeof(float);
   k_encoder<<<grid, 256, smem, st>>>(mix, Wenc, vis, gate, vln_w, vln_b, T, Tv, N, K, L, S, C, P, enc, seg,
-                                     seg16);
+                                     seg16, seg16lo);
   VATSS_LAUNCH_OK();
   return 0;
 }

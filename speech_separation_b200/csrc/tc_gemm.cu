@@ -98,6 +98,7 @@ struct TcGemmArgs {
   long long ldo32;
   __half* out16;
   long long ldo16;
+  __half* out16lo;   // optional: half(value - half(value)) (hi/lo split for the PRECISE LSTM), same pitch as out16
   int act16;  // activation applied to the fp16 copy only: 0 none, 1 relu, 2 prelu
   const float* prelu_a;
 };
@@ -381,6 +382,19 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
               pk[j] = *reinterpret_cast<const uint32_t*>(&h);
             }
             staged_store_f16(p.out16 + row0 * p.ldo16 + c0, p.ldo16, rows_valid, stage, lane, pk);
+            if (p.out16lo) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const __half2 hi = *reinterpret_cast<const __half2*>(&pk[j]);
+                const float2 hf = __half22float2(hi);
+                float a = v[c0 + 2 * j], b = v[c0 + 2 * j + 1];
+                if (p.act16 == 1) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                else if (p.act16 == 2) { a = a >= 0.f ? a : slope * a; b = b >= 0.f ? b : slope * b; }
+                const __half2 lo = __floats2half2_rn(a - hf.x, b - hf.y);
+                pk[j] = *reinterpret_cast<const uint32_t*>(&lo);
+              }
+              staged_store_f16(p.out16lo + row0 * p.ldo16 + c0, p.ldo16, rows_valid, stage, lane, pk);
+            }
           }
         }
       }
@@ -434,7 +448,7 @@ static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const
 int launch_tc_gemm(int epi, const __half* A, long long lda, const __half* W, const float* bias, const float* res,
                    long long ldr, const float* ln_w, const float* ln_b, float* out32, long long ldo32, __half* out16,
                    long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int KDIM,
-                   cudaStream_t st) {
+                   cudaStream_t st, __half* out16lo) {
   if (M == 0) return 0;
   VATSS_CHECK_ARG(((uintptr_t)A & 15) == 0 && (lda * 2) % 16 == 0, "tc_gemm: A must be 16-byte aligned with 16-byte row pitch");
   TcGemmArgs a;
@@ -442,6 +456,7 @@ int launch_tc_gemm(int epi, const __half* A, long long lda, const __half* W, con
   a.num_tiles = (int)((M + 127) / 128);
   a.bias = bias; a.res = res; a.ldr = ldr; a.ln_w = ln_w; a.ln_b = ln_b;
   a.out32 = out32; a.ldo32 = ldo32; a.out16 = out16; a.ldo16 = ldo16; a.act16 = act16; a.prelu_a = prelu_a;
+  a.out16lo = out16lo;
   if (epi == TC_EPI_F16) VATSS_CHECK_ARG(out16 != nullptr, "tc_gemm: fp16 output missing");
   if (epi == TC_EPI_F32) VATSS_CHECK_ARG(out32 != nullptr, "tc_gemm: fp32 output missing");
   if (epi == TC_EPI_LN || epi == TC_EPI_LN_POST)

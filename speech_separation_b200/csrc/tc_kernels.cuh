@@ -19,16 +19,18 @@ extern long long* g_lstm_trace;   // debug trace buffer of k_tc_lstm (NULL in pr
 //   TC_EPI_LN_POST -> out32 = LN(.) + res, out16 = act16(out32)
 int launch_tc_gemm(int epi, const __half* A, long long lda, const __half* W, const float* bias, const float* res,
                    long long ldr, const float* ln_w, const float* ln_b, float* out32, long long ldo32, __half* out16,
-                   long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int KDIM, cudaStream_t st);
+                   long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int KDIM, cudaStream_t st,
+                   __half* out16lo = nullptr);
 
 // Persistent LSTM recurrence on a CTA pair (tc_lstm.cu).  x16: token-major (B,S,C,NFEAT) fp16 activation,
 // Wpack / bias_pack from launch_pack_lstm, out16: (tokens, ndir*128) fp16 (relu(h) when act=1).
 // mode 0: intra-chunk sequences (time = chunk position), mode 1: inter-chunk sequences (time = chunk index).
-int launch_tc_lstm(const __half* x16, const __half* Wpack, const float* bias_pack, __half* out16, int mode, int B,
-                   int S, int C, int NFEAT, int ndir, int act, cudaStream_t st);
-// Wpack: [ndir][512][NFEAT+128] fp16, bias_pack: [ndir][512] fp32
+// x16lo != NULL selects the PRECISE variant (N = 64): hi/lo fp16 splits of x and W_ih, accurate gate functions.
+int launch_tc_lstm(const __half* x16, const __half* x16lo, const __half* Wpack, const float* bias_pack, __half* out16,
+                   int mode, int B, int S, int C, int NFEAT, int ndir, int act, cudaStream_t st);
+// Wpack: [ndir][512][(precise ? 2 : 1) * NFEAT + 128] fp16, bias_pack: [ndir][512] fp32
 int launch_pack_lstm(const float* Wih, const float* Whh, const float* bih, const float* bhh, int N, int dir,
-                     __half* Wpack, float* bias_pack, cudaStream_t st);
+                     int precise, __half* Wpack, float* bias_pack, cudaStream_t st);
 
 // attention core on fp16 packed qkv (tokens, 3N) -> out16 (tokens, N); q is pre-scaled by log2(e)/sqrt(hd)
 // mode 0 intra / 1 inter (map must be intra_map / inter_map of (B,S,C)); force_simt selects the SIMT fallback

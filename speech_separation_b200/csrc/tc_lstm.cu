@@ -44,9 +44,13 @@ struct TcLstmArgs {
   long long* trace;    // optional clock64 trace of CTA 0 (debug), NULL in production
 };
 
-template <int NFEAT>
+// PRECISE (N = 64 only): the input contraction runs on fp16 hi/lo splits of both x and W_ih
+//   x W^T ~= x_hi W_hi^T + x_lo W_hi^T + x_hi W_lo^T       (lo = value - half(value), |lo| <= 2^-11 |value|)
+// because DPRNN's un-normalised residual stream makes fp16-rounded W_ih / x miss the 1e-3 tolerance.
+// Shared-memory layout is that of a 128-feature input: x tile = [x_hi | x_lo], weight rows = [W_hi | W_lo | W_hh].
+template <int NFEAT, bool PRECISE = false>
 struct TcLstmSmem {
-  static constexpr int KBX = NFEAT / 64;             // x k-blocks
+  static constexpr int KBX = PRECISE ? 2 : NFEAT / 64;   // x k-blocks
   static constexpr int KBT = KBX + 2;                // + 2 h k-blocks
   static constexpr int W_BLOCK = 64 * 128;           // 64 B-rows x 128 B
   static constexpr int W_BYTES = LSTM_CHUNKS * KBT * W_BLOCK;
@@ -66,11 +70,23 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return y;
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+// ~1e-6-accurate variants (two MUFU ops each: ex2 + rcp) for the PRECISE kernel
+__device__ __forceinline__ float sigmoid_acc(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+__device__ __forceinline__ float tanh_acc(float x) { return fmaf(2.0f, sigmoid_acc(2.0f * x), -1.0f); }
+template <bool PRECISE> __device__ __forceinline__ float act_sigmoid(float x) { return PRECISE ? sigmoid_acc(x) : sigmoid_fast(x); }
+template <bool PRECISE> __device__ __forceinline__ float act_tanh(float x) { return PRECISE ? tanh_acc(x) : tanh_fast(x); }
 
-template <int NFEAT>
+template <int NFEAT, bool PRECISE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
-k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapW, TcLstmArgs p) {
-  using L = TcLstmSmem<NFEAT>;
+k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapXlo,
+          const __grid_constant__ CUtensorMap tmapW, TcLstmArgs p) {
+  static_assert(!PRECISE || NFEAT == 64, "the hi/lo split variant is built for 64 input features");
+  using L = TcLstmSmem<NFEAT, PRECISE>;
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t base = smem_u32(smem);
   const uint32_t sW = base + L::OFF_W, sX = base + L::OFF_X, sH = base + L::OFF_H;
@@ -159,8 +175,10 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
         if (leader) mbar_expect_tx(bar_xfull + 8 * s, 2 * L::KBX * box_bytes);
         for (int kb = 0; kb < L::KBX; ++kb) {
           const uint32_t dst = sX + s * L::X_STAGE + kb * 16384;
-          if (p.mode == 0) tma_load_4d_cg2(dst, &tmapX, xfull_leader[s], kb * 64, t, c0, 0);
-          else tma_load_4d_cg2(dst, &tmapX, xfull_leader[s], kb * 64, c1, t, c2);
+          const CUtensorMap* tm = (PRECISE && kb == 1) ? &tmapXlo : &tmapX;   // k-block 1 = x_lo in PRECISE mode
+          const int f0 = PRECISE ? 0 : kb * 64;
+          if (p.mode == 0) tma_load_4d_cg2(dst, tm, xfull_leader[s], f0, t, c0, 0);
+          else tma_load_4d_cg2(dst, tm, xfull_leader[s], f0, c1, t, c2);
         }
       }
     }
@@ -173,12 +191,26 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
     // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
     if (leader && lane == 0) {
       auto issue_x = [&](int c, int s) {
+        if constexpr (!PRECISE) {
 #pragma unroll
-        for (int k16 = 0; k16 < NFEAT / 16; ++k16) {
-          const int kb = k16 >> 2, kk = k16 & 3;
-          const uint64_t a = smem_desc_sw128_kmajor(sX + s * L::X_STAGE + kb * 16384) + (uint64_t)(kk * 2);
-          const uint64_t b = smem_desc_sw128_kmajor(sW + (c * L::KBT + kb) * L::W_BLOCK) + (uint64_t)(kk * 2);
-          umma_f16<2>(tmem + c * 128, a, b, IDESC, k16 > 0 ? 1u : 0u);
+          for (int k16 = 0; k16 < NFEAT / 16; ++k16) {
+            const int kb = k16 >> 2, kk = k16 & 3;
+            const uint64_t a = smem_desc_sw128_kmajor(sX + s * L::X_STAGE + kb * 16384) + (uint64_t)(kk * 2);
+            const uint64_t b = smem_desc_sw128_kmajor(sW + (c * L::KBT + kb) * L::W_BLOCK) + (uint64_t)(kk * 2);
+            umma_f16<2>(tmem + c * 128, a, b, IDESC, k16 > 0 ? 1u : 0u);
+          }
+        } else {
+          // x_hi W_hi + x_lo W_hi + x_hi W_lo: (A k-block, B k-block) = (0,0), (1,0), (0,1)
+#pragma unroll
+          for (int t3 = 0; t3 < 3; ++t3) {
+            const int akb = t3 == 1 ? 1 : 0, bkb = t3 == 2 ? 1 : 0;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t a = smem_desc_sw128_kmajor(sX + s * L::X_STAGE + akb * 16384) + (uint64_t)(kk * 2);
+              const uint64_t b = smem_desc_sw128_kmajor(sW + (c * L::KBT + bkb) * L::W_BLOCK) + (uint64_t)(kk * 2);
+              umma_f16<2>(tmem + c * 128, a, b, IDESC, (t3 > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
         }
       };
       auto issue_h = [&](int c) {
@@ -292,13 +324,13 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
         float hv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float ig = sigmoid_fast(__uint_as_float(gi[j]) + bc[j]);
-          const float fg = sigmoid_fast(__uint_as_float(gf[j]) + bc[32 + j]);
-          const float g_ = tanh_fast(__uint_as_float(gg[j]) + bc[64 + j]);
-          const float og = sigmoid_fast(__uint_as_float(go[j]) + bc[96 + j]);
+          const float ig = act_sigmoid<PRECISE>(__uint_as_float(gi[j]) + bc[j]);
+          const float fg = act_sigmoid<PRECISE>(__uint_as_float(gf[j]) + bc[32 + j]);
+          const float g_ = act_tanh<PRECISE>(__uint_as_float(gg[j]) + bc[64 + j]);
+          const float og = act_sigmoid<PRECISE>(__uint_as_float(go[j]) + bc[96 + j]);
           const float cc = fmaf(fg, cst[c][j], ig * g_);
           cst[c][j] = cc;
-          hv[j] = og * tanh_fast(cc);
+          hv[j] = og * act_tanh<PRECISE>(cc);
         }
         uint32_t ho[8];
 #pragma unroll
@@ -343,30 +375,34 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
   if (warp == 1) tmem_dealloc<2>(tmem, 512);
 }
 
-template <int NFEAT>
-static int tc_lstm_launch(const __half* x16, const __half* Wpack, const TcLstmArgs& a, cudaStream_t st) {
-  using L = TcLstmSmem<NFEAT>;
+template <int NFEAT, bool PRECISE>
+static int tc_lstm_launch(const __half* x16, const __half* x16lo, const __half* Wpack, const TcLstmArgs& a,
+                          cudaStream_t st) {
+  using L = TcLstmSmem<NFEAT, PRECISE>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
-  CUtensorMap tmX, tmW;
-  if (a.mode == 0) {
-    const uint64_t dims[4] = {(uint64_t)NFEAT, (uint64_t)a.C, (uint64_t)a.G, 1};
-    const uint64_t str[3] = {(uint64_t)NFEAT * 2, (uint64_t)a.C * NFEAT * 2, (uint64_t)a.G * a.C * NFEAT * 2};
-    const uint32_t box[4] = {64, 1, 128, 1};
-    if (make_tmap_f16(&tmX, x16, 4, dims, str, box)) return -1;
-  } else {
+  CUtensorMap tmX, tmXlo, tmW;
+  auto make_x = [&](CUtensorMap* tm, const __half* ptr) -> int {
+    if (a.mode == 0) {
+      const uint64_t dims[4] = {(uint64_t)NFEAT, (uint64_t)a.C, (uint64_t)a.G, 1};
+      const uint64_t str[3] = {(uint64_t)NFEAT * 2, (uint64_t)a.C * NFEAT * 2, (uint64_t)a.G * a.C * NFEAT * 2};
+      const uint32_t box[4] = {64, 1, 128, 1};
+      return make_tmap_f16(tm, ptr, 4, dims, str, box);
+    }
     const uint64_t dims[4] = {(uint64_t)NFEAT, (uint64_t)a.C, (uint64_t)a.S, (uint64_t)a.B};
     const uint64_t str[3] = {(uint64_t)NFEAT * 2, (uint64_t)a.C * NFEAT * 2, (uint64_t)a.S * a.C * NFEAT * 2};
     const uint32_t box[4] = {64, (uint32_t)a.Kc, 1, (uint32_t)a.Bc};
-    if (make_tmap_f16(&tmX, x16, 4, dims, str, box)) return -1;
-  }
+    return make_tmap_f16(tm, ptr, 4, dims, str, box);
+  };
+  if (make_x(&tmX, x16)) return -1;
+  if (make_x(&tmXlo, PRECISE ? x16lo : x16)) return -1;
   {
-    const uint64_t ktot = NFEAT + LSTM_H;
+    const uint64_t ktot = (PRECISE ? 2 * NFEAT : NFEAT) + LSTM_H;
     const uint64_t dims[2] = {ktot, (uint64_t)a.ndir * 2 * LSTM_CHUNKS * 64};
     const uint64_t str[1] = {ktot * 2};
     const uint32_t box[2] = {64, 64};
     if (make_tmap_f16(&tmW, Wpack, 2, dims, str, box)) return -1;
   }
-  auto kern = k_tc_lstm<NFEAT>;
+  auto kern = k_tc_lstm<NFEAT, PRECISE>;
   static bool configured = false;
   if (!configured) {
     VATSS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -374,7 +410,7 @@ static int tc_lstm_launch(const __half* x16, const __half* Wpack, const TcLstmAr
   }
   const int pairs = (a.num_tiles + 1) / 2;
   dim3 grid(2 * pairs, a.ndir);
-  kern<<<grid, LSTM_THREADS, L::TOTAL, st>>>(tmX, tmW, a);
+  kern<<<grid, LSTM_THREADS, L::TOTAL, st>>>(tmX, tmXlo, tmW, a);
   VATSS_LAUNCH_OK();
   return 0;
 }
@@ -395,8 +431,8 @@ static void pick_inter_tile(int C, int B, int* Kc, int* Bc) {
 
 long long* g_lstm_trace = nullptr;   // debug: set through vatss_debug_lstm_trace
 
-int launch_tc_lstm(const __half* x16, const __half* Wpack, const float* bias_pack, __half* out16, int mode, int B,
-                   int S, int C, int NFEAT, int ndir, int act, cudaStream_t st) {
+int launch_tc_lstm(const __half* x16, const __half* x16lo, const __half* Wpack, const float* bias_pack, __half* out16,
+                   int mode, int B, int S, int C, int NFEAT, int ndir, int act, cudaStream_t st) {
   TcLstmArgs a;
   a.mode = mode; a.ndir = ndir; a.B = B; a.S = S; a.C = C; a.act = act; a.bias = bias_pack; a.out = out16;
   a.Kc = 0; a.Bc = 0; a.kblocks = 1; a.G = 0;
@@ -412,8 +448,12 @@ int launch_tc_lstm(const __half* x16, const __half* Wpack, const float* bias_pac
     a.num_tiles = a.kblocks * ((B + a.Bc - 1) / a.Bc);
   }
   if (a.num_tiles == 0 || a.len == 0) return 0;
-  if (NFEAT == 128) return tc_lstm_launch<128>(x16, Wpack, a, st);
-  if (NFEAT == 64) return tc_lstm_launch<64>(x16, Wpack, a, st);
+  if (x16lo != nullptr) {
+    VATSS_CHECK_ARG(NFEAT == 64, "tc_lstm: the hi/lo split variant needs num_features = 64");
+    return tc_lstm_launch<64, true>(x16, x16lo, Wpack, a, st);
+  }
+  if (NFEAT == 128) return tc_lstm_launch<128, false>(x16, nullptr, Wpack, a, st);
+  if (NFEAT == 64) return tc_lstm_launch<64, false>(x16, nullptr, Wpack, a, st);
   set_error("tc_lstm: num_features %d unsupported (64 or 128)", NFEAT);
   return -1;
 }
@@ -425,22 +465,30 @@ int launch_tc_lstm(const __half* x16, const __half* Wpack, const float* bias_pac
 //   bias_pack[dir][128*c + 32*gate + u] = b_ih + b_hh of (gate, unit 32*c+u)   (accumulator-column order)
 // ------------------------------------------------------------------------------------------
 __global__ void k_pack_lstm(const float* __restrict__ Wih, const float* __restrict__ Whh,
-                            const float* __restrict__ bih, const float* __restrict__ bhh, int N, int dir,
+                            const float* __restrict__ bih, const float* __restrict__ bhh, int N, int dir, int precise,
                             __half* __restrict__ Wpack, float* __restrict__ bias_pack) {
-  const int ktot = N + LSTM_H;
+  const int nx = precise ? 2 * N : N;   // precise: [half(W) | half(W - half(W))]
+  const int ktot = nx + LSTM_H;
   const int prow = blockIdx.x;  // 0..511 within this direction: (rank, c, j)
   const int rank = prow / 256, c = (prow % 256) / 64, j = prow % 64;
   const int gate = 2 * rank + j / 32, unit = 32 * c + j % 32;
   const int src = gate * LSTM_H + unit;
   __half* dst = Wpack + ((size_t)dir * 512 + prow) * ktot;
-  for (int k = threadIdx.x; k < ktot; k += blockDim.x)
-    dst[k] = __float2half_rn(k < N ? Wih[(size_t)src * N + k] : Whh[(size_t)src * LSTM_H + (k - N)]);
+  for (int k = threadIdx.x; k < ktot; k += blockDim.x) {
+    float v;
+    if (k < N) v = Wih[(size_t)src * N + k];
+    else if (k < nx) {
+      const float w = Wih[(size_t)src * N + (k - N)];
+      v = w - __half2float(__float2half_rn(w));
+    } else v = Whh[(size_t)src * LSTM_H + (k - nx)];
+    dst[k] = __float2half_rn(v);
+  }
   if (threadIdx.x == 0) bias_pack[dir * 512 + 128 * c + 32 * gate + unit % 32] = bih[src] + bhh[src];
 }
 
 int launch_pack_lstm(const float* Wih, const float* Whh, const float* bih, const float* bhh, int N, int dir,
-                     __half* Wpack, float* bias_pack, cudaStream_t st) {
-  k_pack_lstm<<<512, 128, 0, st>>>(Wih, Whh, bih, bhh, N, dir, Wpack, bias_pack);
+                     int precise, __half* Wpack, float* bias_pack, cudaStream_t st) {
+  k_pack_lstm<<<512, 128, 0, st>>>(Wih, Whh, bih, bhh, N, dir, precise, Wpack, bias_pack);
   VATSS_LAUNCH_OK();
   return 0;
 }

@@ -54,7 +54,7 @@ size_t carve_packed(const vatss_model_desc* d, void* buf, Packed* out) {
     s.bin = b.take<float>(dprnn ? 0 : 3 * N);
     s.wout = b.take<__half>(dprnn ? 0 : N * N);
     s.wffn = b.take<__half>(N * ndir * H);
-    s.wlstm = b.take<__half>((size_t)ndir * 512 * (N + 128));
+    s.wlstm = b.take<__half>((size_t)ndir * 512 * ((dprnn ? 2 : 1) * N + 128));   // DPRNN: [W_hi | W_lo | W_hh]
     s.blstm = b.take<float>((size_t)ndir * 512);
   }
   p.wspk = b.take<__half>(2 * N * N);
@@ -87,7 +87,7 @@ int to_half(const float* src, __half* dst, long long rows, int cols, int scaled_
 // ---- workspace ----------------------------------------------------------------------------
 struct Work {
   float *enc32, *vis, *xa32, *xb32, *y32, *ola32, *u32, *hT, *hG, *proj;
-  __half *xa16, *xb16, *qkv16, *att16, *rnn16, *ola16;
+  __half *xa16, *xb16, *xa16lo, *xb16lo, *qkv16, *att16, *rnn16, *ola16;
 };
 
 size_t carve_work(const vatss_model_desc* d, int B, int Tv, int L, int S, void* buf, Work* out) {
@@ -101,6 +101,8 @@ size_t carve_work(const vatss_model_desc* d, int B, int Tv, int L, int S, void* 
   w.xb32 = b.take<float>(tok * N);
   w.xa16 = b.take<__half>(tok * N);
   w.xb16 = b.take<__half>(tok * N);
+  w.xa16lo = b.take<__half>(dprnn ? tok * N : 0);   // lo halves of the hi/lo split LSTM input (DPRNN)
+  w.xb16lo = b.take<__half>(dprnn ? tok * N : 0);
   w.qkv16 = b.take<__half>(dprnn ? 0 : tok * 3 * N);
   w.att16 = b.take<__half>(dprnn ? 0 : tok * N);
   w.rnn16 = b.take<__half>(tok * 2 * H);
@@ -120,6 +122,7 @@ size_t carve_work(const vatss_model_desc* d, int B, int Tv, int L, int S, void* 
 bool tensor_engine_supports(const vatss_model_desc* d) {
   if (d->H != 128) return false;
   if (d->N != 128 && d->N != 64) return false;
+  if (d->kind == VATSS_KIND_DPRNN && d->N != 64) return false;   // hi/lo split LSTM exists for 64 input features
   if (d->kind != VATSS_KIND_DPRNN) {
     const int hd = d->N / d->heads;
     if (d->N % d->heads != 0 || (hd != 16 && hd != 32)) return false;
@@ -157,7 +160,7 @@ int tensor_engine_pack(const vatss_model_desc* d, const float* const* params, vo
       for (int dir = 0; dir < ndir; ++dir) {
         const int o = dir ? (VATSS_S_WIH_R - VATSS_S_WIH) : 0;
         if ((rc = launch_pack_lstm(sp(VATSS_S_WIH + o), sp(VATSS_S_WHH + o), sp(VATSS_S_BIH + o), sp(VATSS_S_BHH + o),
-                                   N, dir, s.wlstm, s.blstm, st)))
+                                   N, dir, dprnn ? 1 : 0, s.wlstm, s.blstm, st)))
           return rc;
       }
     }
@@ -189,7 +192,7 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
     }
     if ((rc = launch_encoder(mix, params[VATSS_P_ENCODER_W], av ? w.vis : nullptr, params[VATSS_P_GATE],
                              params[VATSS_P_VLN_W], params[VATSS_P_VLN_B], B, T, Tv, N, d->K, L, S, C, d->P, w.enc32,
-                             w.xa32, w.xa16, st)))
+                             w.xa32, w.xa16, st, dprnn ? w.xa16lo : nullptr)))
       return rc;
   }
   for (int blk = 0; blk < d->num_blocks; ++blk)
@@ -202,15 +205,16 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
       if (dprnn) {
         {
           StageScope sc(ST_LSTM_RECURRENT, st);
-          if ((rc = launch_tc_lstm(w.xa16, s.wlstm, s.blstm, w.rnn16, path, B, S, C, N, ndir, 0, st))) return rc;
+          if ((rc = launch_tc_lstm(w.xa16, w.xa16lo, s.wlstm, s.blstm, w.rnn16, path, B, S, C, N, ndir, 0, st))) return rc;
         }
         StageScope sc(ST_FFN_LN, st);
         if ((rc = launch_tc_gemm(TC_EPI_LN_POST, w.rnn16, ndir * H, s.wffn, sp(VATSS_S_FFN_B), w.xa32, N,
                                  sp(VATSS_S_LN2_W), sp(VATSS_S_LN2_B), w.xb32, N, w.xb16, N, last ? 2 : 0,
-                                 params[VATSS_P_PRELU], tok, N, ndir * H, st)))
+                                 params[VATSS_P_PRELU], tok, N, ndir * H, st, last ? nullptr : w.xb16lo)))
           return rc;
         float* t32 = w.xa32; w.xa32 = w.xb32; w.xb32 = t32;
         __half* t16 = w.xa16; w.xa16 = w.xb16; w.xb16 = t16;
+        t16 = w.xa16lo; w.xa16lo = w.xb16lo; w.xb16lo = t16;
       } else {
         {
           StageScope sc(ST_QKV, st);
@@ -230,7 +234,7 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
         }
         {
           StageScope sc(ST_LSTM_RECURRENT, st);
-          if ((rc = launch_tc_lstm(w.xb16, s.wlstm, s.blstm, w.rnn16, path, B, S, C, N, ndir, 1, st))) return rc;
+          if ((rc = launch_tc_lstm(w.xb16, nullptr, s.wlstm, s.blstm, w.rnn16, path, B, S, C, N, ndir, 1, st))) return rc;
         }
         StageScope sc(ST_FFN_LN, st);
         if ((rc = launch_tc_gemm(TC_EPI_LN, w.rnn16, ndir * H, s.wffn, sp(VATSS_S_FFN_B), w.xb32, N, sp(VATSS_S_LN2_W),

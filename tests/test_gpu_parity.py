@@ -358,17 +358,19 @@ def test_training_shape_forward_plus_loss(V):
     assert abs(float(out["loss"]) - want) < 1e-3
 
 
-def test_dprnn_tensor_engine_documented_precision(V, golden_dir):
-    """DPRNN on the tcgen05 engine (explicit request only): fp16 LSTM weights on an un-normalised residual stream
-    cost 2-4e-3 of waveform error; AUTO keeps DPRNN on the GENERIC engine for that reason."""
+def test_dprnn_runs_on_the_tensor_engine_within_tolerance(V, golden_dir):
+    """DPRNN (cfg-4 model) on the tcgen05 engine: hi/lo split LSTM input contraction + accurate gate functions keep the
+    un-normalised residual stream within the 1e-3 waveform tolerance (plain fp16 W_ih gives 2-4e-3)."""
+    from speech_separation_b200 import _lib
+
     z = np.load(os.path.join(golden_dir, "prod_dprnn_B2_T16000.npz"))
     mix, s1, s2, _, _ = make_inputs(2, 16000, seed=int(z["input_seed"]))
-    s1p, s2p = run(prod_net(V, "dprnn", "tensor"), "dprnn", mix)
+    net = prod_net(V, "dprnn", "auto")
+    s1p, s2p = run(net, "dprnn", mix)
+    assert _lib.load().vatss_packed_weight_bytes(ctypes.byref(net._desc)) > 0   # AUTO picked the tensor engine
     r1, r2 = rel_l2(s1p.cpu().numpy(), z["s1_pred"]), rel_l2(s2p.cpu().numpy(), z["s2_pred"])
     print(f"dprnn tensor engine rel-L2 {r1:.3e} {r2:.3e}")
-    assert r1 < 8e-3 and r2 < 8e-3
-    a1, a2 = run(prod_net(V, "dprnn", "auto"), "dprnn", mix)
-    assert rel_l2(a1.cpu().numpy(), z["s1_pred"]) < 2e-4
+    assert r1 <= WAVE_TOL and r2 <= WAVE_TOL
 
 
 def test_micro_batched_shard_equals_single_batch(V):

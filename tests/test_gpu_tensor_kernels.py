@@ -129,7 +129,7 @@ def test_tc_lstm_matches_torch(lib, mode, B, S, C, N, ndir, act):
     out = torch.full((B * S * C, ndir * H), float("nan"), dtype=torch.float16, device=dev)
     wpack = torch.empty(ndir * 512 * (N + H), dtype=torch.float16, device=dev)
     bpack = torch.empty(ndir * 512, dtype=torch.float32, device=dev)
-    rc = lib.vatss_tc_lstm(_p(xd), table, _p(out), mode, B, S, C, N, ndir, act, _p(wpack), _p(bpack), None)
+    rc = lib.vatss_tc_lstm(_p(xd), None, table, _p(out), mode, B, S, C, N, ndir, act, _p(wpack), _p(bpack), None)
     _lib.check(rc, "vatss_tc_lstm")
     torch.cuda.synchronize()
     got = out.float().cpu().reshape(B, S, C, ndir * H)
@@ -182,3 +182,40 @@ def test_tc_attention_matches_torch(lib, mode, B, S, C, N, heads, force_simt):
     err = ((got - ref).norm() / ref.norm()).item()
     print(f"attention simt={force_simt} mode={mode} B={B} S={S} C={C} N={N}: rel err {err:.3e}")
     assert err < 2e-3
+
+
+@pytest.mark.parametrize("mode,B,S,C", [(0, 2, 40, 25), (1, 3, 11, 250)])
+def test_tc_lstm_hi_lo_split_variant(lib, mode, B, S, C):
+    """PRECISE variant (DPRNN): fp32 weights and inputs, hi/lo fp16 splits inside; must track the fp32 LSTM much
+    more closely than the plain fp16 kernel (whose error is dominated by the fp16 rounding of W_ih and x)."""
+    from speech_separation_b200 import _lib
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3 + mode)
+    N, H, ndir = 64, 128, 2
+    rnn = torch.nn.LSTM(N, H, batch_first=True, bidirectional=True)
+    x = 3.0 * torch.randn(B, S, C, N)   # un-normalised magnitudes like DPRNN's residual stream
+    seqs = x.reshape(B * S, C, N) if mode == 0 else x.permute(0, 2, 1, 3).reshape(B * C, S, N)
+    with torch.no_grad():
+        ref = rnn(seqs)[0]
+    ref = ref.reshape(B, S, C, ndir * H) if mode == 0 else ref.reshape(B, C, S, ndir * H).permute(0, 2, 1, 3)
+    names = ["weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"]
+    keep = [getattr(rnn, n + suf).detach().to(dev).contiguous() for suf in ("", "_reverse") for n in names]
+    table = (ctypes.c_void_p * 8)(*[t.data_ptr() for t in keep])
+    xd = x.to(dev)
+    hi = xd.half()
+    lo = (xd - hi.float()).half()
+    errs = []
+    for use_lo in (True, False):
+        out = torch.full((B * S * C, ndir * H), float("nan"), dtype=torch.float16, device=dev)
+        wpack = torch.empty(ndir * 512 * (2 * N + H), dtype=torch.float16, device=dev)
+        bpack = torch.empty(ndir * 512, dtype=torch.float32, device=dev)
+        rc = lib.vatss_tc_lstm(_p(hi), _p(lo) if use_lo else None, table, _p(out), mode, B, S, C, N, ndir, 0, _p(wpack),
+                               _p(bpack), None)
+        _lib.check(rc, "vatss_tc_lstm")
+        torch.cuda.synchronize()
+        got = out.float().cpu().reshape(B, S, C, ndir * H)
+        errs.append(((got - ref).norm() / ref.norm()).item())
+    print(f"lstm hi/lo mode={mode}: rel err precise {errs[0]:.3e}, plain fp16 {errs[1]:.3e}")
+    assert errs[0] < 4e-4           # output rounding to fp16 (2^-11) dominates
+    assert errs[0] < 0.7 * errs[1]

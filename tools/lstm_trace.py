@@ -19,7 +19,7 @@ for mode, B, S, C in [(0, 32, 283, 150), (1, 32, 283, 150)]:
     trace = torch.zeros(128, dtype=torch.int64, device=dev)
     for it in range(3):
         lib.vatss_debug_lstm_trace(P(trace) if it == 2 else None)
-        _lib.check(lib.vatss_tc_lstm(P(x), table, P(out), mode, B, S, C, N, ndir, 1, P(wpack), P(bpack), None), "lstm")
+        _lib.check(lib.vatss_tc_lstm(P(x), None, table, P(out), mode, B, S, C, N, ndir, 1, P(wpack), P(bpack), None), "lstm")
     torch.cuda.synchronize()
     lib.vatss_debug_lstm_trace(None)
     t = trace.cpu().reshape(4, 32)

@@ -105,10 +105,13 @@ struct TcGemmArgs {
 
 constexpr int TCG_THREADS = 192;   // TMA warp, MMA warp, 4 epilogue warps
 
-template <int NOUT, int KDIM, bool RES_TMA = false>
+// WSPLIT: W is stored as [half(W) | half(W - half(W))] (hi/lo split, 2 x KDIM columns) and both halves are
+// contracted with the same A tile - used where an fp16-rounded weight misses the tolerance (DPRNN fc).
+template <int NOUT, int KDIM, bool RES_TMA = false, bool WSPLIT = false>
 struct TcGemmSmem {
   static constexpr int KB = KDIM / 64;
-  static constexpr int W_BYTES = KB * NOUT * 128;
+  static constexpr int KBW = WSPLIT ? 2 * KB : KB;
+  static constexpr int W_BYTES = KBW * NOUT * 128;
   static constexpr int A_STAGE_BYTES = KB * 128 * 128;
   // residual tile [128 rows x NOUT fp32] as NOUT/32 column blocks of 128-byte rows (SWIZZLE_128B), TMA-prefetched
   static constexpr int RES_BYTES = RES_TMA ? 128 * NOUT * 4 : 0;
@@ -184,12 +187,12 @@ __device__ __forceinline__ void staged_store_f16(__half* __restrict__ g, long lo
   __syncwarp();
 }
 
-template <int NOUT, int KDIM, int EPI>
+template <int NOUT, int KDIM, int EPI, bool WSPLIT>
 __global__ void __launch_bounds__(TCG_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapW,
           const __grid_constant__ CUtensorMap tmapR, TcGemmArgs p) {
   constexpr bool RES_TMA = (EPI == TC_EPI_LN || EPI == TC_EPI_LN_POST);   // residual tile prefetched by TMA
-  using L = TcGemmSmem<NOUT, KDIM, RES_TMA>;
+  using L = TcGemmSmem<NOUT, KDIM, RES_TMA, WSPLIT>;
   static_assert(NOUT % 16 == 0 && NOUT <= 512 && KDIM % 64 == 0, "shape");
   static_assert(EPI != TC_EPI_LN && EPI != TC_EPI_LN_POST || NOUT <= 128, "LayerNorm epilogue needs the row in regs");
   extern __shared__ unsigned char smem_raw[];
@@ -239,7 +242,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_expect_tx(bar_w, L::W_BYTES);
-      for (int kb = 0; kb < L::KB; ++kb)
+      for (int kb = 0; kb < L::KBW; ++kb)
         for (int n0 = 0; n0 < NOUT; n0 += 64) tma_load_2d(sW + kb * NOUT * 128 + n0 * 128, &tmapW, bar_w, kb * 64, n0);
       int i = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
@@ -272,11 +275,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
           const int nn = (NOUT - n0) < 256 ? (NOUT - n0) : 256;
           const uint32_t idesc = idesc_f16(128, nn, 0);
 #pragma unroll
-          for (int k16 = 0; k16 < KDIM / 16; ++k16) {
-            const int kb = k16 >> 2, kk = k16 & 3;
-            const uint64_t a_desc = smem_desc_sw128_kmajor(sA + s * L::A_STAGE_BYTES + kb * 16384) + (uint64_t)(kk * 2);
-            const uint64_t b_desc = smem_desc_sw128_kmajor(sW + kb * NOUT * 128 + n0 * 128) + (uint64_t)(kk * 2);
-            umma_f16<1>(tmem + as * NOUT + n0, a_desc, b_desc, idesc, k16 > 0 ? 1u : 0u);
+          for (int part = 0; part < (WSPLIT ? 2 : 1); ++part) {
+#pragma unroll
+            for (int k16 = 0; k16 < KDIM / 16; ++k16) {
+              const int kb = k16 >> 2, kk = k16 & 3;
+              const uint64_t a_desc = smem_desc_sw128_kmajor(sA + s * L::A_STAGE_BYTES + kb * 16384) + (uint64_t)(kk * 2);
+              const uint64_t b_desc = smem_desc_sw128_kmajor(sW + (part * L::KB + kb) * NOUT * 128 + n0 * 128) + (uint64_t)(kk * 2);
+              umma_f16<1>(tmem + as * NOUT + n0, a_desc, b_desc, idesc, (part > 0 || k16 > 0) ? 1u : 0u);
+            }
           }
         }
         umma_commit(bar_aempty + 8 * s);
@@ -408,10 +414,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
   if (warp == 1) tmem_dealloc<1>(tmem, L::TMEM_COLS);
 }
 
-template <int NOUT, int KDIM, int EPI>
+template <int NOUT, int KDIM, int EPI, bool WSPLIT = false>
 static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const TcGemmArgs& args, cudaStream_t st) {
   constexpr bool RES_TMA = (EPI == TC_EPI_LN || EPI == TC_EPI_LN_POST);
-  using L = TcGemmSmem<NOUT, KDIM, RES_TMA>;
+  using L = TcGemmSmem<NOUT, KDIM, RES_TMA, WSPLIT>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
   CUtensorMap tmA, tmW, tmR;
   tmR = CUtensorMap();
@@ -428,12 +434,13 @@ static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const
     if (make_tmap_f16(&tmA, A, 2, dims, str, box)) return -1;
   }
   {
-    const uint64_t dims[2] = {(uint64_t)KDIM, (uint64_t)NOUT};
-    const uint64_t str[1] = {(uint64_t)KDIM * 2};
+    const uint64_t kw = WSPLIT ? 2 * KDIM : KDIM;
+    const uint64_t dims[2] = {kw, (uint64_t)NOUT};
+    const uint64_t str[1] = {kw * 2};
     const uint32_t box[2] = {64, 64};
     if (make_tmap_f16(&tmW, W, 2, dims, str, box)) return -1;
   }
-  auto kern = k_tc_gemm<NOUT, KDIM, EPI>;
+  auto kern = k_tc_gemm<NOUT, KDIM, EPI, WSPLIT>;
   static bool configured = false;
   if (!configured) {
     VATSS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -448,7 +455,7 @@ static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const
 int launch_tc_gemm(int epi, const __half* A, long long lda, const __half* W, const float* bias, const float* res,
                    long long ldr, const float* ln_w, const float* ln_b, float* out32, long long ldo32, __half* out16,
                    long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int KDIM,
-                   cudaStream_t st, __half* out16lo) {
+                   cudaStream_t st, __half* out16lo, int wsplit) {
   if (M == 0) return 0;
   VATSS_CHECK_ARG(((uintptr_t)A & 15) == 0 && (lda * 2) % 16 == 0, "tc_gemm: A must be 16-byte aligned with 16-byte row pitch");
   TcGemmArgs a;
@@ -461,6 +468,12 @@ int launch_tc_gemm(int epi, const __half* A, long long lda, const __half* W, con
   if (epi == TC_EPI_F32) VATSS_CHECK_ARG(out32 != nullptr, "tc_gemm: fp32 output missing");
   if (epi == TC_EPI_LN || epi == TC_EPI_LN_POST)
     VATSS_CHECK_ARG(out32 && res && ln_w && ln_b, "tc_gemm: LayerNorm epilogue needs out32/res/ln_w/ln_b");
+  if (wsplit) {   // W = [hi | lo], 2 x KDIM columns
+    if (NOUT == 64 && KDIM == 256 && epi == TC_EPI_LN_POST) return tc_gemm_launch<64, 256, TC_EPI_LN_POST, true>(A, lda, W, a, st);
+    if (NOUT == 64 && KDIM == 128 && epi == TC_EPI_LN_POST) return tc_gemm_launch<64, 128, TC_EPI_LN_POST, true>(A, lda, W, a, st);
+    set_error("tc_gemm: no hi/lo weight instantiation for NOUT=%d K=%d epilogue=%d", NOUT, KDIM, epi);
+    return -1;
+  }
 #define TCG_CASE(N_, K_, E_) \
   if (NOUT == N_ && KDIM == K_ && epi == E_) return tc_gemm_launch<N_, K_, E_>(A, lda, W, a, st);
   // N = 128 models

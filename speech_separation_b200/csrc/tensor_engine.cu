@@ -53,7 +53,7 @@ size_t carve_packed(const vatss_model_desc* d, void* buf, Packed* out) {
     s.win = b.take<__half>(dprnn ? 0 : 3 * N * N);
     s.bin = b.take<float>(dprnn ? 0 : 3 * N);
     s.wout = b.take<__half>(dprnn ? 0 : N * N);
-    s.wffn = b.take<__half>(N * ndir * H);
+    s.wffn = b.take<__half>((dprnn ? 2 : 1) * N * ndir * H);   // DPRNN: [half(W) | half(W - half(W))]
     s.wlstm = b.take<__half>((size_t)ndir * 512 * ((dprnn ? 2 : 1) * N + 128));   // DPRNN: [W_hi | W_lo | W_hh]
     s.blstm = b.take<float>((size_t)ndir * 512);
   }
@@ -71,6 +71,16 @@ __global__ void k_to_half(const float* __restrict__ src, __half* __restrict__ ds
     const float s = (i / cols) < scaled_rows ? scale : 1.f;
     dst[i] = __float2half_rn(src[i] * s);
   }
+}
+// dst[r, 0:cols] = half(src), dst[r, cols:2cols] = half(src - half(src))
+__global__ void k_to_half_split(const float* __restrict__ src, __half* __restrict__ dst, int rows, int cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int r = i / cols, c = i - r * cols;
+  const float w = src[i];
+  const __half hi = __float2half_rn(w);
+  dst[(size_t)r * 2 * cols + c] = hi;
+  dst[(size_t)r * 2 * cols + cols + c] = __float2half_rn(w - __half2float(hi));
 }
 __global__ void k_scale_bias(const float* __restrict__ src, float* __restrict__ dst, int n, int scaled, float scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -156,7 +166,10 @@ int tensor_engine_pack(const vatss_model_desc* d, const float* const* params, vo
         VATSS_LAUNCH_OK();
         if ((rc = to_half(sp(VATSS_S_OUTPROJ_W), s.wout, N, N, 0, 1.f, st))) return rc;
       }
-      if ((rc = to_half(sp(VATSS_S_FFN_W), s.wffn, N, ndir * H, 0, 1.f, st))) return rc;
+      if (dprnn) {
+        k_to_half_split<<<(N * ndir * H + 255) / 256, 256, 0, st>>>(sp(VATSS_S_FFN_W), s.wffn, N, ndir * H);
+        VATSS_LAUNCH_OK();
+      } else if ((rc = to_half(sp(VATSS_S_FFN_W), s.wffn, N, ndir * H, 0, 1.f, st))) return rc;
       for (int dir = 0; dir < ndir; ++dir) {
         const int o = dir ? (VATSS_S_WIH_R - VATSS_S_WIH) : 0;
         if ((rc = launch_pack_lstm(sp(VATSS_S_WIH + o), sp(VATSS_S_WHH + o), sp(VATSS_S_BIH + o), sp(VATSS_S_BHH + o),
@@ -210,7 +223,7 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
         StageScope sc(ST_FFN_LN, st);
         if ((rc = launch_tc_gemm(TC_EPI_LN_POST, w.rnn16, ndir * H, s.wffn, sp(VATSS_S_FFN_B), w.xa32, N,
                                  sp(VATSS_S_LN2_W), sp(VATSS_S_LN2_B), w.xb32, N, w.xb16, N, last ? 2 : 0,
-                                 params[VATSS_P_PRELU], tok, N, ndir * H, st, last ? nullptr : w.xb16lo)))
+                                 params[VATSS_P_PRELU], tok, N, ndir * H, st, last ? nullptr : w.xb16lo, 1)))
           return rc;
         float* t32 = w.xa32; w.xa32 = w.xb32; w.xb32 = t32;
         __half* t16 = w.xa16; w.xa16 = w.xb16; w.xb16 = t16;

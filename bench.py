@@ -30,6 +30,15 @@ sys.path.insert(0, ROOT)
 SR = 16000
 MODEL_KW = dict(num_features=128, video_emb_size=512, hidden_video=128, kernel_size_enc=7, hidden_dim=128,
                 num_blocks=6, chunk_size=150, step_size=75, num_heads=4, dropout=0.1, bidir=True)
+# the other BASELINE.json configurations (src/configs/model/{dptn_wav,dptn,dprnn}.yaml)
+OTHER_MODELS = {
+    "dptn_wav": ("DPTNWavEncDec", dict(num_features=64, kernel_size_enc=7, hidden_dim=128, num_blocks=6, chunk_size=150,
+                                       step_size=75, num_heads=4, dropout=0.1, bidir=True)),
+    "dptn_mask": ("DPTNEncDec", dict(num_features=64, kernel_size_enc=7, hidden_dim=128, num_blocks=6, chunk_size=150,
+                                     step_size=75, num_heads=4, dropout=0.1, bidir=True)),
+    "dprnn": ("DPRNNEncDec", dict(num_features=64, kernel_size_enc=2, hidden_dim=128, num_blocks=6, chunk_size=250,
+                                  step_size=125, bidir=True)),
+}
 METRIC = "dptn_av_separated_audio_seconds_per_second"
 UNIT = "audio-s/s"
 
@@ -40,11 +49,19 @@ def geometry(T):
     return L, S
 
 
-def stage_flops(B, T):
+def stage_flops(B, T, model="dptn_av"):
     """Algorithmic FLOPs (2MNK) per forward by stage (SURVEY.md §8a per-token figures)."""
+    if model == "dprnn":
+        L = (T - 2) // 1 + 1
+        S = (L - 250) // 125 + 1
+        tok = B * S * 250
+        N, H = 64, 128
+        return {"lstm_recurrent": 12 * tok * 2 * (N + H) * 8 * H, "ffn_ln2": 12 * tok * 2 * 2 * H * N,
+                "tail": tok * 2 * N * 2 * N + 2 * B * L * (2 * N * N + 2 * N * 2), "frontend": B * L * 2 * N * 2,
+                "qkv": 0, "attention": 0, "outproj_ln1": 0, "lstm_input": 0}
     L, S = geometry(T)
     tok = B * S * 150
-    N, H = 128, 128
+    N, H = (128, 128) if model == "dptn_av" else (64, 128)
     per_sub = {
         "qkv": 2 * N * 3 * N,
         "outproj_ln1": 2 * N * N,
@@ -55,7 +72,7 @@ def stage_flops(B, T):
     fl = {k: 12 * tok * v for k, v in per_sub.items()}
     fl["attention"] = 6 * tok * 4 * N * (150 + S)  # QK^T and PV, intra (len C) + inter (len S)
     fl["tail"] = tok * 2 * N * 2 * N + 2 * B * L * (2 * N * N + 2 * N * 7)
-    fl["frontend"] = B * L * 2 * N * 7 + 2 * B * (T // 640) * 512 * N
+    fl["frontend"] = B * L * 2 * N * 7 + (2 * B * (T // 640) * 512 * N if model == "dptn_av" else 0)
     return fl
 
 
@@ -121,7 +138,7 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_arm(steps, warmup, B_sample, T):
+def cpu_reference_arm(steps, warmup, B_sample, T, model="dptn_av"):
     """The reference's CPU path (torch-op port) on the host cores; returns (audio-s/s, ms/step, info)."""
     import torch
 
@@ -131,8 +148,13 @@ def cpu_reference_arm(steps, warmup, B_sample, T):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(42)
-    net = V.DPTNAVWavEncDec(**MODEL_KW).eval()
+    if model == "dptn_av":
+        net = V.DPTNAVWavEncDec(**MODEL_KW).eval()
+    else:
+        net = getattr(V, OTHER_MODELS[model][0])(**OTHER_MODELS[model][1]).eval()
     mix, s1, s2, e1, e2 = make_batch(B_sample, T, 1234)
+    if model != "dptn_av":
+        e1 = e2 = None
     for _ in range(warmup):
         torch_port.forward(net, mix, e1, e2)
     t0 = time.perf_counter()
@@ -155,6 +177,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--engine", default="auto", choices=["auto", "generic", "tensor"])
+    ap.add_argument("--model", default="dptn_av", choices=["dptn_av"] + sorted(OTHER_MODELS),
+                    help="dptn_av = the headline config; the others are the remaining BASELINE.json models")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -162,9 +186,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     B, T = args.batch, int(round(args.seconds * SR))
-    config = {"workload": f"DPTN-AV (dptn_wav_av.yaml) inference, batch {B} x {args.seconds:g} s 16 kHz per GPU, "
-                          f"synthetic lip embeddings (B,512,{25 * T // SR}), random-init weights seed 42, "
-                          "+ PIT SI-SNRi reduction",
+    wname = {"dptn_av": "DPTN-AV (dptn_wav_av.yaml)", "dptn_wav": "DPTN audio-only (dptn_wav.yaml)",
+             "dptn_mask": "DPTN masking (dptn.yaml)", "dprnn": "DPRNN (dprnn.yaml)"}[args.model]
+    config = {"workload": f"{wname} inference, batch {B} x {args.seconds:g} s 16 kHz per GPU, "
+                          + (f"synthetic lip embeddings (B,512,{25 * T // SR}), " if args.model == "dptn_av" else "")
+                          + "random-init weights seed 42, + PIT SI-SNRi reduction",
               "batch_per_gpu": B, "seconds": args.seconds, "sharding": f"utterance x{max(world, args.gpus)}",
               "l2": "256 MiB buffer written between timed steps (L2 flush); per-step activations >> 126 MB L2"}
 
@@ -172,8 +198,8 @@ def main():
         if rank != 0:
             return 0
         # bounded sample: 1 utterance per step keeps K steps within minutes on the host cores
-        val, ms, info = cpu_reference_arm(max(args.steps, 1), min(args.warmup, 1), 1, T)
-        print(json.dumps({"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        val, ms, info = cpu_reference_arm(max(args.steps, 1), min(args.warmup, 1), 1, T, args.model)
+        print(json.dumps({"metric": METRIC.replace("dptn_av", args.model), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                           "impl": "reference", "cpu_baseline": info, "gpu_launches": 0,
@@ -195,15 +221,23 @@ def main():
     lib = _lib.load()
 
     torch.manual_seed(42)
-    net = V.DPTNAVWavEncDec(**MODEL_KW).eval().to(dev).set_engine(args.engine)
+    av = args.model == "dptn_av"
+    if av:
+        net = V.DPTNAVWavEncDec(**MODEL_KW)
+    else:
+        net = getattr(V, OTHER_MODELS[args.model][0])(**OTHER_MODELS[args.model][1])
+    net = net.eval().to(dev).set_engine(args.engine)
     metric = V.SISNRiMetric()
     mix_h, s1_h, s2_h, e1_h, e2_h = (t.pin_memory() for t in make_batch(B, T, 1234 + rank))
     mix, s1, s2, e1, e2 = (t.to(dev) for t in (mix_h, s1_h, s2_h, e1_h, e2_h))
     out_h = [torch.empty(B, T).pin_memory() for _ in range(2)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    def fwd(m, a, b):
+        return net(mix=m, s1_embedding=a, s2_embedding=b) if av else net(mix=m)
+
     def step_resident():
-        out = net(mix=mix, s1_embedding=e1, s2_embedding=e2)
+        out = fwd(mix, e1, e2)
         rows, rows_loss, _ = V.pit_sisnr_all(out["s1_pred"], out["s2_pred"], s1, s2, mix)
         return reduce_sisnr(sisnr_sums(rows, rows_loss)) if world > 1 else rows
 
@@ -211,7 +245,7 @@ def main():
         m = mix_h.to(dev, non_blocking=True)
         a = e1_h.to(dev, non_blocking=True)
         b = e2_h.to(dev, non_blocking=True)
-        out = net(mix=m, s1_embedding=a, s2_embedding=b)
+        out = fwd(m, a, b)
         out_h[0].copy_(out["s1_pred"], non_blocking=True)
         out_h[1].copy_(out["s2_pred"], non_blocking=True)
         val = metric(s1_pred=out["s1_pred"], s2_pred=out["s2_pred"], s1=s1, s2=s2, mix=m)
@@ -267,7 +301,7 @@ def main():
 
     # parity signal carried with the number: SI-SNRi of this rank's batch
     with torch.no_grad():
-        out = net(mix=mix, s1_embedding=e1, s2_embedding=e2)
+        out = fwd(mix, e1, e2)
         snri = float(metric(s1_pred=out["s1_pred"], s2_pred=out["s2_pred"], s1=s1, s2=s2, mix=mix))
 
     if rank != 0:
@@ -288,8 +322,8 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"
-    fl = stage_flops(B, T)
-    compute = {k: v for k, v in stage_ms.items() if k in fl and k not in ("frontend", "tail")}
+    fl = stage_flops(B, T, args.model)
+    compute = {k: v for k, v in stage_ms.items() if k in fl and fl[k] > 0 and k not in ("frontend", "tail")}
     dom = max(compute, key=compute.get)
     dom_launches = max(stage_launches.get(dom, 1), 1)
     achieved = fl[dom] / (stage_ms[dom] / 1e3) / 1e12
@@ -299,16 +333,16 @@ def main():
                 "whole_forward_frac": sum(fl.values()) / (sum(stage_ms[k] for k in fl) / 1e3) / 1e12 / peak_tf,
                 "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()}}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
+    line = {"metric": METRIC.replace("dptn_av", args.model), "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.engine == "generic" or not _engine_is_tensor(lib, net) else "f16",
             "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": int(mix_h.numel() + e1_h.numel() + e2_h.numel()) * 4,
+                    "h2d_bytes_per_step": int(mix_h.numel() + (e1_h.numel() + e2_h.numel() if av else 0)) * 4,
                     "d2h_bytes_per_step": int(2 * B * T) * 4 + 4},
             "gpu_launches": int(launches), "roofline": roofline, "si_snri_db": snri, "wall_s_timed": wall}
     if world == 1 and not args.no_cpu_baseline:
-        _, _, info = cpu_reference_arm(2, 1, 1, T)
+        _, _, info = cpu_reference_arm(2, 1, 1, T, args.model)
         line["cpu_baseline"] = info
     print(json.dumps(line))
     if world > 1:

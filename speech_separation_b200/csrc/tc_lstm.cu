@@ -309,42 +309,53 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
         if (T) T[3 * c + 1] = clock64();
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + c * 128 + half * 16;
-        uint32_t gi[16], gf[16], gg[16], go[16];
-        tmem_ld_32x32b_x16(taddr + 0, gi);
-        tmem_ld_32x32b_x16(taddr + 32, gf);
-        tmem_ld_32x32b_x16(taddr + 64, gg);
-        tmem_ld_32x32b_x16(taddr + 96, go);
-        tmem_ld_wait();
-        // accumulator chunk drained -> the MMA warp may start the next step's x-part into it
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0)
-          asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(accempty_leader[c]) : "memory");
-        const float* bc = sBias + c * 128 + half * 16;
-        float hv[16];
+        __half* orow = p.out + (row_base + (long long)t * row_tstride) * ldo + dir * LSTM_H + c * LSTM_UNITS_PER_CHUNK + half * 16;
+        // two passes of 8 hidden units keep the live register set small (no spills of the packed h values)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float ig = act_sigmoid<PRECISE>(__uint_as_float(gi[j]) + bc[j]);
-          const float fg = act_sigmoid<PRECISE>(__uint_as_float(gf[j]) + bc[32 + j]);
-          const float g_ = act_tanh<PRECISE>(__uint_as_float(gg[j]) + bc[64 + j]);
-          const float og = act_sigmoid<PRECISE>(__uint_as_float(go[j]) + bc[96 + j]);
-          const float cc = fmaf(fg, cst[c][j], ig * g_);
-          cst[c][j] = cc;
-          hv[j] = og * act_tanh<PRECISE>(cc);
-        }
-        uint32_t ho[8];
+        for (int sub = 0; sub < 2; ++sub) {
+          uint32_t gi[8], gf[8], gg[8], go[8];
+          tmem_ld_32x32b_x8(taddr + sub * 8 + 0, gi);
+          tmem_ld_32x32b_x8(taddr + sub * 8 + 32, gf);
+          tmem_ld_32x32b_x8(taddr + sub * 8 + 64, gg);
+          tmem_ld_32x32b_x8(taddr + sub * 8 + 96, go);
+          tmem_ld_wait();
+          if (sub == 1) {
+            // accumulator chunk drained -> the MMA warp may start the next step's x-part into it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+              asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(accempty_leader[c]) : "memory");
+          }
+          // biases: broadcast 16-byte reads (i | f | g | o blocks of 32 units per chunk)
+          const float4* b4 = reinterpret_cast<const float4*>(sBias + c * 128 + half * 16 + sub * 8);
+          float bi[8], bf[8], bg[8], bo[8];
+          {
+            const float4 i0 = b4[0], i1 = b4[1], f0 = b4[8], f1 = b4[9], g0 = b4[16], g1 = b4[17], o0 = b4[24], o1 = b4[25];
+            bi[0] = i0.x; bi[1] = i0.y; bi[2] = i0.z; bi[3] = i0.w; bi[4] = i1.x; bi[5] = i1.y; bi[6] = i1.z; bi[7] = i1.w;
+            bf[0] = f0.x; bf[1] = f0.y; bf[2] = f0.z; bf[3] = f0.w; bf[4] = f1.x; bf[5] = f1.y; bf[6] = f1.z; bf[7] = f1.w;
+            bg[0] = g0.x; bg[1] = g0.y; bg[2] = g0.z; bg[3] = g0.w; bg[4] = g1.x; bg[5] = g1.y; bg[6] = g1.z; bg[7] = g1.w;
+            bo[0] = o0.x; bo[1] = o0.y; bo[2] = o0.z; bo[3] = o0.w; bo[4] = o1.x; bo[5] = o1.y; bo[6] = o1.z; bo[7] = o1.w;
+          }
+          float hv[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const __half2 a = __floats2half2_rn(hv[2 * j], hv[2 * j + 1]);
-          hp[c][j] = *reinterpret_cast<const uint32_t*>(&a);
-          const __half2 o = p.act ? __floats2half2_rn(fmaxf(hv[2 * j], 0.f), fmaxf(hv[2 * j + 1], 0.f)) : a;
-          ho[j] = *reinterpret_cast<const uint32_t*>(&o);
-        }
-        if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(p.out + (row_base + (long long)t * row_tstride) * ldo + dir * LSTM_H +
-                                                c * LSTM_UNITS_PER_CHUNK + half * 16);
-          dst[0] = make_uint4(ho[0], ho[1], ho[2], ho[3]);
-          dst[1] = make_uint4(ho[4], ho[5], ho[6], ho[7]);
+          for (int j = 0; j < 8; ++j) {
+            const float ig = act_sigmoid<PRECISE>(__uint_as_float(gi[j]) + bi[j]);
+            const float fg = act_sigmoid<PRECISE>(__uint_as_float(gf[j]) + bf[j]);
+            const float g_ = act_tanh<PRECISE>(__uint_as_float(gg[j]) + bg[j]);
+            const float og = act_sigmoid<PRECISE>(__uint_as_float(go[j]) + bo[j]);
+            const float cc = fmaf(fg, cst[c][sub * 8 + j], ig * g_);
+            cst[c][sub * 8 + j] = cc;
+            hv[j] = og * act_tanh<PRECISE>(cc);
+          }
+          uint32_t ho[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __half2 a = __floats2half2_rn(hv[2 * j], hv[2 * j + 1]);
+            hp[c][sub * 4 + j] = *reinterpret_cast<const uint32_t*>(&a);
+            const __half2 o = p.act ? __floats2half2_rn(fmaxf(hv[2 * j], 0.f), fmaxf(hv[2 * j + 1], 0.f)) : a;
+            ho[j] = *reinterpret_cast<const uint32_t*>(&o);
+          }
+          if (valid) *reinterpret_cast<uint4*>(orow + sub * 8) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
         }
         if (T) T[3 * c + 2] = clock64();
       }

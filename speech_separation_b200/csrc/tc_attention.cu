@@ -6,16 +6,24 @@
 // probabilities are exp2(s - rowmax).
 //
 // Work item = (sequence, 64-feature head group): the Q/K/V tiles of a head group are 128-byte rows, i.e. plain
-// SWIZZLE_128B TMA tiles; a head is a 16/32-column K-slice of them.  One persistent CTA per SM:
+// SWIZZLE_128B TMA tiles; a head is a 16/32-column K-slice of them.  One persistent CTA per SM, 20 warps:
 //   warp 0        TMA producer (K and V of the item once, Q per 128-query tile, double buffered)
-//   warps 1,2     MMA issuers, one per softmax warpgroup (decoupled pipelines): S = Q K^T (M=128, N<=192, K=hd)
-//                 and O += P V (M=128, N=hd, K=64 per kv block)
-//   warps 3..10   softmax warpgroup 0  (heads [0, HPT/2) of the group): two warps per TMEM lane quadrant, each
+//   warp 1        S issuer for both warpgroups: S block = Q K_j^T (M=128, N=64, K=hd) into a ring of three
+//                 64-column TMEM slots per warpgroup, running up to three blocks ahead of the softmax warps
+//   warps 2,3     P V issuers, one per warpgroup: O += P_j V_j (M=128, N=hd, K=16 steps of the kv block)
+//   warps 4..11   softmax warpgroup 0  (heads [0, HPT/2) of the group): two warps per TMEM lane quadrant, each
 //                 thread owns one query row and one 32-column half of every 64-column S block
-//   warps 11..18  softmax warpgroup 1  (heads [HPT/2, HPT))
-// Each warpgroup owns an S slot and an O accumulator in TMEM and a P tile in shared memory, so the two
-// heads' MMAs and exponentials overlap.  Sequences longer than one kv block use an exact two-pass softmax
-// (pass A: row max over all blocks, pass B: exp / P V accumulation) - no accumulator rescaling.
+//   warps 12..19  softmax warpgroup 1  (heads [HPT/2, HPT))
+// Each warpgroup owns its S ring, two O accumulators in TMEM and two P tiles in shared memory.  The read-out of a
+// group's O is deferred until the next group's probabilities are written, so S, the exponentials and P V of
+// neighbouring groups overlap.  The row maximum is exact: resident mode (<= 3 kv blocks) keeps S in TMEM between
+// the max and the exp pass; longer sequences recompute S in a second pass (no accumulator rescaling).
+// A ragged last query tile (<= 32 rows: 150 = 128 + 22, 283 = 2 x 128 + 27) is loaded into all four lane quadrants
+// and its rows are shared by the eight warps of the warpgroup in 8-column strips.
+//
+// Measured (tools/attn_trace.py, tools/ubench/tcgen05_issue.cu): the kernel is bound by the per-block
+// synchronisation chain (mbarrier round trips ~100 cycles each, tcgen05 issue ~30-50 cycles per instruction in
+// isolation and 2-3x that next to four busy softmax warps on the same scheduler), not by the MUFU or tensor pipes.
 //
 // k_attention_f16_simt is the shape-agnostic fallback (sequence too long for the shared-memory plan).
 #include "common.cuh"
@@ -102,14 +110,18 @@ struct TcAttnArgs {
   int mtiles;     // 128-query tiles per sequence
   int num_items;  // sequences * groups
   int stream;     // 1: K / V super-blocks stream through a shared-memory ring (sequence too long to keep resident)
+  int rag;        // 1: the last query tile has <= 32 valid rows.  It is loaded four times, once per TMEM lane quadrant,
+                  // so that all eight softmax warps of a warpgroup can share its rows (8-column strips each)
+                  // instead of one warp per column half doing all of it on a single SM sub-partition
   SeqMap map;
   __half* out;    // (tokens, N)
+  long long* trace;   // optional clock64 trace of CTA 0 (debug), NULL in production
 };
 
-constexpr int ATT_THREADS = 608;        // producer warp, 2 MMA warps (one per warpgroup), 2 x 8 softmax warps
+constexpr int ATT_THREADS = 640;        // producer warp, S issuer warp, 2 P V issuer warps, 2 x 8 softmax warps
 constexpr int ATT_NB = 64;             // kv rows per block = one SWIZZLE_128B k-block of the P tile
 constexpr int ATT_SUPER = 3;           // 64-row kv blocks per S job: one N <= 192 MMA fills the whole S region
-constexpr uint32_t ATT_WG_COLS = 256;  // TMEM columns per warpgroup: 192 (S region) + 32 (O)
+constexpr uint32_t ATT_WG_COLS = 256;  // TMEM columns per warpgroup: 3 x 64 (S slots) + 2 x 32 (O, double buffered)
 constexpr uint32_t ATT_O_COL = 192;
 constexpr int ATT_RING = 4;            // streaming mode: ring stages of one super-block (3 x 64 rows x 128 B = 24 KB)
 constexpr uint32_t ATT_STAGE_BYTES = ATT_SUPER * ATT_NB * 128;
@@ -147,7 +159,8 @@ struct AttBars {
 
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
-k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CUtensorMap tmapKV, TcAttnArgs p) {
+k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CUtensorMap tmapQ32,
+               const __grid_constant__ CUtensorMap tmapKV, TcAttnArgs p) {
   constexpr int HPT = 64 / HD;       // heads per 64-feature group
   constexpr int HPW = HPT / 2;       // heads per warpgroup
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -165,28 +178,29 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
   B.kfull = bars; B.kfree = bars + 16;             // 2 each
   B.vfull = bars + 32; B.vfree = bars + 40;
   B.qfull = bars + 48; B.qfree = bars + 64;        // 2 each
-  B.sfull = bars + 80; B.sfree = bars + 128;       // 6 each
-  B.pfull = bars + 176; B.pfree = bars + 208;      // 4 each
-  B.ofull = bars + 240; B.ofree = bars + 256;      // 2 each
-  const uint32_t tmem_slot = bars + 272;
-  const uint32_t b_rfull = bars + 2336, b_rfree = bars + 2336 + 8 * ATT_RING;   // after the 2 KB exchange buffer
-  float* s_mx = reinterpret_cast<float*>(smem + (bars + 288 - base));   // [2 wg][2 sets][128 rows]
+  B.sfull = bars + 80; B.sfree = bars + 128;       // [2 wg][3 slots]
+  B.pfull = bars + 176; B.pfree = bars + 208;      // [2 wg][2 buffers]
+  B.ofull = bars + 240; B.ofree = bars + 272;      // [2 wg][2 buffers]
+  const uint32_t tmem_slot = bars + 304;
+  const uint32_t b_rfull = bars + 320, b_rfree = bars + 320 + 8 * ATT_RING;
+  float* s_mx = reinterpret_cast<float*>(smem + (bars + 512 - base));   // row max / row sum exchange, 8 KB
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool resident = p.nblk <= ATT_SUPER;       // all of S of a (tile, head) fits the S region: single S pass
   const int nsuper = (p.nblk + ATT_SUPER - 1) / ATT_SUPER;
 
   if (threadIdx.x == 0) {
-    mbar_init(B.vfull, 1); mbar_init(B.vfree, 2);      // "free" barriers: one commit from each MMA warp
+    mbar_init(B.vfull, 1); mbar_init(B.vfree, 2);      // V: one commit from each P V issuer
     for (int i = 0; i < 2; ++i) {
-      mbar_init(B.kfull + 8 * i, 1); mbar_init(B.kfree + 8 * i, 2);
-      mbar_init(B.qfull + 8 * i, 1); mbar_init(B.qfree + 8 * i, 2);
+      mbar_init(B.kfull + 8 * i, 1); mbar_init(B.kfree + 8 * i, 1);
+      mbar_init(B.qfull + 8 * i, 1); mbar_init(B.qfree + 8 * i, 1);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(B.sfull + 8 * i, 1); mbar_init(B.sfree + 8 * i, 256); }
+    for (int i = 0; i < 6; ++i) { mbar_init(B.sfull + 8 * i, 1); mbar_init(B.sfree + 8 * i, 256); }
     for (int i = 0; i < 4; ++i) { mbar_init(B.pfull + 8 * i, 256); mbar_init(B.pfree + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(B.ofull + 8 * i, 1); mbar_init(B.ofree + 8 * i, 256); }
+    for (int i = 0; i < 4; ++i) { mbar_init(B.ofull + 8 * i, 1); mbar_init(B.ofree + 8 * i, 256); }
     for (int i = 0; i < ATT_RING; ++i) { mbar_init(b_rfull + 8 * i, 1); mbar_init(b_rfree + 8 * i, 2); }
     fence_mbar_init();
     prefetch_tmap(&tmapQ);
+    prefetch_tmap(&tmapQ32);
     prefetch_tmap(&tmapKV);
   }
   if (warp == 1) {
@@ -224,8 +238,14 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
         for (int m = 0; m < p.mtiles; ++m, ++qn) {
           const int s = qn & 1;
           mbar_wait(B.qfree + 8 * s, ((qn >> 1) & 1) ^ 1);
-          mbar_expect_tx(B.qfull + 8 * s, 16384);
-          load_rows(&tmapQ, sQ + s * 16384, B.qfull + 8 * s, colq, m * 128);
+          if (p.rag && m == p.mtiles - 1) {
+            mbar_expect_tx(B.qfull + 8 * s, 16384);
+            for (int k = 0; k < 4; ++k)
+              load_rows(&tmapQ32, sQ + s * 16384 + k * 32 * 128, B.qfull + 8 * s, colq, m * 128);
+          } else {
+            mbar_expect_tx(B.qfull + 8 * s, 16384);
+            load_rows(&tmapQ, sQ + s * 16384, B.qfull + 8 * s, colq, m * 128);
+          }
           if (!stream) {
             if (m == 0) {
               mbar_wait(B.vfree, (it & 1) ^ 1);
@@ -253,142 +273,185 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
       }
     }
     __syncwarp();
-  } else if (warp == 1 || warp == 2) {
-    // ---------------------------------------------------------------- MMA issuer (warp 1 -> warpgroup 0, warp 2 -> 1)
-    // Small tcgen05.mma instructions cost a fixed ~100+ cycles each, so the instruction count is what matters:
-    // S uses one N = 64..192 MMA per 16-wide K step for a whole super-block, P V needs kv/16 MMAs of N = hd.
-    if (lane == 0) {
-      const int w = warp - 1;
-      const uint32_t idesc_o = idesc_f16(128, HD, 0) | (1u << 16);     // B (= V) is MN-major
-      // a "group" = one (item, query tile, head-of-warpgroup); both warpgroups run the same group sequence
-      struct Cur { int item, it, m, qn, hh; bool valid; };
-      auto advance = [&](Cur& c) {
-        if (++c.hh == HPW) {
-          c.hh = 0; ++c.qn;
-          if (++c.m == p.mtiles) { c.m = 0; c.item += gridDim.x; ++c.it; c.valid = c.item < p.num_items; }
-        }
-      };
-      uint32_t sjob = 0, pjob = 0, ohead = 0, rseq = 0, v_stage = 0;
-      int k_seen = -1, q_seen = -1, v_seen = -1;
-      // S super-block sb (kv blocks [3 sb, 3 sb + nb)) of group c into the S region of both warpgroups
-      auto issue_s = [&](const Cur& c, int sb, bool last_job_of_group) {
-        uint32_t kbase, rst = 0;
-        if (!stream) {
-          if (k_seen != c.it) { mbar_wait(B.kfull + 8 * (c.it & 1), (c.it >> 1) & 1); k_seen = c.it; }
-          kbase = sK + (c.it & 1) * KV_BYTES + sb * ATT_SUPER * ATT_NB * 128;
-        } else {
-          rst = rseq % ATT_RING;
-          mbar_wait(b_rfull + 8 * rst, (rseq / ATT_RING) & 1);
-          kbase = sRing + rst * ATT_STAGE_BYTES;
-          ++rseq;
-        }
-        if (q_seen != c.qn) { mbar_wait(B.qfull + 8 * (c.qn & 1), (c.qn >> 1) & 1); q_seen = c.qn; }
-        const int nb = min(ATT_SUPER, p.nblk - sb * ATT_SUPER);
-        const uint32_t idesc_s = idesc_f16(128, nb * ATT_NB, 0);
-        {
-          const int hsel = w * HPW + c.hh;
-          mbar_wait(B.sfree + 8 * w, (sjob & 1) ^ 1);
-          tc_fence_after();
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- S issuer (both warpgroups)
+    // The S region of a warpgroup is a ring of three 64-column slots: S block jobs run up to three blocks ahead of
+    // the softmax warps (into the next group / item), so S is ready when the exponentials of the previous block end.
+    // Every lane runs the warp-uniform loop; one elected lane issues (see umma_f16_warp).  The issuer warps are
+    // the scarce resource of this kernel (each tcgen05 instruction costs ~20 issue slots of address arithmetic,
+    // competing with four softmax warps on the same scheduler), hence one warp for S and one per warpgroup for P V.
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc_s = idesc_f16(128, ATT_NB, 0);
+    uint32_t slot = 0, sphase = 0, gidx = 0;
+    int it = 0, qn = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      if (!stream) mbar_wait(B.kfull + 8 * (it & 1), (it >> 1) & 1);
+      for (int m = 0; m < p.mtiles; ++m, ++qn) {
+        mbar_wait(B.qfull + 8 * (qn & 1), (qn >> 1) & 1);
+        const uint32_t qbase = sQ + (qn & 1) * 16384;
+        for (int hh = 0; hh < HPW; ++hh, ++gidx) {
+          for (int pass = resident ? 1 : 0; pass < 2; ++pass) {
+            for (int j = 0; j < p.nblk; ++j) {
+              uint32_t kbase, rst = 0;
+              if (!stream) {
+                kbase = sK + (it & 1) * KV_BYTES + j * ATT_NB * 128;
+              } else {
+                // ring sequence of the K super-block: pass A: base + sb, pass B: base + nsuper + 2 sb
+                const uint32_t sb = j / ATT_SUPER;
+                const uint32_t rs = gidx * 3u * nsuper + (pass == 0 ? sb : nsuper + 2u * sb);
+                rst = rs % ATT_RING;
+                if (j % ATT_SUPER == 0) mbar_wait(b_rfull + 8 * rst, (rs / ATT_RING) & 1);
+                kbase = sRing + rst * ATT_STAGE_BYTES + (j % ATT_SUPER) * ATT_NB * 128;
+              }
 #pragma unroll
-          for (int k16 = 0; k16 < HD / 16; ++k16) {
-            const uint32_t koff = (uint32_t)(hsel * HD * 2 + k16 * 32) >> 4;
-            const uint64_t a = smem_desc_sw128_kmajor(sQ + (c.qn & 1) * 16384) + koff;
-            const uint64_t b = smem_desc_sw128_kmajor(kbase) + koff;
-            umma_f16<1>(tmem + w * ATT_WG_COLS, a, b, idesc_s, k16 > 0 ? 1u : 0u);
-          }
-          umma_commit(B.sfull + 8 * w);
-          if (stream) umma_commit(b_rfree + 8 * rst);   // this warp's S MMAs were the last readers of the K stage
-        }
-        ++sjob;
-        if (last_job_of_group && c.hh == HPW - 1) {
-          umma_commit(B.qfree + 8 * (c.qn & 1));                       // last S MMA reading this Q tile
-          if (!stream && c.m == p.mtiles - 1) umma_commit(B.kfree + 8 * (c.it & 1));   // ... and this K buffer
-        }
-      };
-      // O += P_j V_j for group c, both warpgroups
-      auto issue_pv = [&](const Cur& c, int j) {
-        uint32_t vbase;
-        if (!stream) {
-          if (v_seen != c.it) { mbar_wait(B.vfull, c.it & 1); v_seen = c.it; }
-          vbase = sV + j * ATT_NB * 128;
-        } else {
-          if (j % ATT_SUPER == 0) {   // first block of a V super-block: next ring stage
-            v_stage = rseq % ATT_RING;
-            mbar_wait(b_rfull + 8 * v_stage, (rseq / ATT_RING) & 1);
-            ++rseq;
-          }
-          vbase = sRing + v_stage * ATT_STAGE_BYTES + (j % ATT_SUPER) * ATT_NB * 128;
-        }
-        const uint32_t pb = pjob & 1;
-        {
-          const int hsel = w * HPW + c.hh;
-          if (j == 0) mbar_wait(B.ofree + 8 * w, (ohead & 1) ^ 1);     // previous O of this warpgroup read out
-          mbar_wait(B.pfull + 8 * (w * 2 + pb), (pjob >> 1) & 1);
-          tc_fence_after();
-          const uint32_t d_o = tmem + w * ATT_WG_COLS + ATT_O_COL;
+              for (int w = 0; w < 2; ++w) {
+                const uint32_t koff = (uint32_t)((w * HPW + hh) * HD * 2) >> 4;
+                mbar_wait(B.sfree + 8 * (w * 3 + slot), sphase ^ 1);
+                tc_fence_after();
 #pragma unroll
-          for (int k16 = 0; k16 < ATT_NB / 16; ++k16) {
-            const uint64_t a = smem_desc_sw128_kmajor(sP + (w * 2 + pb) * 16384) + (uint64_t)(k16 * 2);
-            const uint64_t bv = smem_desc_sw128_mnmajor(vbase + k16 * 16 * 128 + hsel * HD * 2);
-            umma_f16<1>(d_o, a, bv, idesc_o, (j > 0 || k16 > 0) ? 1u : 0u);
-          }
-          umma_commit(B.pfree + 8 * (w * 2 + pb));
-          if (j == p.nblk - 1) umma_commit(B.ofull + 8 * w);
-          if (stream && (j % ATT_SUPER == ATT_SUPER - 1 || j == p.nblk - 1)) umma_commit(b_rfree + 8 * v_stage);
-        }
-        ++pjob;
-        if (j == p.nblk - 1) {
-          ++ohead;
-          if (!stream && c.hh == HPW - 1 && c.m == p.mtiles - 1) umma_commit(B.vfree);   // last P V reading this item's V
-        }
-      };
-      Cur cur = {(int)blockIdx.x, 0, 0, 0, 0, (int)blockIdx.x < p.num_items};
-      while (cur.valid) {
-        if (resident) {
-          issue_s(cur, 0, true);
-          for (int j = 0; j < p.nblk; ++j) issue_pv(cur, j);
-        } else {
-          for (int sb = 0; sb < nsuper; ++sb) issue_s(cur, sb, false);             // pass A: row maxima
-          for (int sb = 0; sb < nsuper; ++sb) {                                    // pass B: exp, P V
-            issue_s(cur, sb, sb == nsuper - 1);
-            const int j1 = min(p.nblk, (sb + 1) * ATT_SUPER);
-            for (int j = sb * ATT_SUPER; j < j1; ++j) issue_pv(cur, j);
+                for (int k16 = 0; k16 < HD / 16; ++k16)
+                  umma_f16_warp<1>(tmem_u + w * ATT_WG_COLS + slot * ATT_NB, smem_desc_sw128_kmajor(qbase) + koff + 2 * k16,
+                                   smem_desc_sw128_kmajor(kbase) + koff + 2 * k16, idesc_s, k16 > 0 ? 1u : 0u);
+                umma_commit_warp(B.sfull + 8 * (w * 3 + slot));
+              }
+              if (stream && (j % ATT_SUPER == ATT_SUPER - 1 || j == p.nblk - 1)) {
+                umma_commit_warp(b_rfree + 8 * rst);     // the ring barriers count two readers (the P V issuers
+                umma_commit_warp(b_rfree + 8 * rst);     // of a V stage); a K stage has this warp only
+              }
+              if (++slot == 3) { slot = 0; sphase ^= 1; }
+            }
           }
         }
-        advance(cur);
+        umma_commit_warp(B.qfree + 8 * (qn & 1));                      // last S MMA reading this Q tile
       }
+      if (!stream) umma_commit_warp(B.kfree + 8 * (it & 1));           // ... and this K buffer
     }
-    __syncwarp();
+  } else if (warp == 2 || warp == 3) {
+    // ---------------------------------------------------------------- P V issuer of warpgroup (warp - 2)
+    const int w = __shfl_sync(0xffffffffu, warp, 0) - 2;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc_o = idesc_f16(128, HD, 0) | (1u << 16);     // B (= V) is MN-major
+    const int nk_last = (p.len - (p.nblk - 1) * ATT_NB + 15) >> 4;   // 16-row K steps of the (ragged) last kv block
+    uint32_t pjob = 0, gidx = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      if (!stream) mbar_wait(B.vfull, it & 1);
+      for (int m = 0; m < p.mtiles; ++m) {
+        for (int hh = 0; hh < HPW; ++hh, ++gidx) {
+          const uint32_t ob = gidx & 1;
+          const uint32_t d_o = tmem_u + w * ATT_WG_COLS + ATT_O_COL + ob * 32;
+          const uint32_t hoff = (uint32_t)((w * HPW + hh) * HD * 2);
+          mbar_wait(B.ofree + 8 * (w * 2 + ob), ((gidx >> 1) & 1) ^ 1);   // O buffer read out by the softmax warps
+          for (int j = 0; j < p.nblk; ++j, ++pjob) {
+            uint32_t vbase, rst = 0;
+            if (!stream) {
+              vbase = sV + j * ATT_NB * 128;
+            } else {
+              const uint32_t sb = j / ATT_SUPER;
+              const uint32_t rs = gidx * 3u * nsuper + nsuper + 2u * sb + 1u;
+              rst = rs % ATT_RING;
+              if (j % ATT_SUPER == 0) mbar_wait(b_rfull + 8 * rst, (rs / ATT_RING) & 1);
+              vbase = sRing + rst * ATT_STAGE_BYTES + (j % ATT_SUPER) * ATT_NB * 128;
+            }
+            const uint32_t pb = pjob & 1;
+            const uint64_t adesc = smem_desc_sw128_kmajor(sP + (w * 2 + pb) * 16384);
+            const uint64_t bdesc = smem_desc_sw128_mnmajor(vbase + hoff);
+            const int nk = j == p.nblk - 1 ? nk_last : ATT_NB / 16;
+            mbar_wait(B.pfull + 8 * (w * 2 + pb), (pjob >> 1) & 1);
+            tc_fence_after();
+            for (int k16 = 0; k16 < nk; ++k16)
+              umma_f16_warp<1>(d_o, adesc + 2 * k16, bdesc + ((k16 * 16 * 128) >> 4), idesc_o, (j > 0 || k16 > 0) ? 1u : 0u);
+            umma_commit_warp(B.pfree + 8 * (w * 2 + pb));
+            if (stream && (j % ATT_SUPER == ATT_SUPER - 1 || j == p.nblk - 1)) umma_commit_warp(b_rfree + 8 * rst);
+          }
+          umma_commit_warp(B.ofull + 8 * (w * 2 + ob));
+        }
+      }
+      if (!stream) umma_commit_warp(B.vfree);                          // last P V reading this item's V
+    }
   } else {
     // ---------------------------------------------------------------- softmax warpgroups
-    const int sw = warp - 3;
+    const int sw = warp - 4;
     const int w = sw >> 3;                       // warpgroup
     const int set = (sw >> 2) & 1;               // which 32-column half of each 64-column kv block this thread owns
     const int q = warp & 3;                      // TMEM lane quadrant of this warp
     const int r = q * 32 + lane;                 // query row inside the 128-row tile
     const uint32_t t_base = tmem + ((uint32_t)(q * 32) << 16) + w * ATT_WG_COLS;
     const int cb = set * 32;
-    float* ex = s_mx + w * 256;
-    uint32_t sjob = 0, pjob = 0, ohead = 0;
+    float* ex_mx = s_mx + w * 512;               // [2 parities][2 sets][128 rows]
+    float* ex_sum = s_mx + 1024 + w * 512;
+    uint32_t sseq = 0, pjob = 0, gidx = 0;
+    // the read-out of a group's O accumulator is deferred until the next group's probabilities are written, so the
+    // P V MMAs of one group overlap the exponentials of the next
+    struct Pending { bool valid, rag; float sum; long long row; int head; uint32_t gidx; } pend = {false, false, 0.f, 0, 0, 0u};
+    auto read_out = [&](const Pending& pd) {
+      const uint32_t ob = pd.gidx & 1;
+      mbar_wait(B.ofull + 8 * (w * 2 + ob), (pd.gidx >> 1) & 1);
+      tc_fence_after();
+      uint32_t o[HD / 2];
+      if constexpr (HD == 32) tmem_ld_32x32b_x16(t_base + ATT_O_COL + ob * 32 + set * 16, o);
+      else tmem_ld_32x32b_x8(t_base + ATT_O_COL + ob * 32 + set * 8, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(B.ofree + 8 * (w * 2 + ob));
+      if (pd.row >= 0) {
+        float tot = pd.sum;
+        if (pd.rag) {
+          tot = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) tot += ex_sum[ob * 256 + i * 32 + lane];
+        } else {
+          tot += ex_sum[ob * 256 + (set ^ 1) * 128 + r];
+        }
+        const float inv = 1.f / tot;
+        uint4* dst = reinterpret_cast<uint4*>(p.out + pd.row * p.N + pd.head * HD + set * (HD / 2));
+#pragma unroll
+        for (int c = 0; c < HD / 16; ++c) {
+          uint32_t wd[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __half2 h2 = __floats2half2_rn(__uint_as_float(o[c * 8 + 2 * e]) * inv,
+                                                 __uint_as_float(o[c * 8 + 2 * e + 1]) * inv);
+            wd[e] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          dst[c] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        }
+      }
+    };
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int g = item / p.groups, grp = item - g * p.groups;
       for (int m = 0; m < p.mtiles; ++m) {
-        const int qi = m * 128 + r;
-        const bool warp_live = m * 128 + q * 32 < p.len;     // warp-uniform: any valid query row in this warp
-        for (int hh = 0; hh < HPW; ++hh) {
+        // Ragged last tile (<= 32 queries, replicated in every lane quadrant): lane = query, and the eight warps of
+        // the warpgroup split each 64-column block into 8-column strips (cc) instead of 32-column halves.
+        const bool rag = p.rag && m == p.mtiles - 1;
+        const int qi = m * 128 + (rag ? lane : r);
+        const bool warp_live = rag || m * 128 + q * 32 < p.len;     // warp-uniform: any valid query row in this warp
+        const int cc = rag ? cb + q * 8 : cb;                        // first column (inside a block) of this thread
+        const int cw = rag ? 8 : 32;                                 // columns per block of this thread
+        for (int hh = 0; hh < HPW; ++hh, ++gidx) {
           const int head = grp * HPT + w * HPW + hh;
+          const uint32_t par = gidx & 1;
+          long long* T = (p.trace != nullptr && blockIdx.x == 0 && sw == 0 && lane == 0 && gidx >= 8 && gidx < 12)
+                             ? p.trace + (gidx - 8) * 32 : nullptr;
+          if (T) T[0] = clock64();
           float mx = -INFINITY;
-          // ---- row maximum over this thread's columns
-          for (int sb = 0; sb < nsuper; ++sb) {
-            mbar_wait(B.sfull + 8 * w, (sjob + sb) & 1);
+          // ---- row maximum over this thread's columns (resident: the blocks stay in their slots for the exp pass)
+          for (int j = 0; j < p.nblk; ++j) {
+            const uint32_t sq = sseq + j, slot = sq % 3u;
+            mbar_wait(B.sfull + 8 * (w * 3 + slot), (sq / 3u) & 1);
             tc_fence_after();
-            const int j1 = min(p.nblk, (sb + 1) * ATT_SUPER);
-            if (warp_live) {
-              for (int j = sb * ATT_SUPER; j < j1; ++j) {
-                const int nv = min(ATT_NB, p.len - j * ATT_NB) - cb;   // valid columns of this thread's half
-                if (nv <= 0) continue;
+            const int nv = min(ATT_NB, p.len - j * ATT_NB) - cc;   // valid columns of this thread's strip
+            if (warp_live && nv > 0) {
+              if (rag) {
+                uint32_t v[8];
+                tmem_ld_32x32b_x8(t_base + slot * ATT_NB + cc, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (i < nv) mx = fmaxf(mx, __uint_as_float(v[i]));
+              } else {
                 uint32_t v[32];
-                tmem_ld_32x32b_x32(t_base + (j - sb * ATT_SUPER) * ATT_NB + cb, v);
+                tmem_ld_32x32b_x32(t_base + slot * ATT_NB + cc, v);
                 tmem_ld_wait();
                 if (nv >= 32) {
 #pragma unroll
@@ -400,103 +463,111 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
                 }
               }
             }
-            if (!resident) {   // the S region is recycled for the next super-block
+            if (!resident) {   // pass A of the two-pass softmax: the slot is recycled right away
               tc_fence_before();
-              mbar_arrive(B.sfree + 8 * w);
+              mbar_arrive(B.sfree + 8 * (w * 3 + slot));
             }
           }
-          if (!resident) sjob += nsuper;
-          // combine the two column halves of the row through shared memory (named barrier of this warpgroup)
-          ex[set * 128 + r] = mx;
+          if (!resident) sseq += p.nblk;
+          if (T) T[1] = clock64();
+          // combine the partial maxima of the row through shared memory (named barrier of this warpgroup)
+          ex_mx[par * 256 + set * 128 + r] = mx;
           asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
-          mx = fmaxf(mx, ex[(set ^ 1) * 128 + r]);
-          asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");   // both halves read before the buffer is reused
+          if (rag) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mx = fmaxf(mx, ex_mx[par * 256 + i * 32 + lane]);
+          } else {
+            mx = fmaxf(mx, ex_mx[par * 256 + (set ^ 1) * 128 + r]);
+          }
+          if (T) T[2] = clock64();
           // ---- probabilities -> P tiles (fp16, K-major SWIZZLE_128B), consumed by the P V MMAs
           float sum = 0.f;
-          for (int sb = 0; sb < nsuper; ++sb, ++sjob) {
+          for (int j = 0; j < p.nblk; ++j, ++sseq, ++pjob) {
+            const uint32_t slot = sseq % 3u, pb = pjob & 1;
             if (!resident) {
-              mbar_wait(B.sfull + 8 * w, sjob & 1);
+              mbar_wait(B.sfull + 8 * (w * 3 + slot), (sseq / 3u) & 1);
               tc_fence_after();
             }
-            const int j1 = min(p.nblk, (sb + 1) * ATT_SUPER);
-            for (int j = sb * ATT_SUPER; j < j1; ++j, ++pjob) {
-              const uint32_t pb = pjob & 1;
-              if (warp_live) {
-                const int nv = min(ATT_NB, p.len - j * ATT_NB) - cb;
-                uint32_t pk[16];
-                if (nv > 0) {
-                  uint32_t v[32];
-                  tmem_ld_32x32b_x32(t_base + (j - sb * ATT_SUPER) * ATT_NB + cb, v);
-                  tmem_ld_wait();
+            const int nv = min(ATT_NB, p.len - j * ATT_NB) - cc;
+            const uint32_t sPw = sP + (w * 2 + pb) * 16384;
+            if (rag) {
+              uint32_t pk[4] = {0u, 0u, 0u, 0u};
+              if (nv > 0) {
+                uint32_t v[8];
+                tmem_ld_32x32b_x8(t_base + slot * ATT_NB + cc, v);
+                tmem_ld_wait();
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) {
-                    float e0 = ex2_fast(__uint_as_float(v[2 * i]) - mx);
-                    float e1 = ex2_fast(__uint_as_float(v[2 * i + 1]) - mx);
-                    if (nv < 32) {
-                      e0 = (2 * i < nv) ? e0 : 0.f;
-                      e1 = (2 * i + 1 < nv) ? e1 : 0.f;
-                    }
-                    sum += e0 + e1;
-                    const __half2 h2 = __floats2half2_rn(e0, e1);
-                    pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
-                  }
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                for (int i = 0; i < 4; ++i) {
+                  float e0 = ex2_fast(__uint_as_float(v[2 * i]) - mx);
+                  float e1 = ex2_fast(__uint_as_float(v[2 * i + 1]) - mx);
+                  e0 = (2 * i < nv) ? e0 : 0.f;
+                  e1 = (2 * i + 1 < nv) ? e1 : 0.f;
+                  sum += e0 + e1;
+                  const __half2 h2 = __floats2half2_rn(e0, e1);
+                  pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
                 }
-                // the P buffer of two blocks ago must have been consumed by its P V MMAs
-                mbar_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
-                const uint32_t sPw = sP + (w * 2 + pb) * 16384;
+              }
+              tc_fence_before();
+              mbar_arrive(B.sfree + 8 * (w * 3 + slot));
+              mbar_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
+              // P row = query = lane (tile rows 0..31); the read-out is done by the quadrant-0 warps
+              const uint32_t a0 = sPw + sw128_offset((uint32_t)lane, (uint32_t)(cc >> 3));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                           "r"(pk[3]) : "memory");
+              fence_proxy_async();
+            } else {
+              uint32_t pk[16];
+              if (warp_live && nv > 0) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(t_base + slot * ATT_NB + cc, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(B.sfree + 8 * (w * 3 + slot));     // values are in registers: the slot may be refilled
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  float e0 = ex2_fast(__uint_as_float(v[2 * i]) - mx);
+                  float e1 = ex2_fast(__uint_as_float(v[2 * i + 1]) - mx);
+                  if (nv < 32) {
+                    e0 = (2 * i < nv) ? e0 : 0.f;
+                    e1 = (2 * i + 1 < nv) ? e1 : 0.f;
+                  }
+                  sum += e0 + e1;
+                  const __half2 h2 = __floats2half2_rn(e0, e1);
+                  pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+              } else {
+                tc_fence_before();
+                mbar_arrive(B.sfree + 8 * (w * 3 + slot));
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = 0u;
+              }
+              // the P buffer of two blocks ago must have been consumed by its P V MMAs
+              mbar_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
+              if (warp_live) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                   const uint32_t a0 = sPw + sw128_offset((uint32_t)r, (uint32_t)(cb >> 3) + c);
                   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
                                "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
                 }
-              } else {
-                mbar_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
+                fence_proxy_async();
               }
-              if (j == j1 - 1) {   // last block of the super-block: the S region may be overwritten
-                tc_fence_before();
-                mbar_arrive(B.sfree + 8 * w);
-              }
-              fence_proxy_async();
-              mbar_arrive(B.pfull + 8 * (w * 2 + pb));
             }
+            mbar_arrive(B.pfull + 8 * (w * 2 + pb));
+            if (T && j < 5) T[8 + j] = clock64();
           }
-          // row sums: combine the two column halves
-          ex[set * 128 + r] = sum;
-          asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
-          sum += ex[(set ^ 1) * 128 + r];
-          asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
-          // ---- O = sum_j P_j V_j complete; this thread stores HD/2 features of its row
-          mbar_wait(B.ofull + 8 * w, ohead & 1);
-          ++ohead;
-          tc_fence_after();
-          uint32_t o[HD / 2];
-          if constexpr (HD == 32) tmem_ld_32x32b_x16(t_base + ATT_O_COL + set * 16, o);
-          else tmem_ld_32x32b_x8(t_base + ATT_O_COL + set * 8, o);
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(B.ofree + 8 * w);
-          if (qi < p.len) {
-            const float inv = 1.f / sum;
-            uint4* dst = reinterpret_cast<uint4*>(p.out + p.map.row(g, qi) * p.N + head * HD + set * (HD / 2));
-#pragma unroll
-            for (int c = 0; c < HD / 16; ++c) {
-              uint32_t wd[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const __half2 h2 = __floats2half2_rn(__uint_as_float(o[c * 8 + 2 * e]) * inv,
-                                                     __uint_as_float(o[c * 8 + 2 * e + 1]) * inv);
-                wd[e] = *reinterpret_cast<const uint32_t*>(&h2);
-              }
-              dst[c] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-            }
-          }
+          if (T) T[3] = clock64();
+          ex_sum[par * 256 + set * 128 + r] = sum;     // partial row sums, combined at read-out time (after a barrier)
+          if (pend.valid) read_out(pend);
+          if (T) T[4] = clock64();
+          pend.valid = true; pend.sum = sum; pend.head = head; pend.gidx = gidx; pend.rag = rag;
+          // ragged tile: O rows 0..31 are the queries, read out by the quadrant-0 warps
+          pend.row = (warp_live && qi < p.len && (!rag || q == 0)) ? p.map.row(g, qi) : -1;
         }
       }
     }
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
+    if (pend.valid) read_out(pend);
   }
   tc_fence_before();
   __syncthreads();
@@ -508,30 +579,34 @@ static int tc_attention_launch(const __half* qkv, __half* out, SeqMap map, int m
                                cudaStream_t st, bool* handled) {
   *handled = false;
   TcAttnArgs a;
+  a.trace = g_lstm_trace;
   a.mode = mode; a.len = map.len; a.N = N; a.groups = N / 64; a.map = map; a.out = out;
   a.nblk = (a.len + ATT_NB - 1) / ATT_NB;
   a.mtiles = (a.len + 127) / 128;
   a.num_items = map.G * a.groups;
-  const size_t fixed = 2 * 16384 + 4 * 16384 + 512 + 2048 + 128;
+  const size_t fixed = 2 * 16384 + 4 * 16384 + 512 + 8192;
   size_t smem = fixed + 3 * (size_t)a.nblk * ATT_NB * 128;
   a.stream = 0;
   if (smem > 227 * 1024) {   // K / V do not fit: stream them through the ring (two-pass softmax re-reads K)
     a.stream = 1;
     smem = fixed + (size_t)ATT_RING * ATT_STAGE_BYTES;
   }
-  CUtensorMap tmQ, tmKV;
+  a.rag = a.len - (a.mtiles - 1) * 128 <= 32;
+  CUtensorMap tmQ, tmQ32, tmKV;
   const long long tok = (long long)B * S * C;
   if (mode == 0) {
     const uint64_t dims[2] = {(uint64_t)3 * N, (uint64_t)tok};
     const uint64_t str[1] = {(uint64_t)3 * N * 2};
-    const uint32_t boxq[2] = {64, 128}, boxkv[2] = {64, ATT_NB};
+    const uint32_t boxq[2] = {64, 128}, boxq32[2] = {64, 32}, boxkv[2] = {64, ATT_NB};
     if (make_tmap_f16(&tmQ, qkv, 2, dims, str, boxq)) return -1;
+    if (make_tmap_f16(&tmQ32, qkv, 2, dims, str, boxq32)) return -1;
     if (make_tmap_f16(&tmKV, qkv, 2, dims, str, boxkv)) return -1;
   } else {
     const uint64_t dims[4] = {(uint64_t)3 * N, (uint64_t)C, (uint64_t)S, (uint64_t)B};
     const uint64_t str[3] = {(uint64_t)3 * N * 2, (uint64_t)C * 3 * N * 2, (uint64_t)S * C * 3 * N * 2};
-    const uint32_t boxq[4] = {64, 1, 128, 1}, boxkv[4] = {64, 1, ATT_NB, 1};
+    const uint32_t boxq[4] = {64, 1, 128, 1}, boxq32[4] = {64, 1, 32, 1}, boxkv[4] = {64, 1, ATT_NB, 1};
     if (make_tmap_f16(&tmQ, qkv, 4, dims, str, boxq)) return -1;
+    if (make_tmap_f16(&tmQ32, qkv, 4, dims, str, boxq32)) return -1;
     if (make_tmap_f16(&tmKV, qkv, 4, dims, str, boxkv)) return -1;
   }
   auto kern = k_tc_attention<HD>;
@@ -541,7 +616,7 @@ static int tc_attention_launch(const __half* qkv, __half* out, SeqMap map, int m
     configured = true;
   }
   const int grid = a.num_items < num_sms() ? a.num_items : num_sms();
-  kern<<<grid, ATT_THREADS, smem, st>>>(tmQ, tmKV, a);
+  kern<<<grid, ATT_THREADS, smem, st>>>(tmQ, tmQ32, tmKV, a);
   VATSS_LAUNCH_OK();
   *handled = true;
   return 0;

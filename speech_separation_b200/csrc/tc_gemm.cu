@@ -103,7 +103,12 @@ struct TcGemmArgs {
   const float* prelu_a;
 };
 
-constexpr int TCG_THREADS = 192;   // TMA warp, MMA warp, 4 epilogue warps
+// TMA warp, MMA warp and 8 epilogue warps: two warps per TMEM lane quadrant split the columns of the 128-row tile
+// (with one warp per scheduler every tcgen05.ld / shared / global latency of the store path was exposed).  Plain
+// epilogues take alternate 32-column pieces; LayerNorm epilogues take half a row each and exchange the partial
+// mean / variance sums through shared memory.  Falls back to 4 warps (thread = whole row) where the extra staging
+// tiles do not fit next to W, A and the residual tile (K = 256 FFN).
+constexpr int tcg_epilogue_warps(int fixed_bytes) { return fixed_bytes + 8 * 32 * 36 * 4 + 1024 + 2048 <= 227 * 1024 ? 8 : 4; }
 
 // WSPLIT: W is stored as [half(W) | half(W - half(W))] (hi/lo split, 2 x KDIM columns) and both halves are
 // contracted with the same A tile - used where an fp16-rounded weight misses the tolerance (DPRNN fc).
@@ -121,14 +126,23 @@ struct TcGemmSmem {
   static constexpr int OFF_RES = OFF_A + A_STAGES * A_STAGE_BYTES;
   static constexpr int OFF_PAR = OFF_RES + RES_BYTES;  // bias, ln_w, ln_b
   static constexpr int OFF_BAR = OFF_PAR + 3 * NOUT * 4;
-  static constexpr int OFF_STAGE = OFF_BAR + 128;        // per epilogue warp: [32 rows][36 floats] transpose tile
-  static constexpr int TOTAL = OFF_STAGE + 4 * 32 * 36 * 4 + 1024;  // + alignment slack
-  static constexpr int ACC_STAGES = (2 * NOUT <= 512) ? 2 : 1;
-  static constexpr int TMEM_COLS = (ACC_STAGES * NOUT <= 32)    ? 32
-                                   : (ACC_STAGES * NOUT <= 64)  ? 64
-                                   : (ACC_STAGES * NOUT <= 128) ? 128
-                                   : (ACC_STAGES * NOUT <= 256) ? 256
-                                                                : 512;
+  static constexpr int OFF_XCH = OFF_BAR + 128;          // LayerNorm partial sums: [2 halves][128 rows] x (sum, sq)
+  static constexpr int OFF_STAGE = OFF_XCH + 2048;       // per epilogue warp: [32 rows][36 floats] transpose tile
+  static constexpr int EPW = tcg_epilogue_warps(OFF_STAGE);
+  static constexpr int THREADS = 64 + 32 * EPW;
+  static constexpr int TOTAL = OFF_STAGE + EPW * 32 * 36 * 4 + 1024;  // + alignment slack
+  // Accumulators live in a ring of TMEM slots of CH columns.  A tile wider than 256 columns (QKV: 384) is issued
+  // as NCH chunks of 128 columns, each with its own full/empty barrier, so the MMAs of the next chunk / tile overlap
+  // the epilogue of the current one instead of waiting for the whole 384-column tile to drain.
+  static constexpr int NCH = (NOUT > 256) ? NOUT / 128 : 1;
+  static constexpr int CH = NOUT / NCH;
+  static constexpr int ACC_SLOTS = (4 * CH <= 512 && NCH > 1) ? 4 : ((2 * CH <= 512) ? 2 : 1);
+  static constexpr int TMEM_COLS = (ACC_SLOTS * CH <= 32)    ? 32
+                                   : (ACC_SLOTS * CH <= 64)  ? 64
+                                   : (ACC_SLOTS * CH <= 128) ? 128
+                                   : (ACC_SLOTS * CH <= 256) ? 256
+                                                             : 512;
+  static_assert(NOUT % NCH == 0 && CH <= 256, "chunking");
 };
 
 // ---- warp-level staged global access: a warp owns 32 consecutive rows; thread = row in registers, but every
@@ -188,7 +202,7 @@ __device__ __forceinline__ void staged_store_f16(__half* __restrict__ g, long lo
 }
 
 template <int NOUT, int KDIM, int EPI, bool WSPLIT>
-__global__ void __launch_bounds__(TCG_THREADS, 1)
+__global__ void __launch_bounds__((TcGemmSmem<NOUT, KDIM, (EPI == TC_EPI_LN || EPI == TC_EPI_LN_POST), WSPLIT>::THREADS), 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapW,
           const __grid_constant__ CUtensorMap tmapR, TcGemmArgs p) {
   constexpr bool RES_TMA = (EPI == TC_EPI_LN || EPI == TC_EPI_LN_POST);   // residual tile prefetched by TMA
@@ -203,9 +217,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
   float* sPar = reinterpret_cast<float*>(gen + L::OFF_PAR);
   const uint32_t bars = base + L::OFF_BAR;
   const uint32_t bar_w = bars, bar_afull = bars + 8, bar_aempty = bars + 24, bar_accfull = bars + 40,
-                 bar_accempty = bars + 56, bar_rfull = bars + 72, bar_rempty = bars + 80;
+                 bar_accempty = bars + 72, bar_rfull = bars + 104, bar_rempty = bars + 112;
   const uint32_t sR = base + L::OFF_RES;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + L::OFF_BAR + 96);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + L::OFF_BAR + 120);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -214,11 +228,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_afull + 8 * s, 1);
       mbar_init(bar_aempty + 8 * s, 1);
+    }
+    for (int s = 0; s < 4; ++s) {
       mbar_init(bar_accfull + 8 * s, 1);
-      mbar_init(bar_accempty + 8 * s, 128);
+      mbar_init(bar_accempty + 8 * s, 32 * L::EPW);
     }
     mbar_init(bar_rfull, 1);
-    mbar_init(bar_rempty, 128);
+    mbar_init(bar_rempty, 32 * L::EPW);
     fence_mbar_init();
     prefetch_tmap(&tmapA);
     prefetch_tmap(&tmapW);
@@ -230,7 +246,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
     sPar[2 * NOUT + i] = p.ln_b ? p.ln_b[i] : 0.f;
   }
   if (warp == 1) {
-    tmem_alloc<1>(bars + 96, L::TMEM_COLS);
+    tmem_alloc<1>(bars + 120, L::TMEM_COLS);
     tmem_relinquish<1>();
   }
   tc_fence_before();
@@ -266,14 +282,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
       int i = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
         const int s = i % L::A_STAGES, ph = (i / L::A_STAGES) & 1;
-        const int as = i % L::ACC_STAGES, aph = (i / L::ACC_STAGES) & 1;
-        mbar_wait(bar_accempty + 8 * as, aph ^ 1);
         mbar_wait(bar_afull + 8 * s, ph);
-        tc_fence_after();
 #pragma unroll
-        for (int n0 = 0; n0 < NOUT; n0 += 256) {
-          const int nn = (NOUT - n0) < 256 ? (NOUT - n0) : 256;
-          const uint32_t idesc = idesc_f16(128, nn, 0);
+        for (int ch = 0; ch < L::NCH; ++ch) {
+          const int jj = i * L::NCH + ch, as = jj % L::ACC_SLOTS, aph = (jj / L::ACC_SLOTS) & 1;
+          const int n0 = ch * L::CH;
+          const uint32_t idesc = idesc_f16(128, L::CH, 0);
+          mbar_wait(bar_accempty + 8 * as, aph ^ 1);
+          tc_fence_after();
 #pragma unroll
           for (int part = 0; part < (WSPLIT ? 2 : 1); ++part) {
 #pragma unroll
@@ -281,12 +297,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
               const int kb = k16 >> 2, kk = k16 & 3;
               const uint64_t a_desc = smem_desc_sw128_kmajor(sA + s * L::A_STAGE_BYTES + kb * 16384) + (uint64_t)(kk * 2);
               const uint64_t b_desc = smem_desc_sw128_kmajor(sW + (part * L::KB + kb) * NOUT * 128 + n0 * 128) + (uint64_t)(kk * 2);
-              umma_f16<1>(tmem + as * NOUT + n0, a_desc, b_desc, idesc, (part > 0 || k16 > 0) ? 1u : 0u);
+              umma_f16<1>(tmem + as * L::CH, a_desc, b_desc, idesc, (part > 0 || k16 > 0) ? 1u : 0u);
             }
           }
+          if (ch == L::NCH - 1) umma_commit(bar_aempty + 8 * s);
+          umma_commit(bar_accfull + 8 * as);
         }
-        umma_commit(bar_aempty + 8 * s);
-        umma_commit(bar_accfull + 8 * as);
       }
     }
     __syncwarp();
@@ -300,19 +316,30 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
     const float slope = (p.act16 == 2 && p.prelu_a) ? p.prelu_a[0] : 0.f;
     int i = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
-      const int as = i % L::ACC_STAGES, aph = (i / L::ACC_STAGES) & 1;
       const long long row0 = (long long)tile * 128 + q * 32;          // first row of this warp
       const long long left = p.M - row0;
       const int rows_valid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + as * NOUT;
+      // (LayerNorm epilogues have one chunk per tile: slot / phase of chunk 0)
+      const int as = (i * L::NCH) % L::ACC_SLOTS, aph = ((i * L::NCH) / L::ACC_SLOTS) & 1;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + as * L::CH;
       if constexpr (EPI == TC_EPI_F16 || EPI == TC_EPI_F32) {
-        mbar_wait(bar_accfull + 8 * as, aph);
-        tc_fence_after();
+        const int half = (warp - 2) >> 2;       // which of the (EPW / 4) warps of this lane quadrant
+        int cur = -1;
 #pragma unroll 1
-        for (int c0 = 0; c0 < NOUT; c0 += 32) {
+        for (int c0 = half * 32; c0 < NOUT; c0 += 8 * L::EPW) {
+          const int jj = i * L::NCH + c0 / L::CH, cs = jj % L::ACC_SLOTS;
+          if (c0 / L::CH != cur) {
+            cur = c0 / L::CH;
+            mbar_wait(bar_accfull + 8 * cs, (jj / L::ACC_SLOTS) & 1);
+            tc_fence_after();
+          }
           uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + c0, r);
+          tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + cs * L::CH + c0 % L::CH, r);
           tmem_ld_wait();
+          if (L::NCH > 1 && c0 % L::CH == L::CH - 8 * L::EPW + half * 32) {   // this warp's last piece of the chunk is in
+            tc_fence_before();                                        // registers: hand the slot back
+            mbar_arrive(bar_accempty + 8 * cs);
+          }
           if constexpr (EPI == TC_EPI_F16) {
             uint32_t pk[16];
 #pragma unroll
@@ -331,23 +358,30 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
           }
         }
       } else {
-        // LayerNorm over the whole row held in registers; the residual tile was prefetched into shared memory by TMA
-        float v[NOUT];
+        // LayerNorm over the row: each thread holds NOUT / NH columns (NH = warps per lane quadrant); the residual tile
+        // was prefetched into shared memory by TMA
+        constexpr int NH = L::EPW / 4;
+        constexpr int NC = NOUT / NH;
+        static_assert(NC % 32 == 0, "LayerNorm epilogue: column split");
+        const int half = (warp - 2) >> 2;
+        const int cbase = half * NC;
+        float* xch = reinterpret_cast<float*>(gen + L::OFF_XCH);
+        float v[NC];
         const int rr = q * 32 + lane;
         mbar_wait(bar_rfull, i & 1);
         mbar_wait(bar_accfull + 8 * as, aph);
         tc_fence_after();
 #pragma unroll
-        for (int c0 = 0; c0 < NOUT; c0 += 32) {
+        for (int c0 = 0; c0 < NC; c0 += 32) {
           uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + c0, r);
+          tmem_ld_32x32b_x32(taddr + cbase + c0, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[c0 + j] = __uint_as_float(r[j]) + sBias[c0 + j];
+          for (int j = 0; j < 32; ++j) v[c0 + j] = __uint_as_float(r[j]) + sBias[cbase + c0 + j];
           if constexpr (EPI == TC_EPI_LN) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              const float4 x = *reinterpret_cast<const float4*>(gen + L::OFF_RES + (c0 / 32) * 16384 +
+              const float4 x = *reinterpret_cast<const float4*>(gen + L::OFF_RES + ((cbase + c0) / 32) * 16384 +
                                                                 sw128_offset((uint32_t)rr, (uint32_t)c));
               v[c0 + 4 * c] += x.x; v[c0 + 4 * c + 1] += x.y; v[c0 + 4 * c + 2] += x.z; v[c0 + 4 * c + 3] += x.w;
             }
@@ -355,28 +389,38 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
         }
         float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < NOUT; ++j) sum += v[j];
+        for (int j = 0; j < NC; ++j) sum += v[j];
+        if constexpr (NH == 2) {   // the two warps of a lane quadrant meet at named barrier 1 + q
+          xch[half * 256 + rr] = sum;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+          sum += xch[(half ^ 1) * 256 + rr];
+        }
         const float mean = sum * (1.f / NOUT);
         float sq = 0.f;
 #pragma unroll
-        for (int j = 0; j < NOUT; ++j) {
+        for (int j = 0; j < NC; ++j) {
           const float d = v[j] - mean;
           sq = fmaf(d, d, sq);
         }
+        if constexpr (NH == 2) {
+          xch[half * 256 + 128 + rr] = sq;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+          sq += xch[(half ^ 1) * 256 + 128 + rr];
+        }
         const float rstd = rsqrtf(sq * (1.f / NOUT) + 1e-5f);
 #pragma unroll
-        for (int j = 0; j < NOUT; ++j) v[j] = (v[j] - mean) * rstd * sLw[j] + sLb[j];
+        for (int j = 0; j < NC; ++j) v[j] = (v[j] - mean) * rstd * sLw[cbase + j] + sLb[cbase + j];
 #pragma unroll
-        for (int c0 = 0; c0 < NOUT; c0 += 32) {
+        for (int c0 = 0; c0 < NC; c0 += 32) {
           if constexpr (EPI == TC_EPI_LN_POST) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              const float4 x = *reinterpret_cast<const float4*>(gen + L::OFF_RES + (c0 / 32) * 16384 +
+              const float4 x = *reinterpret_cast<const float4*>(gen + L::OFF_RES + ((cbase + c0) / 32) * 16384 +
                                                                 sw128_offset((uint32_t)rr, (uint32_t)c));
               v[c0 + 4 * c] += x.x; v[c0 + 4 * c + 1] += x.y; v[c0 + 4 * c + 2] += x.z; v[c0 + 4 * c + 3] += x.w;
             }
           }
-          staged_store_f32(p.out32 + row0 * p.ldo32 + c0, p.ldo32, rows_valid, stage, lane, v + c0);
+          staged_store_f32(p.out32 + row0 * p.ldo32 + cbase + c0, p.ldo32, rows_valid, stage, lane, v + c0);
           if (p.out16) {
             uint32_t pk[16];
 #pragma unroll
@@ -387,7 +431,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
               const __half2 h = __floats2half2_rn(a, b);
               pk[j] = *reinterpret_cast<const uint32_t*>(&h);
             }
-            staged_store_f16(p.out16 + row0 * p.ldo16 + c0, p.ldo16, rows_valid, stage, lane, pk);
+            staged_store_f16(p.out16 + row0 * p.ldo16 + cbase + c0, p.ldo16, rows_valid, stage, lane, pk);
             if (p.out16lo) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -399,14 +443,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
                 const __half2 lo = __floats2half2_rn(a - hf.x, b - hf.y);
                 pk[j] = *reinterpret_cast<const uint32_t*>(&lo);
               }
-              staged_store_f16(p.out16lo + row0 * p.ldo16 + c0, p.ldo16, rows_valid, stage, lane, pk);
+              staged_store_f16(p.out16lo + row0 * p.ldo16 + cbase + c0, p.ldo16, rows_valid, stage, lane, pk);
             }
           }
         }
       }
       if constexpr (RES_TMA) mbar_arrive(bar_rempty);
-      tc_fence_before();
-      mbar_arrive(bar_accempty + 8 * as);
+      if constexpr (L::NCH == 1) {
+        tc_fence_before();
+        mbar_arrive(bar_accempty + 8 * as);
+      }
     }
   }
   tc_fence_before();
@@ -447,7 +493,7 @@ static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const
     configured = true;
   }
   const int grid = args.num_tiles < num_sms() ? args.num_tiles : num_sms();
-  kern<<<grid, TCG_THREADS, L::TOTAL, st>>>(tmA, tmW, tmR, args);
+  kern<<<grid, L::THREADS, L::TOTAL, st>>>(tmA, tmW, tmR, args);
   VATSS_LAUNCH_OK();
   return 0;
 }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: DPTN-AV separation forward (+ PIT SI-SNRi) in separated audio-seconds/s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|eager]
                     [--batch 32] [--seconds 4] [--engine auto|generic|tensor]
 
 One "step" = one forward pass of DPTN-AV (src/configs/model/dptn_wav_av.yaml) over one batch of
@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--engine", default="auto", choices=["auto", "generic", "tensor"])
@@ -204,6 +204,38 @@ def main():
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                           "impl": "reference", "cpu_baseline": info, "gpu_launches": 0,
                           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    if args.impl == "eager":
+        # the same stock torch.nn modules on one B200 ("library Blackwell kernels": cuDNN LSTM, fused
+        # MHA, cuBLAS) - a second reported baseline, not part of the driver contract.  fp32 with torch's default TF32 flags.
+        if rank != 0:
+            return 0
+        import torch
+
+        import speech_separation_b200 as V
+        from oracle import torch_port
+        dev = torch.device("cuda", local_rank)
+        torch.manual_seed(42)
+        net = (V.DPTNAVWavEncDec(**MODEL_KW) if args.model == "dptn_av"
+               else getattr(V, OTHER_MODELS[args.model][0])(**OTHER_MODELS[args.model][1])).eval().to(dev)
+        mix, s1, s2, e1, e2 = (t.to(dev) for t in make_batch(B, T, 1234))
+        if args.model != "dptn_av":
+            e1 = e2 = None
+        for _ in range(max(args.warmup, 3)):
+            torch_port.forward(net, mix, e1, e2)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            torch_port.forward(net, mix, e1, e2)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / args.steps
+        print(json.dumps({"metric": METRIC.replace("dptn_av", args.model), "value": B * T / SR / (ms * 1e-3), "unit": UNIT,
+                          "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "dtype": "f32 (TF32 defaults)", "data": "synthetic", "config": config,
+                          "impl": "eager_torch_gpu", "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
         return 0
 
     import torch

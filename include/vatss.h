@@ -196,6 +196,8 @@ int vatss_tc_attention(const void* qkv16, void* out16, int mode, int B, int S, i
 unsigned long long vatss_launch_count(void);
 /* debug: device buffer (>= 128 int64) receiving a clock64 trace of CTA 0 of vatss_tc_lstm; NULL disables */
 void vatss_debug_lstm_trace(void* dev_buffer);
+/* debug / experiments: cap the grid of the persistent GEMM and attention kernels (0 = one CTA per SM) */
+void vatss_debug_cta_limit(int ctas);
 int vatss_profile_begin(void);
 int vatss_profile_end(float* ms_per_stage, int* launches_per_stage, int n_stages);
 

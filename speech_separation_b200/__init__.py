@@ -4,11 +4,12 @@ Public surface mirrors the reference's `src.model`, `src.loss` and `src.metrics`
 the DPTN-AV separation forward pass and its PIT SI-SNR loss / metrics.  All compute happens in
 hand-written CUDA kernels inside libvatss_b200.so (C ABI in include/vatss.h).
 """
+from .inference import Inferencer, MetricTracker
 from .loss import SiSNRLoss, SiSNRWavLoss, pit_sisnr_all
 from .metrics import SISNRiMetric, SISNRMetric
 from .model import DPRNNEncDec, DPTNAVWavEncDec, DPTNEncDec, DPTNWavEncDec, OverlapAdd, SplitToFolds
 
 __all__ = [
     "DPTNAVWavEncDec", "DPTNWavEncDec", "DPTNEncDec", "DPRNNEncDec", "SplitToFolds", "OverlapAdd",
-    "SiSNRLoss", "SiSNRWavLoss", "SISNRMetric", "SISNRiMetric", "pit_sisnr_all",
+    "SiSNRLoss", "SiSNRWavLoss", "SISNRMetric", "SISNRiMetric", "pit_sisnr_all", "Inferencer", "MetricTracker",
 ]

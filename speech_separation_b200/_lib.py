@@ -69,6 +69,7 @@ EXPORTS = {
     "vatss_tc_attention": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 7 + [ctypes.c_void_p]),
     "vatss_launch_count": (ctypes.c_ulonglong, []),
     "vatss_debug_lstm_trace": (None, [ctypes.c_void_p]),
+    "vatss_debug_cta_limit": (None, [ctypes.c_int]),
     "vatss_profile_begin": (ctypes.c_int, []),
     "vatss_profile_end": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "vatss_sisnr_chunks": (ctypes.c_int, [ctypes.c_int]),

@@ -615,7 +615,7 @@ static int tc_attention_launch(const __half* qkv, __half* out, SeqMap map, int m
     VATSS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
     configured = true;
   }
-  const int grid = a.num_items < num_sms() ? a.num_items : num_sms();
+  const int grid = a.num_items < grid_cap() ? a.num_items : grid_cap();
   kern<<<grid, ATT_THREADS, smem, st>>>(tmQ, tmQ32, tmKV, a);
   VATSS_LAUNCH_OK();
   *handled = true;

@@ -72,6 +72,9 @@ static int make_tmap_any(CUtensorMap* out, CUtensorMapDataType dt, const void* b
   return 0;
 }
 
+int g_cta_limit = 0;   // experiment knob: cap on persistent-kernel grids (0 = all SMs)
+int grid_cap() { return (g_cta_limit > 0 && g_cta_limit < num_sms()) ? g_cta_limit : num_sms(); }
+
 int num_sms() {
   static int n = 0;
   if (!n) {
@@ -492,7 +495,7 @@ static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const
     VATSS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  const int grid = args.num_tiles < num_sms() ? args.num_tiles : num_sms();
+  const int grid = args.num_tiles < grid_cap() ? args.num_tiles : grid_cap();
   kern<<<grid, L::THREADS, L::TOTAL, st>>>(tmA, tmW, tmR, args);
   VATSS_LAUNCH_OK();
   return 0;

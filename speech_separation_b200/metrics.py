@@ -24,6 +24,12 @@ class SS2BaseMetric:
             mix = mix.to(dev) if mix is not None else None
         return pit_sisnr_all(s1_pred, s2_pred, s1, s2, mix)
 
+    def _shared_summary(self, shared, s1_pred, s2_pred, s1, s2, mix):
+        """summary[8] of the batch; `shared` (inference._SharedSisnr) lets several metrics reuse one kernel pass."""
+        if shared is not None and (self.device is None or self.device == "auto"):
+            return shared.summary({"s1_pred": s1_pred, "s2_pred": s2_pred, "s1": s1, "s2": s2, "mix": mix})
+        return self._summary(s1_pred, s2_pred, s1, s2, mix)[2]
+
 
 class SISNRMetric(SS2BaseMetric):
     """__call__(**batch) -> float: batch-level PIT SI-SNR in dB."""
@@ -32,6 +38,10 @@ class SISNRMetric(SS2BaseMetric):
         _, _, summary = self._summary(s1_pred, s2_pred, s1, s2)
         return float(summary[3].item())
 
+    def device_value(self, s1_pred, s2_pred, s1, s2, mix=None, shared=None, **batch):
+        """Same value as __call__, as a 0-d float32 device tensor (no host synchronisation)."""
+        return self._shared_summary(shared, s1_pred, s2_pred, s1, s2, mix)[3].float()
+
 
 class SISNRiMetric(SS2BaseMetric):
     """__call__(**batch) -> 0-d tensor: PIT SI-SNR minus the mean SI-SNR of the mixture."""
@@ -39,6 +49,9 @@ class SISNRiMetric(SS2BaseMetric):
     def __call__(self, s1_pred, s2_pred, s1, s2, mix, **batch):
         _, _, summary = self._summary(s1_pred, s2_pred, s1, s2, mix)
         return summary[4].float()
+
+    def device_value(self, s1_pred, s2_pred, s1, s2, mix, shared=None, **batch):
+        return self._shared_summary(shared, s1_pred, s2_pred, s1, s2, mix)[4].float()
 
     def per_utterance(self, s1_pred, s2_pred, s1, s2, mix, **batch):
         """Per-utterance PIT SI-SNRi (B,) f64 - what src/utils/eval_si_snri.py:31-39 computes file by file."""

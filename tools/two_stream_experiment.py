@@ -19,7 +19,10 @@ def timed(fn, n=5):
     return a.elapsed_time(b) / n
 net = mk()
 print("1 stream, B=32:", timed(lambda: net(mix=mix, s1_embedding=e1, s2_embedding=e2)))
-for nsplit in (2, 4):
+from speech_separation_b200 import _lib
+lib = _lib.load()
+for nsplit, cap in ((2, 0), (2, 74), (2, 100), (2, 60), (4, 37), (4, 74)):
+    lib.vatss_debug_cta_limit(cap)
     nets = [mk() for _ in range(nsplit)]
     for n_ in nets: n_.load_state_dict(net.state_dict())
     streams = [torch.cuda.Stream() for _ in range(nsplit)]
@@ -31,4 +34,5 @@ for nsplit in (2, 4):
             with torch.cuda.stream(st):
                 n_(mix=mix[i*h:(i+1)*h], s1_embedding=e1[i*h:(i+1)*h], s2_embedding=e2[i*h:(i+1)*h])
         for st in streams: cur.wait_stream(st)
-    print(f"{nsplit} streams, B={h} each:", timed(run))
+    print(f"{nsplit} streams, B={h} each, CTA cap {cap}:", timed(run))
+lib.vatss_debug_cta_limit(0)

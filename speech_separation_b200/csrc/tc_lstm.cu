@@ -302,12 +302,15 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
       const int t = dir == 0 ? step : len - 1 - step;
       long long* T = (trg && step >= 8 && step < 12) ? p.trace + (step - 8) * 32 + 8 : nullptr;
       uint32_t hp[LSTM_CHUNKS][8];   // packed fp16 h of this step (kept until all h-part MMAs have read sH)
+      bool next_ready = false;       // accfull of the next chunk, probed while this chunk's gate math runs
 #pragma unroll
       for (int c = 0; c < LSTM_CHUNKS; ++c) {
         if (T) T[3 * c] = clock64();
-        mbar_wait(bar_accfull + 8 * c, step & 1);
+        if (!next_ready) mbar_wait(bar_accfull + 8 * c, step & 1);
         if (T) T[3 * c + 1] = clock64();
         tc_fence_after();
+        // the ~90-cycle round trip of a (normally already complete) barrier test overlaps the gate math below
+        next_ready = (c + 1 < LSTM_CHUNKS) && mbar_try_wait(bar_accfull + 8 * (c + 1), step & 1);
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + c * 128 + half * 16;
         __half* orow = p.out + (row_base + (long long)t * row_tstride) * ldo + dir * LSTM_H + c * LSTM_UNITS_PER_CHUNK + half * 16;
         // two passes of 8 hidden units keep the live register set small (no spills of the packed h values)

@@ -122,6 +122,11 @@ int launch_ola_token_major(const float* y, int B, int S, int C, int P, int L, in
 int launch_mask_combine(const float* t, const float* g, const float* enc, float* u, long long n, cudaStream_t st);
 int launch_decoder(const float* u, const float* Wd, int B, int L, int N, int K, int T, float* proj,
                    float* wav, cudaStream_t st);
+int launch_decoder_ola(const float* proj, int pitch, int B, int L, int K, int T, float* wav, cudaStream_t st);
+int launch_fold_head(const float* Whead, const float* bhead, const float* Wd, int N, int K, float* wfold, float* wdT,
+                     float* cfold, cudaStream_t st);
+int launch_ola_decode(const float* y, const float* enc, const float* wfold, const float* wdT, const float* cfold, int B,
+                      int S, int C, int P, int L, int N, int K, float* proj, cudaStream_t st);
 
 // sisnr.cu
 int sisnr_chunks(int T);

@@ -40,6 +40,7 @@ struct SubPacked {
 struct Packed {
   SubPacked sub[64];
   __half *wspk, *whead, *wgate;
+  float *wfold, *wdT, *cfold;   // Wd^T Whead, Wd^T, Wd^T bhead (post-conv head folded into the decoder projection)
 };
 
 size_t carve_packed(const vatss_model_desc* d, void* buf, Packed* out) {
@@ -60,6 +61,10 @@ size_t carve_packed(const vatss_model_desc* d, void* buf, Packed* out) {
   p.wspk = b.take<__half>(2 * N * N);
   p.whead = b.take<__half>(N * N);
   p.wgate = b.take<__half>(d->kind == VATSS_KIND_DPTN_MASK ? N * N : 0);
+  const bool fold = d->kind != VATSS_KIND_DPTN_MASK;   // post-conv head folded into the decoder projection
+  p.wfold = b.take<float>(fold ? (size_t)d->K * N : 0);
+  p.wdT = b.take<float>(fold ? (size_t)d->K * N : 0);
+  p.cfold = b.take<float>(fold ? (size_t)d->K : 0);
   if (out) *out = p;
   return b.off;
 }
@@ -96,7 +101,7 @@ int to_half(const float* src, __half* dst, long long rows, int cols, int scaled_
 
 // ---- workspace ----------------------------------------------------------------------------
 struct Work {
-  float *enc32, *vis, *xa32, *xb32, *y32, *ola32, *u32, *hT, *hG, *proj;
+  float *enc32, *vis, *xa32, *xb32, *y32, *u32, *hT, *hG, *proj;
   __half *xa16, *xb16, *xa16lo, *xb16lo, *qkv16, *att16, *rnn16, *ola16;
 };
 
@@ -117,12 +122,11 @@ size_t carve_work(const vatss_model_desc* d, int B, int Tv, int L, int S, void* 
   w.att16 = b.take<__half>(dprnn ? 0 : tok * N);
   w.rnn16 = b.take<__half>(tok * 2 * H);
   w.y32 = b.take<float>(tok * 2 * N);
-  w.ola32 = b.take<float>(fr * 2 * N);
   w.ola16 = b.take<__half>(fr * 2 * N);
   w.u32 = b.take<float>(fr * N);
   w.hT = b.take<float>(mask ? fr * N : 0);
   w.hG = b.take<float>(mask ? fr * N : 0);
-  w.proj = b.take<float>(fr * d->K);
+  w.proj = b.take<float>(fr * 2 * d->K);
   if (out) *out = w;
   return b.off;
 }
@@ -179,8 +183,12 @@ int tensor_engine_pack(const vatss_model_desc* d, const float* const* params, vo
     }
   if ((rc = to_half(params[VATSS_P_SPK_W], p.wspk, 2 * N, N, 0, 1.f, st))) return rc;
   if ((rc = to_half(params[VATSS_P_HEAD_W], p.whead, N, N, 0, 1.f, st))) return rc;
-  if (d->kind == VATSS_KIND_DPTN_MASK)
+  if (d->kind == VATSS_KIND_DPTN_MASK) {
     if ((rc = to_half(params[VATSS_P_HGATE_W], p.wgate, N, N, 0, 1.f, st))) return rc;
+  } else if ((rc = launch_fold_head(params[VATSS_P_HEAD_W], params[VATSS_P_HEAD_B], params[VATSS_P_DECODER_W], N, d->K,
+                                    p.wfold, p.wdT, p.cfold, st))) {
+    return rc;
+  }
   return 0;
 }
 
@@ -265,8 +273,18 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
   if ((rc = launch_tc_gemm(TC_EPI_F32, w.xa16, N, p.wspk, params[VATSS_P_SPK_B], nullptr, 0, nullptr, nullptr, w.y32,
                            2 * N, nullptr, 0, 0, nullptr, tok, 2 * N, N, st)))
     return rc;
-  if ((rc = launch_ola_token_major(w.y32, B, S, C, d->P, L, 2 * N, w.ola32, w.ola16, st))) return rc;
   float* preds[2] = {s1_pred, s2_pred};
+  if (d->kind != VATSS_KIND_DPTN_MASK) {
+    // overlap-add + post-conv + skip + decoder projection in one pass over the speaker-split output
+    rc = launch_ola_decode(w.y32, w.enc32, p.wfold, p.wdT, p.cfold, B, S, C, d->P, L, N, d->K, w.proj, st);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      for (int j = 0; j < 2; ++j)
+        if ((rc = launch_decoder_ola(w.proj + j * d->K, 2 * d->K, B, L, d->K, T, preds[j], st))) return rc;
+      return 0;
+    }
+  }
+  if ((rc = launch_ola_token_major(w.y32, B, S, C, d->P, L, 2 * N, nullptr, w.ola16, st))) return rc;
   for (int j = 0; j < 2; ++j) {
     if (d->kind == VATSS_KIND_DPTN_MASK) {
       if ((rc = launch_tc_gemm(TC_EPI_F32, w.ola16 + j * N, 2 * N, p.whead, params[VATSS_P_HEAD_B], nullptr, 0, nullptr,

@@ -185,14 +185,126 @@ k_encoder(const float* __restrict__ mix, const float* __restrict__ Wenc, const f
   }
 }
 
+// Same computation for N = 32 * CH (CH = 2, 4): every lane owns CH consecutive channels, so each warp store is one
+// contiguous row (16-byte fp32 / 8-byte fp16 accesses per lane) instead of CH separate 128-byte instructions.
+template <int CH>
+__global__ void __launch_bounds__(256)
+k_encoder_vec(const float* __restrict__ mix, const float* __restrict__ Wenc, const float* __restrict__ vis,
+              const float* __restrict__ gate, const float* __restrict__ vln_w, const float* __restrict__ vln_b,
+              int T, int Tv, int K, int L, int S, int C, int P, float* __restrict__ enc,
+              float* __restrict__ seg, __half* __restrict__ seg16, __half* __restrict__ seg16lo) {
+  constexpr int N = 32 * CH;
+  extern __shared__ float smem[];
+  const int st = K / 2;
+  const int b = blockIdx.y;
+  const int l0 = blockIdx.x * ENC_FRAMES_PER_BLOCK;
+  const int nfr = min(ENC_FRAMES_PER_BLOCK, L - l0);
+  const int nsamp = (nfr - 1) * st + K;
+  float* s_w = smem;               // [K][N]
+  float* s_mix = smem + K * N;     // [nsamp]
+  for (int i = threadIdx.x; i < K * N; i += blockDim.x) {
+    int k = i / N, n = i % N;
+    s_w[i] = Wenc[n * K + k];
+  }
+  const float* mrow = mix + (size_t)b * T + (size_t)l0 * st;
+  for (int i = threadIdx.x; i < nsamp; i += blockDim.x) s_mix[i] = mrow[i];
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int n0 = lane * CH;
+  const bool av = (vis != nullptr);
+  float tg = 0.f, scale = 0.f, lw[CH], lb[CH];
+  if (av) {
+    tg = tanhf(gate[0]);
+    scale = (float)Tv / (float)L;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) { lw[i] = vln_w[n0 + i]; lb[i] = vln_b[n0 + i]; }
+  }
+  for (int f = warp; f < nfr; f += nwarps) {
+    const int l = l0 + f;
+    float e[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) e[i] = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float x = s_mix[f * st + k];
+#pragma unroll
+      for (int i = 0; i < CH; ++i) e[i] = fmaf(s_w[k * N + n0 + i], x, e[i]);
+    }
+    if (av) {
+      float src = scale * ((float)l + 0.5f) - 0.5f;
+      src = src < 0.f ? 0.f : src;
+      int i0 = (int)src;
+      if (i0 > Tv - 1) i0 = Tv - 1;
+      const int i1 = i0 + ((i0 < Tv - 1) ? 1 : 0);
+      const float lam1 = src - (float)i0, lam0 = 1.f - lam1;
+      const float* v0 = vis + ((size_t)b * Tv + i0) * N + n0;
+      const float* v1 = vis + ((size_t)b * Tv + i1) * N + n0;
+      float vi[CH];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        vi[i] = lam0 * v0[i] + lam1 * v1[i];
+        sum += vi[i];
+      }
+      const float mean = warp_sum(sum) / (float)N;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const float d = vi[i] - mean;
+        sq += d * d;
+      }
+      const float rstd = rsqrtf(warp_sum(sq) / (float)N + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < CH; ++i) e[i] += tg * ((vi[i] - mean) * rstd * lw[i] + lb[i]);
+    }
+    auto store32 = [&](float* dst) {
+      if constexpr (CH == 4) *reinterpret_cast<float4*>(dst) = make_float4(e[0], e[1], e[2], e[3]);
+      else *reinterpret_cast<float2*>(dst) = make_float2(e[0], e[1]);
+    };
+    store32(enc + ((size_t)b * L + l) * N + n0);
+    if (seg != nullptr || seg16 != nullptr) {
+      uint32_t hi[CH / 2], lo[CH / 2];
+#pragma unroll
+      for (int i = 0; i < CH / 2; ++i) {
+        const __half2 h2 = __floats2half2_rn(e[2 * i], e[2 * i + 1]);
+        const float2 back = __half22float2(h2);
+        const __half2 l2 = __floats2half2_rn(e[2 * i] - back.x, e[2 * i + 1] - back.y);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
+      auto store16 = [&](__half* dst, const uint32_t* v) {
+        if constexpr (CH == 4) *reinterpret_cast<uint2*>(dst) = make_uint2(v[0], v[1]);
+        else *reinterpret_cast<uint32_t*>(dst) = v[0];
+      };
+      int s_lo = (l - C + 1 + P - 1);
+      s_lo = s_lo <= 0 ? 0 : s_lo / P;
+      int s_hi = l / P;
+      if (s_hi > S - 1) s_hi = S - 1;
+      for (int s = s_lo; s <= s_hi; ++s) {
+        const size_t row = ((size_t)b * S + s) * C + (l - P * s);
+        if (seg) store32(seg + row * N + n0);
+        if (seg16) store16(seg16 + row * N + n0, hi);
+        if (seg16lo) store16(seg16lo + row * N + n0, lo);
+      }
+    }
+  }
+}
+
 int launch_encoder(const float* mix, const float* Wenc, const float* vis, const float* gate,
                    const float* vln_w, const float* vln_b, int B, int T, int Tv, int N, int K, int L, int S,
                    int C, int P, float* enc, float* seg, __half* seg16, cudaStream_t st, __half* seg16lo) {
   VATSS_CHECK_ARG(N <= 32 * ENC_MAX_NI, "encoder: num_features %d > %d unsupported", N, 32 * ENC_MAX_NI);
   dim3 grid(ceil_div(L, ENC_FRAMES_PER_BLOCK), B);
   size_t smem = ((size_t)K * N + (size_t)(ENC_FRAMES_PER_BLOCK - 1) * (K / 2) + K) * sizeof(float);
-  k_encoder<<<grid, 256, smem, st>>>(mix, Wenc, vis, gate, vln_w, vln_b, T, Tv, N, K, L, S, C, P, enc, seg,
-                                     seg16, seg16lo);
+  if (N == 128)
+    k_encoder_vec<4><<<grid, 256, smem, st>>>(mix, Wenc, vis, gate, vln_w, vln_b, T, Tv, K, L, S, C, P, enc, seg, seg16,
+                                              seg16lo);
+  else if (N == 64)
+    k_encoder_vec<2><<<grid, 256, smem, st>>>(mix, Wenc, vis, gate, vln_w, vln_b, T, Tv, K, L, S, C, P, enc, seg, seg16,
+                                              seg16lo);
+  else
+    k_encoder<<<grid, 256, smem, st>>>(mix, Wenc, vis, gate, vln_w, vln_b, T, Tv, N, K, L, S, C, P, enc, seg,
+                                       seg16, seg16lo);
   VATSS_LAUNCH_OK();
   return 0;
 }

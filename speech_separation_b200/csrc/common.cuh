@@ -125,6 +125,10 @@ int launch_decoder(const float* u, const float* Wd, int B, int L, int N, int K, 
 int launch_decoder_ola(const float* proj, int pitch, int B, int L, int K, int T, float* wav, cudaStream_t st);
 int launch_fold_head(const float* Whead, const float* bhead, const float* Wd, int N, int K, float* wfold, float* wdT,
                      float* cfold, cudaStream_t st);
+int launch_fold_spk(const float* wfold, const float* Wspk, const float* bspk, int N, int K, float* w2, float* c2,
+                    cudaStream_t st);
+int launch_tail_fused(const __half* px, const float* enc, const float* w2, const float* c2, const float* wdT,
+                      const float* cfold, int B, int S, int C, int P, int L, int N, int K, float* proj, cudaStream_t st);
 int launch_ola_decode(const float* y, const float* enc, const float* wfold, const float* wdT, const float* cfold, int B,
                       int S, int C, int P, int L, int N, int K, float* proj, cudaStream_t st);
 

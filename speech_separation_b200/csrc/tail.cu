@@ -156,6 +156,139 @@ k_ola_decode(const float* __restrict__ y, const float* __restrict__ enc, const f
   }
 }
 
+// ----------------------------------------------------------------------------------------
+// The speaker split is linear too (dptn_wav.py:47: Conv2d 1x1 on PReLU(x)), so it folds into the same pass:
+//   frames[b,l,spk,k] = sum_n w2[spk,k,n] (sum over the <= 2 chunk rows of PReLU(x)[row, n])
+//                       + rows * c2[spk,k] + sum_n Wd[n,k] enc[b,l,n] + cfold[k]
+// with w2 = wfold Wspk[spk] and c2 = wfold bspk[spk].  The whole tail becomes one gather over the fp16 PReLU(x)
+// copy (each token row is read exactly once) and the encoder output; the 1.4 GB speaker-split tensor never exists.
+// ----------------------------------------------------------------------------------------
+__global__ void k_fold_spk(const float* __restrict__ wfold, const float* __restrict__ Wspk,
+                           const float* __restrict__ bspk, int N, int K, float* __restrict__ w2,
+                           float* __restrict__ c2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * K * N) {
+    const int s = i / (K * N), k = (i / N) % K, n = i % N;
+    double acc = 0.0;
+    for (int m = 0; m < N; ++m) acc += (double)wfold[k * N + m] * (double)Wspk[(size_t)(s * N + m) * N + n];
+    w2[i] = (float)acc;
+  }
+  if (i < 2 * K) {
+    const int s = i / K, k = i % K;
+    double acc = 0.0;
+    for (int m = 0; m < N; ++m) acc += (double)wfold[k * N + m] * (double)bspk[s * N + m];
+    c2[i] = (float)acc;
+  }
+}
+
+int launch_fold_spk(const float* wfold, const float* Wspk, const float* bspk, int N, int K, float* w2, float* c2,
+                    cudaStream_t st) {
+  k_fold_spk<<<(2 * K * N + 127) / 128, 128, 0, st>>>(wfold, Wspk, bspk, N, K, w2, c2);
+  VATSS_LAUNCH_OK();
+  return 0;
+}
+
+template <int N, int K>
+__global__ void __launch_bounds__(128)
+k_tail_fused(const __half* __restrict__ px, const float* __restrict__ enc, const float* __restrict__ w2,
+             const float* __restrict__ c2, const float* __restrict__ wdT, const float* __restrict__ cfold, int S, int C,
+             int P, int L, int padl, int Lo, long long frames, float* __restrict__ proj) {
+  constexpr int CH = N / 32;   // channels per lane (4 or 2)
+  const int lane = threadIdx.x & 31, n0 = lane * CH;
+  float wa[2][K][CH], wd[K][CH];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      wa[0][k][i] = w2[k * N + n0 + i];
+      wa[1][k][i] = w2[(K + k) * N + n0 + i];
+      wd[k][i] = wdT[k * N + n0 + i];
+    }
+  // lane k < 2K finally holds output (spk = k / K, k % K): its constants
+  const float cbias = lane < 2 * K ? c2[lane] : 0.f;
+  const float cconst = lane < 2 * K ? cfold[lane % K] : 0.f;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = warp0; row < frames; row += nwarps) {
+    const int b = (int)(row / L);
+    const int t = (int)(row - (long long)b * L) - padl;
+    float o[CH], e[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) o[i] = 0.f;
+    if constexpr (CH == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(enc + row * N + n0);
+      e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w;
+    } else {
+      const float2 v = *reinterpret_cast<const float2*>(enc + row * N + n0);
+      e[0] = v.x; e[1] = v.y;
+    }
+    int nrows = 0;
+    if (t >= 0 && t < Lo) {
+      int s_lo = t - C + 1 + P - 1;
+      s_lo = s_lo <= 0 ? 0 : s_lo / P;
+      int s_hi = t / P;
+      if (s_hi > S - 1) s_hi = S - 1;
+      nrows = s_hi - s_lo + 1;
+      for (int s = s_lo; s <= s_hi; ++s) {
+        const __half* src = px + (((long long)b * S + s) * C + (t - P * s)) * N + n0;
+        if constexpr (CH == 4) {
+          const uint2 v = *reinterpret_cast<const uint2*>(src);
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+          const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+          o[0] += a.x; o[1] += a.y; o[2] += c.x; o[3] += c.y;
+        } else {
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(src));
+          o[0] += a.x; o[1] += a.y;
+        }
+      }
+    }
+    // per-lane partial sums of the 2K outputs, then a transposing butterfly: after the five steps lane q holds the
+    // full sum of output q (q < 2K)
+    float acc[2 * K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float pe = 0.f, p0 = 0.f, p1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        pe = fmaf(wd[k][i], e[i], pe);
+        p0 = fmaf(wa[0][k][i], o[i], p0);
+        p1 = fmaf(wa[1][k][i], o[i], p1);
+      }
+      acc[k] = p0 + pe;
+      acc[K + k] = p1 + pe;
+    }
+    float outv = 0.f;
+#pragma unroll
+    for (int q = 0; q < 2 * K; ++q) {
+      const float v = warp_sum(acc[q]);
+      if (lane == q) outv = v;
+    }
+    if (lane < 2 * K) proj[row * (2 * K) + lane] = outv + (float)nrows * cbias + cconst;
+  }
+}
+
+// whole tail after the last dual-path block for the post-conv heads; returns 1 when (N, K) has no instance
+int launch_tail_fused(const __half* px, const float* enc, const float* w2, const float* c2, const float* wdT,
+                      const float* cfold, int B, int S, int C, int P, int L, int N, int K, float* proj, cudaStream_t st) {
+  const long long frames = (long long)B * L;
+  if (frames == 0) return 0;
+  const int Lo = (S - 1) * P + C;
+  const int padl = (L - Lo) / 2;
+  const int blocks = (int)(ceil_div(frames, 4) < 148 * 16 ? ceil_div(frames, 4) : 148 * 16);
+#define VATSS_TAIL_FUSED(NN, KK)                                                                                      \
+  if (N == NN && K == KK) {                                                                                           \
+    k_tail_fused<NN, KK><<<blocks, 128, 0, st>>>(px, enc, w2, c2, wdT, cfold, S, C, P, L, padl, Lo, frames, proj);    \
+    VATSS_LAUNCH_OK();                                                                                                \
+    return 0;                                                                                                         \
+  }
+  VATSS_TAIL_FUSED(128, 7)
+  VATSS_TAIL_FUSED(64, 7)
+  VATSS_TAIL_FUSED(64, 2)
+  VATSS_TAIL_FUSED(128, 2)
+#undef VATSS_TAIL_FUSED
+  return 1;
+}
+
 // returns 1 when the (N, K) pair has no fused instance (caller falls back to the unfused sequence)
 int launch_ola_decode(const float* y, const float* enc, const float* wfold, const float* wdT, const float* cfold, int B,
                       int S, int C, int P, int L, int N, int K, float* proj, cudaStream_t st) {

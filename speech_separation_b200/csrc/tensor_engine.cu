@@ -41,6 +41,7 @@ struct Packed {
   SubPacked sub[64];
   __half *wspk, *whead, *wgate;
   float *wfold, *wdT, *cfold;   // Wd^T Whead, Wd^T, Wd^T bhead (post-conv head folded into the decoder projection)
+  float *w2, *c2;               // wfold Wspk[spk], wfold bspk[spk] (speaker split folded in as well)
 };
 
 size_t carve_packed(const vatss_model_desc* d, void* buf, Packed* out) {
@@ -65,6 +66,8 @@ size_t carve_packed(const vatss_model_desc* d, void* buf, Packed* out) {
   p.wfold = b.take<float>(fold ? (size_t)d->K * N : 0);
   p.wdT = b.take<float>(fold ? (size_t)d->K * N : 0);
   p.cfold = b.take<float>(fold ? (size_t)d->K : 0);
+  p.w2 = b.take<float>(fold ? (size_t)2 * d->K * N : 0);
+  p.c2 = b.take<float>(fold ? (size_t)2 * d->K : 0);
   if (out) *out = p;
   return b.off;
 }
@@ -186,7 +189,8 @@ int tensor_engine_pack(const vatss_model_desc* d, const float* const* params, vo
   if (d->kind == VATSS_KIND_DPTN_MASK) {
     if ((rc = to_half(params[VATSS_P_HGATE_W], p.wgate, N, N, 0, 1.f, st))) return rc;
   } else if ((rc = launch_fold_head(params[VATSS_P_HEAD_W], params[VATSS_P_HEAD_B], params[VATSS_P_DECODER_W], N, d->K,
-                                    p.wfold, p.wdT, p.cfold, st))) {
+                                    p.wfold, p.wdT, p.cfold, st)) ||
+             (rc = launch_fold_spk(p.wfold, params[VATSS_P_SPK_W], params[VATSS_P_SPK_B], N, d->K, p.w2, p.c2, st))) {
     return rc;
   }
   return 0;
@@ -270,10 +274,20 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
     set_error("tensor engine needs at least one dual-path block");
     return -1;
   }
+  float* preds[2] = {s1_pred, s2_pred};
+  if (d->kind != VATSS_KIND_DPTN_MASK) {
+    // speaker split + overlap-add + post-conv + skip + decoder projection: one gather over PReLU(x) (fp16) and enc
+    rc = launch_tail_fused(w.xa16, w.enc32, p.w2, p.c2, p.wdT, p.cfold, B, S, C, d->P, L, N, d->K, w.proj, st);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      for (int j = 0; j < 2; ++j)
+        if ((rc = launch_decoder_ola(w.proj + j * d->K, 2 * d->K, B, L, d->K, T, preds[j], st))) return rc;
+      return 0;
+    }
+  }
   if ((rc = launch_tc_gemm(TC_EPI_F32, w.xa16, N, p.wspk, params[VATSS_P_SPK_B], nullptr, 0, nullptr, nullptr, w.y32,
                            2 * N, nullptr, 0, 0, nullptr, tok, 2 * N, N, st)))
     return rc;
-  float* preds[2] = {s1_pred, s2_pred};
   if (d->kind != VATSS_KIND_DPTN_MASK) {
     // overlap-add + post-conv + skip + decoder projection in one pass over the speaker-split output
     rc = launch_ola_decode(w.y32, w.enc32, p.wfold, p.wdT, p.cfold, B, S, C, d->P, L, N, d->K, w.proj, st);

@@ -176,7 +176,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--seconds", type=float, default=4.0)
-    ap.add_argument("--engine", default="auto", choices=["auto", "generic", "tensor"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "generic", "tensor", "tensor-f16res"])
     ap.add_argument("--model", default="dptn_av", choices=["dptn_av"] + sorted(OTHER_MODELS),
                     help="dptn_av = the headline config; the others are the remaining BASELINE.json models")
     ap.add_argument("--no-cpu-baseline", action="store_true")

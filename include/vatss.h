@@ -39,6 +39,9 @@ extern "C" {
 #define VATSS_ENGINE_AUTO 0
 #define VATSS_ENGINE_GENERIC 1
 #define VATSS_ENGINE_TENSOR 2
+/* TENSOR engine with the DPTN block residual stream kept in fp16 only (faster, ~7e-4 instead of ~5.7e-4 rel-L2;
+   ignored by the masking and DPRNN models, whose heads / un-normalised stream do not tolerate it) */
+#define VATSS_ENGINE_TENSOR_F16RES 3
 
 typedef struct vatss_model_desc {
   int32_t kind;        /* VATSS_KIND_*                                   */

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvatss_b200.so")
 
 KIND = {"dptn_av": 0, "dptn_wav": 1, "dptn_mask": 2, "dprnn": 3}
-ENGINE = {"auto": 0, "generic": 1, "tensor": 2}
+ENGINE = {"auto": 0, "generic": 1, "tensor": 2, "tensor-f16res": 3}
 
 P_GLOBAL = [
     "encoder.weight", "decoder.weight", "visual_compression.weight", "visual_compression.bias", "gate",

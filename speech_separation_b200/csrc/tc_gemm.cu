@@ -95,6 +95,8 @@ struct TcGemmArgs {
   const float* bias;
   const float* res;
   long long ldr;
+  const __half* res16;   // fp16 residual (RES16 instances): the same tensor the next operand is read from
+  long long ldr16;
   const float* ln_w;
   const float* ln_b;
   float* out32;
@@ -115,14 +117,15 @@ constexpr int tcg_epilogue_warps(int fixed_bytes) { return fixed_bytes + 8 * 32 
 
 // WSPLIT: W is stored as [half(W) | half(W - half(W))] (hi/lo split, 2 x KDIM columns) and both halves are
 // contracted with the same A tile - used where an fp16-rounded weight misses the tolerance (DPRNN fc).
-template <int NOUT, int KDIM, bool RES_TMA = false, bool WSPLIT = false>
+template <int NOUT, int KDIM, bool RES_TMA = false, bool WSPLIT = false, bool RES16 = false>
 struct TcGemmSmem {
   static constexpr int KB = KDIM / 64;
   static constexpr int KBW = WSPLIT ? 2 * KB : KB;
   static constexpr int W_BYTES = KBW * NOUT * 128;
   static constexpr int A_STAGE_BYTES = KB * 128 * 128;
   // residual tile [128 rows x NOUT fp32] as NOUT/32 column blocks of 128-byte rows (SWIZZLE_128B), TMA-prefetched
-  static constexpr int RES_BYTES = RES_TMA ? 128 * NOUT * 4 : 0;
+  // (RES16: NOUT/64 column blocks of 64 fp16 columns instead)
+  static constexpr int RES_BYTES = RES_TMA ? 128 * NOUT * (RES16 ? 2 : 4) : 0;
   static constexpr int A_STAGES = (W_BYTES + 2 * A_STAGE_BYTES + RES_BYTES + 24 * 1024 <= 227 * 1024) ? 2 : 1;
   static constexpr int OFF_W = 0;
   static constexpr int OFF_A = OFF_W + W_BYTES;
@@ -204,13 +207,14 @@ __device__ __forceinline__ void staged_store_f16(__half* __restrict__ g, long lo
   __syncwarp();
 }
 
-template <int NOUT, int KDIM, int EPI, bool WSPLIT>
-__global__ void __launch_bounds__((TcGemmSmem<NOUT, KDIM, (EPI == TC_EPI_LN || EPI == TC_EPI_LN_POST), WSPLIT>::THREADS), 1)
+template <int NOUT, int KDIM, int EPI, bool WSPLIT, bool RES16>
+__global__ void __launch_bounds__((TcGemmSmem<NOUT, KDIM, (EPI == TC_EPI_LN || EPI == TC_EPI_LN_POST), WSPLIT, RES16>::THREADS), 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapW,
           const __grid_constant__ CUtensorMap tmapR, TcGemmArgs p) {
   constexpr bool RES_TMA = (EPI == TC_EPI_LN || EPI == TC_EPI_LN_POST);   // residual tile prefetched by TMA
-  using L = TcGemmSmem<NOUT, KDIM, RES_TMA, WSPLIT>;
+  using L = TcGemmSmem<NOUT, KDIM, RES_TMA, WSPLIT, RES16>;
   static_assert(NOUT % 16 == 0 && NOUT <= 512 && KDIM % 64 == 0, "shape");
+  static_assert(!RES16 || (RES_TMA && NOUT % 64 == 0), "fp16 residual: LayerNorm epilogues, 64-column blocks");
   static_assert(EPI != TC_EPI_LN && EPI != TC_EPI_LN_POST || NOUT <= 128, "LayerNorm epilogue needs the row in regs");
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -273,7 +277,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
         if constexpr (RES_TMA) {
           mbar_wait(bar_rempty, (i & 1) ^ 1);
           mbar_expect_tx(bar_rfull, L::RES_BYTES);
-          for (int cbk = 0; cbk < NOUT / 32; ++cbk) tma_load_2d(sR + cbk * 16384, &tmapR, bar_rfull, cbk * 32, tile * 128);
+          constexpr int RCOLS = RES16 ? 64 : 32;   // columns per 128-byte-row block
+          for (int cbk = 0; cbk < NOUT / RCOLS; ++cbk)
+            tma_load_2d(sR + cbk * 16384, &tmapR, bar_rfull, cbk * RCOLS, tile * 128);
         }
       }
     }
@@ -371,6 +377,30 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
         float* xch = reinterpret_cast<float*>(gen + L::OFF_XCH);
         float v[NC];
         const int rr = q * 32 + lane;
+        // v[c0 .. c0+32) += residual[row rr, cbase + c0 ...] from the TMA-prefetched tile
+        auto add_residual = [&](int c0) {
+          if constexpr (!RES16) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 x = *reinterpret_cast<const float4*>(gen + L::OFF_RES + ((cbase + c0) / 32) * 16384 +
+                                                                sw128_offset((uint32_t)rr, (uint32_t)c));
+              v[c0 + 4 * c] += x.x; v[c0 + 4 * c + 1] += x.y; v[c0 + 4 * c + 2] += x.z; v[c0 + 4 * c + 3] += x.w;
+            }
+          } else {
+            const int col = cbase + c0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 x = *reinterpret_cast<const uint4*>(gen + L::OFF_RES + (col / 64) * 16384 +
+                                                              sw128_offset((uint32_t)rr, (uint32_t)((col % 64) / 8 + c)));
+              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&x.x));
+              const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&x.y));
+              const float2 cc = __half22float2(*reinterpret_cast<const __half2*>(&x.z));
+              const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&x.w));
+              v[c0 + 8 * c] += a.x; v[c0 + 8 * c + 1] += a.y; v[c0 + 8 * c + 2] += b.x; v[c0 + 8 * c + 3] += b.y;
+              v[c0 + 8 * c + 4] += cc.x; v[c0 + 8 * c + 5] += cc.y; v[c0 + 8 * c + 6] += d.x; v[c0 + 8 * c + 7] += d.y;
+            }
+          }
+        };
         mbar_wait(bar_rfull, i & 1);
         mbar_wait(bar_accfull + 8 * as, aph);
         tc_fence_after();
@@ -381,14 +411,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[c0 + j] = __uint_as_float(r[j]) + sBias[cbase + c0 + j];
-          if constexpr (EPI == TC_EPI_LN) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 x = *reinterpret_cast<const float4*>(gen + L::OFF_RES + ((cbase + c0) / 32) * 16384 +
-                                                                sw128_offset((uint32_t)rr, (uint32_t)c));
-              v[c0 + 4 * c] += x.x; v[c0 + 4 * c + 1] += x.y; v[c0 + 4 * c + 2] += x.z; v[c0 + 4 * c + 3] += x.w;
-            }
-          }
+          if constexpr (EPI == TC_EPI_LN) add_residual(c0);
         }
         float sum = 0.f;
 #pragma unroll
@@ -415,15 +438,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
         for (int j = 0; j < NC; ++j) v[j] = (v[j] - mean) * rstd * sLw[cbase + j] + sLb[cbase + j];
 #pragma unroll
         for (int c0 = 0; c0 < NC; c0 += 32) {
-          if constexpr (EPI == TC_EPI_LN_POST) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 x = *reinterpret_cast<const float4*>(gen + L::OFF_RES + ((cbase + c0) / 32) * 16384 +
-                                                                sw128_offset((uint32_t)rr, (uint32_t)c));
-              v[c0 + 4 * c] += x.x; v[c0 + 4 * c + 1] += x.y; v[c0 + 4 * c + 2] += x.z; v[c0 + 4 * c + 3] += x.w;
-            }
-          }
-          staged_store_f32(p.out32 + row0 * p.ldo32 + cbase + c0, p.ldo32, rows_valid, stage, lane, v + c0);
+          if constexpr (EPI == TC_EPI_LN_POST) add_residual(c0);
+          if (p.out32) staged_store_f32(p.out32 + row0 * p.ldo32 + cbase + c0, p.ldo32, rows_valid, stage, lane, v + c0);
           if (p.out16) {
             uint32_t pk[16];
 #pragma unroll
@@ -463,14 +479,19 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
   if (warp == 1) tmem_dealloc<1>(tmem, L::TMEM_COLS);
 }
 
-template <int NOUT, int KDIM, int EPI, bool WSPLIT = false>
+template <int NOUT, int KDIM, int EPI, bool WSPLIT = false, bool RES16 = false>
 static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const TcGemmArgs& args, cudaStream_t st) {
   constexpr bool RES_TMA = (EPI == TC_EPI_LN || EPI == TC_EPI_LN_POST);
-  using L = TcGemmSmem<NOUT, KDIM, RES_TMA, WSPLIT>;
+  using L = TcGemmSmem<NOUT, KDIM, RES_TMA, WSPLIT, RES16>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
   CUtensorMap tmA, tmW, tmR;
   tmR = CUtensorMap();
-  if (RES_TMA) {
+  if (RES_TMA && RES16) {
+    const uint64_t dims[2] = {(uint64_t)NOUT, (uint64_t)args.M};
+    const uint64_t str[1] = {(uint64_t)args.ldr16 * 2};
+    const uint32_t box[2] = {64, 128};
+    if (make_tmap_f16(&tmR, args.res16, 2, dims, str, box)) return -1;
+  } else if (RES_TMA) {
     const uint64_t dims[2] = {(uint64_t)NOUT, (uint64_t)args.M};
     const uint64_t str[1] = {(uint64_t)args.ldr * 4};
     const uint32_t box[2] = {32, 128};
@@ -489,7 +510,7 @@ static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const
     const uint32_t box[2] = {64, 64};
     if (make_tmap_f16(&tmW, W, 2, dims, str, box)) return -1;
   }
-  auto kern = k_tc_gemm<NOUT, KDIM, EPI, WSPLIT>;
+  auto kern = k_tc_gemm<NOUT, KDIM, EPI, WSPLIT, RES16>;
   static bool configured = false;
   if (!configured) {
     VATSS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -504,19 +525,34 @@ static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const
 int launch_tc_gemm(int epi, const __half* A, long long lda, const __half* W, const float* bias, const float* res,
                    long long ldr, const float* ln_w, const float* ln_b, float* out32, long long ldo32, __half* out16,
                    long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int KDIM,
-                   cudaStream_t st, __half* out16lo, int wsplit) {
+                   cudaStream_t st, __half* out16lo, int wsplit, const __half* res16, long long ldr16) {
   if (M == 0) return 0;
   VATSS_CHECK_ARG(((uintptr_t)A & 15) == 0 && (lda * 2) % 16 == 0, "tc_gemm: A must be 16-byte aligned with 16-byte row pitch");
   TcGemmArgs a;
   a.M = M;
   a.num_tiles = (int)((M + 127) / 128);
-  a.bias = bias; a.res = res; a.ldr = ldr; a.ln_w = ln_w; a.ln_b = ln_b;
+  a.bias = bias; a.res = res; a.ldr = ldr; a.res16 = res16; a.ldr16 = ldr16; a.ln_w = ln_w; a.ln_b = ln_b;
   a.out32 = out32; a.ldo32 = ldo32; a.out16 = out16; a.ldo16 = ldo16; a.act16 = act16; a.prelu_a = prelu_a;
   a.out16lo = out16lo;
   if (epi == TC_EPI_F16) VATSS_CHECK_ARG(out16 != nullptr, "tc_gemm: fp16 output missing");
   if (epi == TC_EPI_F32) VATSS_CHECK_ARG(out32 != nullptr, "tc_gemm: fp32 output missing");
   if (epi == TC_EPI_LN || epi == TC_EPI_LN_POST)
-    VATSS_CHECK_ARG(out32 && res && ln_w && ln_b, "tc_gemm: LayerNorm epilogue needs out32/res/ln_w/ln_b");
+    VATSS_CHECK_ARG((out32 || out16) && (res || res16) && ln_w && ln_b,
+                    "tc_gemm: LayerNorm epilogue needs an output, a residual and ln_w/ln_b");
+  if (res16) {   // fp16 residual stream (DPTN sub-blocks)
+    VATSS_CHECK_ARG(epi == TC_EPI_LN && !wsplit && ((uintptr_t)res16 & 15) == 0 && (ldr16 * 2) % 16 == 0,
+                    "tc_gemm: fp16 residual needs the LayerNorm epilogue and 16-byte aligned rows");
+#define TCG_CASE16(N_, K_) \
+  if (NOUT == N_ && KDIM == K_) return tc_gemm_launch<N_, K_, TC_EPI_LN, false, true>(A, lda, W, a, st);
+    TCG_CASE16(128, 128)
+    TCG_CASE16(128, 256)
+    TCG_CASE16(64, 64)
+    TCG_CASE16(64, 256)
+    TCG_CASE16(64, 128)
+#undef TCG_CASE16
+    set_error("tc_gemm: no fp16-residual instantiation for NOUT=%d K=%d", NOUT, KDIM);
+    return -1;
+  }
   if (wsplit) {   // W = [hi | lo], 2 x KDIM columns
     if (NOUT == 64 && KDIM == 256 && epi == TC_EPI_LN_POST) return tc_gemm_launch<64, 256, TC_EPI_LN_POST, true>(A, lda, W, a, st);
     if (NOUT == 64 && KDIM == 128 && epi == TC_EPI_LN_POST) return tc_gemm_launch<64, 128, TC_EPI_LN_POST, true>(A, lda, W, a, st);

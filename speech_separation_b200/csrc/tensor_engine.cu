@@ -115,8 +115,11 @@ size_t carve_work(const vatss_model_desc* d, int B, int Tv, int L, int S, void* 
   Work w;
   w.enc32 = b.take<float>(fr * N);
   w.vis = b.take<float>(d->kind == VATSS_KIND_DPTN_AV ? (size_t)B * Tv * N : 0);
-  w.xa32 = b.take<float>(tok * N);
-  w.xb32 = b.take<float>(tok * N);
+  // fp32 residual stream: DPRNN keeps both ping-pong copies; the DPTN sub-blocks take the LayerNorm-1 output back as
+  // fp16 (no xb32), and the fp16-stream variant drops the fp32 copy altogether
+  const bool f16res = d->engine == VATSS_ENGINE_TENSOR_F16RES && !dprnn && !mask;
+  w.xa32 = b.take<float>(f16res ? 0 : tok * N);
+  w.xb32 = b.take<float>(dprnn || mask ? tok * N : 0);   // (the masking head keeps y in fp32, see forward)
   w.xa16 = b.take<__half>(tok * N);
   w.xb16 = b.take<__half>(tok * N);
   w.xa16lo = b.take<__half>(dprnn ? tok * N : 0);   // lo halves of the hi/lo split LSTM input (DPRNN)
@@ -206,6 +209,13 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
   const int N = d->N, H = d->H, C = d->C;
   const long long tok = (long long)B * S * C, fr = (long long)B * L;
   const bool dprnn = d->kind == VATSS_KIND_DPRNN, av = d->kind == VATSS_KIND_DPTN_AV;
+  // DPTN residual stream.  Default: fp32 between sub-blocks, the LayerNorm-1 output y only as fp16 (it is the LSTM
+  // operand anyway and re-enters as the FFN residual).  F16RES: the block residual is fp16 as well (1e-3 budget:
+  // 3.8e-4 -> 5.7e-4 -> 7.0e-4 rel-L2 for fp32 / default / F16RES on the production goldens).
+  const bool f16res = d->engine == VATSS_ENGINE_TENSOR_F16RES && !dprnn && d->kind != VATSS_KIND_DPTN_MASK;
+  // the tanh x sigmoid masking head is the most sensitive consumer (7.2e-4 with the fp16 y, 9.1e-4 with the fp16
+  // stream, 4.5e-4 without): it always keeps the fp32 residuals
+  const bool y16res = d->kind != VATSS_KIND_DPTN_MASK;
   int rc;
   {
     StageScope sc(ST_FRONTEND, st);
@@ -217,7 +227,7 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
     }
     if ((rc = launch_encoder(mix, params[VATSS_P_ENCODER_W], av ? w.vis : nullptr, params[VATSS_P_GATE],
                              params[VATSS_P_VLN_W], params[VATSS_P_VLN_B], B, T, Tv, N, d->K, L, S, C, d->P, w.enc32,
-                             w.xa32, w.xa16, st, dprnn ? w.xa16lo : nullptr)))
+                             f16res ? nullptr : w.xa32, w.xa16, st, dprnn ? w.xa16lo : nullptr)))
       return rc;
   }
   for (int blk = 0; blk < d->num_blocks; ++blk)
@@ -253,8 +263,9 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
         }
         {
           StageScope sc(ST_OUTPROJ_LN, st);
-          if ((rc = launch_tc_gemm(TC_EPI_LN, w.att16, N, s.wout, sp(VATSS_S_OUTPROJ_B), w.xa32, N, sp(VATSS_S_LN1_W),
-                                   sp(VATSS_S_LN1_B), w.xb32, N, w.xb16, N, 0, nullptr, tok, N, N, st)))
+          if ((rc = launch_tc_gemm(TC_EPI_LN, w.att16, N, s.wout, sp(VATSS_S_OUTPROJ_B), f16res ? nullptr : w.xa32, N,
+                                   sp(VATSS_S_LN1_W), sp(VATSS_S_LN1_B), y16res ? nullptr : w.xb32, N, w.xb16, N, 0, nullptr,
+                                   tok, N, N, st, nullptr, 0, f16res ? w.xa16 : nullptr, N)))
             return rc;
         }
         {
@@ -262,9 +273,10 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
           if ((rc = launch_tc_lstm(w.xb16, nullptr, s.wlstm, s.blstm, w.rnn16, path, B, S, C, N, ndir, 1, st))) return rc;
         }
         StageScope sc(ST_FFN_LN, st);
-        if ((rc = launch_tc_gemm(TC_EPI_LN, w.rnn16, ndir * H, s.wffn, sp(VATSS_S_FFN_B), w.xb32, N, sp(VATSS_S_LN2_W),
-                                 sp(VATSS_S_LN2_B), w.xa32, N, w.xa16, N, last ? 2 : 0, params[VATSS_P_PRELU], tok, N,
-                                 ndir * H, st)))
+        if ((rc = launch_tc_gemm(TC_EPI_LN, w.rnn16, ndir * H, s.wffn, sp(VATSS_S_FFN_B), y16res ? nullptr : w.xb32, N,
+                                 sp(VATSS_S_LN2_W), sp(VATSS_S_LN2_B), (f16res || last) ? nullptr : w.xa32, N, w.xa16, N,
+                                 last ? 2 : 0, params[VATSS_P_PRELU], tok, N, ndir * H, st, nullptr, 0,
+                                 y16res ? w.xb16 : nullptr, N)))
           return rc;
       }
     }

@@ -145,6 +145,20 @@ def prod_net(V, kind, engine="auto"):
     return cls_of(V, kind)(**PROD[kind]).eval().to(dev()).set_engine(engine)
 
 
+@pytest.mark.parametrize("case", [c for c in PROD_CASES if c[0] != "dprnn"], ids=lambda c: f"{c[0]}-B{c[1]}-T{c[2]}")
+def test_fp16_residual_stream_engine_within_tolerance(V, golden_dir, case):
+    """engine="tensor-f16res": the DPTN block residual stream is kept in fp16 only."""
+    kind, B, T = case
+    z = np.load(os.path.join(golden_dir, f"prod_{kind}_B{B}_T{T}.npz"))
+    net = prod_net(V, kind, "tensor-f16res")
+    Tv = int(z["Tv"]) if int(z["Tv"]) > 0 else None
+    mix, s1, s2, e1, e2 = make_inputs(B, T, Tv=Tv, E=PROD[kind].get("video_emb_size"), seed=int(z["input_seed"]))
+    s1p, s2p = run(net, kind, mix, e1, e2)
+    r1, r2 = rel_l2(s1p.cpu().numpy(), z["s1_pred"]), rel_l2(s2p.cpu().numpy(), z["s2_pred"])
+    print(f"{kind} B{B} T{T} engine=tensor-f16res: rel-L2 {r1:.3e} {r2:.3e}")
+    assert r1 <= WAVE_TOL and r2 <= WAVE_TOL
+
+
 @pytest.mark.parametrize("engine", ["auto", "generic"])
 @pytest.mark.parametrize("case", PROD_CASES, ids=lambda c: f"{c[0]}-B{c[1]}-T{c[2]}")
 def test_production_configs_match_reference_golden(V, golden_dir, case, engine):

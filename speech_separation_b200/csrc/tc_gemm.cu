@@ -413,6 +413,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
           for (int j = 0; j < 32; ++j) v[c0 + j] = __uint_as_float(r[j]) + sBias[cbase + c0 + j];
           if constexpr (EPI == TC_EPI_LN) add_residual(c0);
         }
+        // accumulator and (pre-LayerNorm) residual are in registers: hand both buffers back now, so the next tile's
+        // MMAs and residual prefetch run under this tile's LayerNorm arithmetic and stores
+        tc_fence_before();
+        mbar_arrive(bar_accempty + 8 * as);
+        if constexpr (EPI == TC_EPI_LN) mbar_arrive(bar_rempty);
         float sum = 0.f;
 #pragma unroll
         for (int j = 0; j < NC; ++j) sum += v[j];
@@ -467,8 +472,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
           }
         }
       }
-      if constexpr (RES_TMA) mbar_arrive(bar_rempty);
-      if constexpr (L::NCH == 1) {
+      if constexpr (EPI == TC_EPI_LN_POST) mbar_arrive(bar_rempty);   // (post-LayerNorm residual: read during the stores)
+      if constexpr (L::NCH == 1 && !RES_TMA) {
         tc_fence_before();
         mbar_arrive(bar_accempty + 8 * as);
       }

@@ -76,6 +76,29 @@ def stage_flops(B, T, model="dptn_av"):
     return fl
 
 
+def stage_bytes(B, T, model="dptn_av", f16res=False):
+    """Algorithmic HBM bytes per forward by stage (fp16 activations, fp32 block residual stream)."""
+    if model == "dprnn":
+        return {}
+    L, S = geometry(T)
+    tok = B * S * 150
+    N, H = (128, 128) if model == "dptn_av" else (64, 128)
+    x32 = 0 if f16res else 4 * N   # fp32 copy of the block residual (read by the out-projection, written by the FFN)
+    per_sub = {
+        "qkv": 2 * N + 2 * 3 * N,                                  # x16 in, qkv16 out
+        "attention": 2 * 3 * N + 2 * N,                            # qkv16 in, att16 out
+        "outproj_ln1": 2 * N + (x32 if x32 else 2 * N) + 2 * N,    # att16 + residual x in, y16 out
+        "lstm_recurrent": 2 * 2 * N + 2 * 2 * H,                   # y16 read by both directions, ReLU(h) fp16 out
+        "ffn_ln2": 2 * 2 * H + 2 * N + x32 + 2 * N,                # rnn16 + residual y16 in, x32 + x16 out
+    }
+    return {k: 12 * tok * v for k, v in per_sub.items()}
+
+
+# DRAM traffic per launch measured by ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum) on the headline
+# workload (profiles/r01_ncu_full_final_summary.json): equals the algorithmic bytes, i.e. no wasted re-reads
+NCU_TRAFFIC_BYTES = {"attention": 1.368e9, "lstm_recurrent": 1.322e9}
+
+
 def make_batch(B, T, seed):
     import torch
 
@@ -353,16 +376,40 @@ def main():
     except OSError:
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"
+    peak_bw = float(peaks.get("hbm_gbs", 6500.0))
     fl = stage_flops(B, T, args.model)
-    compute = {k: v for k, v in stage_ms.items() if k in fl and fl[k] > 0 and k not in ("frontend", "tail")}
-    dom = max(compute, key=compute.get)
-    dom_launches = max(stage_launches.get(dom, 1), 1)
-    achieved = fl[dom] / (stage_ms[dom] / 1e3) / 1e12
-    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
-                "launches_per_step": dom_launches, "ms_per_step": stage_ms[dom],
+    by = stage_bytes(B, T, args.model, args.engine == "tensor-f16res")
+    if stage_ms.get("lstm_input", 0.0) == 0.0:   # tensor engine: input and recurrent contractions are one kernel
+        fl["lstm_recurrent"] = fl.get("lstm_recurrent", 0) + fl.pop("lstm_input", 0)
+        fl["lstm_input"] = 0
+    # per stage: achieved rate against both roofs (algorithmic work / CUDA-event time of the stage's launches);
+    # the binding roof of a stage is the one it is closer to
+    stages = {}
+    for k, ms in stage_ms.items():
+        if ms <= 0 or k in ("frontend", "tail", "sisnr", "lstm_input"):
+            continue
+        tf = fl.get(k, 0) / (ms / 1e3) / 1e12
+        gb = by.get(k, 0) / (ms / 1e3) / 1e9
+        stages[k] = {"ms": round(ms, 3), "launches": int(stage_launches.get(k, 0)), "tflops": round(tf, 1),
+                     "tensor_frac": round(tf / peak_tf, 3), "gbs": round(gb, 1), "hbm_frac": round(gb / peak_bw, 3)}
+    dom = max(stages, key=lambda k: stages[k]["ms"])
+    d = stages[dom]
+    dom_launches = max(d["launches"], 1)
+    hbm_bound = d["hbm_frac"] >= d["tensor_frac"]
+    headline = args.model == "dptn_av" and B == 32 and abs(args.seconds - 4.0) < 1e-9 and args.engine in ("auto", "tensor")
+    roofline = {"bound": "hbm" if hbm_bound else "tensor", "kernel": dom,
+                "achieved": d["gbs"] if hbm_bound else d["tflops"], "peak": peak_bw if hbm_bound else peak_tf,
+                "unit": "GB/s" if hbm_bound else "TFLOP/s", "frac": d["hbm_frac"] if hbm_bound else d["tensor_frac"],
+                "traffic": NCU_TRAFFIC_BYTES.get(dom) if headline else None,
+                "algorithmic_bytes_per_launch": by.get(dom, 0) / dom_launches,
+                "algorithmic_flops_per_launch": fl.get(dom, 0) / dom_launches,
+                "peak_source": ("MEASURED_PEAKS.json hbm_gbs / bf16_tflops_sustained" if peaks
+                                else "fallback 6.5 TB/s / 1.4 PFLOP/s sustained"),
+                "launches_per_step": dom_launches, "ms_per_step": d["ms"],
+                "note": "attention and the LSTM are bound by MUFU / synchronisation latency rather than by either roof "
+                        "(DESIGN.md 3.2-3.4); the GEMM stages are HBM-bound",
                 "whole_forward_frac": sum(fl.values()) / (sum(stage_ms[k] for k in fl) / 1e3) / 1e12 / peak_tf,
+                "stages": stages,
                 "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()}}
 
     line = {"metric": METRIC.replace("dptn_av", args.model), "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -517,6 +517,8 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
               fence_proxy_async();
             } else {
               uint32_t pk[16];
+              // (probe the P buffer's barrier now: its ~100-cycle round trip overlaps the exponentials)
+              const bool p_free = mbar_try_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
               if (warp_live && nv > 0) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(t_base + slot * ATT_NB + cc, v);
@@ -542,7 +544,7 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
                 for (int i = 0; i < 16; ++i) pk[i] = 0u;
               }
               // the P buffer of two blocks ago must have been consumed by its P V MMAs
-              mbar_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
+              if (!p_free) mbar_wait(B.pfree + 8 * (w * 2 + pb), ((pjob >> 1) & 1) ^ 1);
               if (warp_live) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {

@@ -151,6 +151,17 @@ ATT_CASES = [
     (0, 1, 2, 250, 128, 4),      # longer chunk: two kv blocks of 128
     (1, 1, 710, 3, 128, 4),      # inter 10 s: K / V streamed through the shared-memory ring
     (1, 2, 400, 2, 64, 4),
+    # ragged last query tile (<= 32 rows: replicated-quadrant / 8-column-strip mode) and its boundaries
+    (0, 3, 2, 129, 128, 4),      # 1 ragged row, 3 kv blocks (resident)
+    (0, 2, 2, 160, 128, 4),      # 32 ragged rows
+    (0, 2, 2, 161, 128, 4),      # 33 rows in the last tile: regular mode
+    (0, 5, 3, 20, 128, 4),       # the only tile is ragged
+    (0, 4, 2, 33, 128, 4),
+    (0, 2, 2, 128, 128, 4),      # exactly one full tile
+    (0, 2, 2, 192, 128, 4),      # 3 full kv blocks, last query tile 64 rows
+    (0, 2, 1, 193, 128, 4),      # 4 kv blocks (two-pass), last kv block 1 row
+    (1, 2, 257, 3, 128, 4),      # 3 query tiles, last with 1 row; 5 kv blocks
+    (1, 3, 150, 5, 64, 4),       # head dim 16 with a ragged tile
 ]
 
 

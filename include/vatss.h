@@ -174,6 +174,14 @@ int vatss_tc_gemm(int epi, const void* A16, long long lda, const void* W16, cons
                   long long ldr, const float* ln_w, const float* ln_b, float* out32, long long ldo32, void* out16,
                   long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int K, void* stream);
 
+/* vatss_tc_gemm_ln16: the LayerNorm epilogue (epi 2) with the residual given as fp16 (res16, row pitch ldr16) and
+ * an optional fp32 output (out32 may be NULL): out = LN(A W^T + bias + res16), out16 = act16(out) - the form the
+ * DPTN sub-blocks use for `ln2(ffn(r) + a)` and, with engine TENSOR_F16RES, `ln1(mha(x) + x)` (src/model/dptn.py:47,51). */
+int vatss_tc_gemm_ln16(const void* A16, long long lda, const void* W16, const float* bias, const void* res16,
+                       long long ldr16, const float* ln_w, const float* ln_b, float* out32, long long ldo32,
+                       void* out16, long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int K,
+                       void* stream);
+
 /* vatss_tc_lstm: nn.LSTM(N->128) recurrence (src/model/dptn.py:23-29,49) on a CTA pair, input and recurrent
  * contractions fused per time step.  x16 (B,S,C,N) fp16 token-major; params: fp32 nn.LSTM tensors of the
  * forward (and reverse, if ndir=2) direction; out16 (B*S*C, ndir*128) fp16, relu(h) if act=1.

@@ -387,6 +387,16 @@ int vatss_tc_gemm(int epi, const void* A16, long long lda, const void* W16, cons
                         (__half*)out16, ldo16, act16, prelu_a, M, NOUT, K, (cudaStream_t)stream);
 }
 
+int vatss_tc_gemm_ln16(const void* A16, long long lda, const void* W16, const float* bias, const void* res16,
+                       long long ldr16, const float* ln_w, const float* ln_b, float* out32, long long ldo32,
+                       void* out16, long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int K,
+                       void* stream) {
+  VATSS_CHECK_ARG(A16 && W16 && res16 && M >= 0, "tc_gemm_ln16: NULL operand");
+  return launch_tc_gemm(TC_EPI_LN, (const __half*)A16, lda, (const __half*)W16, bias, nullptr, 0, ln_w, ln_b, out32,
+                        ldo32, (__half*)out16, ldo16, act16, prelu_a, M, NOUT, K, (cudaStream_t)stream, nullptr, 0,
+                        (const __half*)res16, ldr16);
+}
+
 int vatss_tc_lstm(const void* x16, const void* x16lo, const float* const* lp, void* out16, int mode, int B, int S, int C,
                   int N, int ndir, int act, void* wpack, float* bias_pack, void* stream) {
   VATSS_CHECK_ARG(x16 && lp && out16 && wpack && bias_pack, "tc_lstm: NULL pointer");

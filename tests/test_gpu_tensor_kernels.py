@@ -73,6 +73,35 @@ def test_tc_gemm_matches_torch(lib, epi, NOUT, K, M):
         assert (out32 - want).norm() / want.norm() < 1e-5
 
 
+@pytest.mark.parametrize("NOUT,K,M,with32", [(128, 128, 4321, True), (128, 256, 2000, True), (128, 256, 999, False),
+                                               (64, 64, 1500, True), (64, 256, 640, False), (128, 128, 128, False)])
+def test_tc_gemm_layernorm_with_fp16_residual(lib, NOUT, K, M, with32):
+    """LayerNorm epilogue whose residual tile is the fp16 tensor (DPTN sub-blocks); fp32 output optional."""
+    from speech_separation_b200 import _lib
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(M + NOUT + K)
+    A = torch.randn(M, K, generator=g).to(dev).half()
+    W = (torch.randn(NOUT, K, generator=g) / K ** 0.5).to(dev).half()
+    bias = torch.randn(NOUT, generator=g).to(dev)
+    res16 = torch.randn(M, NOUT, generator=g).to(dev).half()
+    lw = (1 + 0.2 * torch.randn(NOUT, generator=g)).to(dev)
+    lb = (0.1 * torch.randn(NOUT, generator=g)).to(dev)
+    out32 = torch.full((M, NOUT), float("nan"), device=dev)
+    out16 = torch.full((M, NOUT), float("nan"), device=dev, dtype=torch.float16)
+    rc = lib.vatss_tc_gemm_ln16(_p(A), K, _p(W), _p(bias), _p(res16), NOUT, _p(lw), _p(lb),
+                                _p(out32) if with32 else None, NOUT, _p(out16), NOUT, 1, None, M, NOUT, K, None)
+    _lib.check(rc, "vatss_tc_gemm_ln16")
+    torch.cuda.synchronize()
+    want = ln(A.float() @ W.float().t() + bias + res16.float(), lw, lb)
+    if with32:
+        assert (out32 - want).norm() / want.norm() < 1e-5
+    else:
+        assert torch.isnan(out32).all()          # untouched
+    want16 = torch.relu(want)
+    assert (out16.float() - want16).norm() / want16.norm() < 1e-3
+
+
 def test_tc_gemm_strided_operand(lib):
     """A taken as a column slice of a wider matrix (the per-speaker halves of the overlap-add output)."""
     from speech_separation_b200 import _lib

@@ -4,6 +4,7 @@ Public surface mirrors the reference's `src.model`, `src.loss` and `src.metrics`
 the DPTN-AV separation forward pass and its PIT SI-SNR loss / metrics.  All compute happens in
 hand-written CUDA kernels inside libvatss_b200.so (C ABI in include/vatss.h).
 """
+from .data import SSDataset, collate_fn, make_dataloader
 from .inference import Inferencer, MetricTracker
 from .loss import SiSNRLoss, SiSNRWavLoss, pit_sisnr_all
 from .metrics import SISNRiMetric, SISNRMetric
@@ -11,5 +12,5 @@ from .model import DPRNNEncDec, DPTNAVWavEncDec, DPTNEncDec, DPTNWavEncDec, Over
 
 __all__ = [
     "DPTNAVWavEncDec", "DPTNWavEncDec", "DPTNEncDec", "DPRNNEncDec", "SplitToFolds", "OverlapAdd",
-    "SiSNRLoss", "SiSNRWavLoss", "SISNRMetric", "SISNRiMetric", "pit_sisnr_all", "Inferencer", "MetricTracker",
+    "SiSNRLoss", "SiSNRWavLoss", "SISNRMetric", "SISNRiMetric", "pit_sisnr_all", "Inferencer", "MetricTracker", "SSDataset", "collate_fn", "make_dataloader",
 ]

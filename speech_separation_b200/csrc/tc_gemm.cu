@@ -190,19 +190,23 @@ __device__ __forceinline__ void staged_store_f32(float* __restrict__ g, long lon
   }
   __syncwarp();
 }
-// g16[row lane][0..31] = half(pk) where pk[16] holds the row's 32 values as packed half2 (64 B per row)
+// g16[row lane][0..31] = half(pk) where pk[16] holds the row's 32 values as packed half2 (64 B per row).
+// Staging tile: 32 rows x 64 B, unpadded, 16-byte chunk j of row r stored at chunk j ^ ((r >> 1) & 3): both the
+// row-per-lane writes and the 4-lanes-per-row reads are bank-conflict free (a padded pitch of 80 B made every read
+// a 2-way conflict; the QKV kernel sat at 93 % of the L1/shared-memory pipe).
 __device__ __forceinline__ void staged_store_f16(__half* __restrict__ g, long long ld, int rows_valid, float* stage, int lane,
                                                  const uint32_t* pk) {
-  uint32_t* st = reinterpret_cast<uint32_t*>(stage);   // row pitch 20 words
+  uint32_t* st = reinterpret_cast<uint32_t*>(stage);
+  const int wsw = (lane >> 1) & 3;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
-    *reinterpret_cast<uint4*>(st + lane * 20 + 4 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    *reinterpret_cast<uint4*>(st + lane * 16 + ((j ^ wsw) << 2)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int r = i * 8 + (lane >> 2);
-    const uint4 x = *reinterpret_cast<const uint4*>(st + r * 20 + (lane & 3) * 4);
-    if (r < rows_valid) *reinterpret_cast<uint4*>(g + (long long)r * ld + (lane & 3) * 8) = x;
+    const int r = i * 8 + (lane >> 2), c = lane & 3;
+    const uint4 x = *reinterpret_cast<const uint4*>(st + r * 16 + ((c ^ ((r >> 1) & 3)) << 2));
+    if (r < rows_valid) *reinterpret_cast<uint4*>(g + (long long)r * ld + c * 8) = x;
   }
   __syncwarp();
 }

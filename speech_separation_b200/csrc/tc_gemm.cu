@@ -421,7 +421,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
         // MMAs and residual prefetch run under this tile's LayerNorm arithmetic and stores
         tc_fence_before();
         mbar_arrive(bar_accempty + 8 * as);
-        if constexpr (EPI == TC_EPI_LN) mbar_arrive(bar_rempty);
+        if constexpr (EPI == TC_EPI_LN) {
+          // The residual tile is written by TMA (async proxy) and read here with ordinary shared loads.  The proxy
+          // fence orders those reads before the next TMA write that this arrival allows; without it the stress test
+          // (tools/stress_outproj.py) sees rows of one tile normalised with the next tile's residual.
+          fence_proxy_async();
+          mbar_arrive(bar_rempty);
+        }
         float sum = 0.f;
 #pragma unroll
         for (int j = 0; j < NC; ++j) sum += v[j];
@@ -476,7 +482,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
           }
         }
       }
-      if constexpr (EPI == TC_EPI_LN_POST) mbar_arrive(bar_rempty);   // (post-LayerNorm residual: read during the stores)
+      if constexpr (EPI == TC_EPI_LN_POST) {   // (post-LayerNorm residual: read during the stores)
+        fence_proxy_async();
+        mbar_arrive(bar_rempty);
+      }
       if constexpr (L::NCH == 1 && !RES_TMA) {
         tc_fence_before();
         mbar_arrive(bar_accempty + 8 * as);

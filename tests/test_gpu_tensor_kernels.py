@@ -102,6 +102,41 @@ def test_tc_gemm_layernorm_with_fp16_residual(lib, NOUT, K, M, with32):
     assert (out16.float() - want16).norm() / want16.norm() < 1e-3
 
 
+@pytest.mark.parametrize("M", [42450, 84900, 37905])
+def test_tc_gemm_layernorm_epilogue_is_race_free(lib, M):
+    """Repeated launches must be bit-identical.  Regression test for a cross-proxy write-after-read race: the
+    epilogue released the TMA-written residual tile right after its shared-memory reads without a proxy fence, and
+    the next tile's TMA load could overwrite rows that were still being read (a few runs in sixty differed)."""
+    from speech_separation_b200 import _lib
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(M)
+    A = torch.randn(M, 128, generator=g).to(dev).half()
+    W = (torch.randn(128, 128, generator=g) * 0.1).to(dev).half()
+    bias = torch.randn(128, generator=g).to(dev)
+    res = torch.randn(M, 128, generator=g).to(dev)
+    res16 = res.half()
+    lw, lb = torch.ones(128, device=dev), torch.zeros(128, device=dev)
+    o16 = torch.empty(M, 128, dtype=torch.float16, device=dev)
+    for variant in ("fp32 residual", "fp16 residual"):
+        ref = None
+        for _ in range(40):
+            if variant == "fp32 residual":
+                rc = lib.vatss_tc_gemm(2, _p(A), 128, _p(W), _p(bias), _p(res), 128, _p(lw), _p(lb), None, 128, _p(o16), 128,
+                                       0, None, M, 128, 128, None)
+            else:
+                rc = lib.vatss_tc_gemm_ln16(_p(A), 128, _p(W), _p(bias), _p(res16), 128, _p(lw), _p(lb), None, 128, _p(o16),
+                                            128, 0, None, M, 128, 128, None)
+            _lib.check(rc, "gemm")
+            torch.cuda.synchronize()
+            if ref is None:
+                ref = o16.clone()
+            else:
+                assert torch.equal(ref, o16), variant
+        want = ln(A.float() @ W.float().t() + bias + (res if variant == "fp32 residual" else res16.float()), lw, lb)
+        assert (ref.float() - want).norm() / want.norm() < 1e-3
+
+
 def test_tc_gemm_strided_operand(lib):
     """A taken as a column slice of a wider matrix (the per-speaker halves of the overlap-add output)."""
     from speech_separation_b200 import _lib

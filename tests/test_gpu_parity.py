@@ -232,6 +232,21 @@ def test_batch_independence_and_full_size(V):
     assert torch.equal(b1, s1p) and torch.equal(b2, s2p)
 
 
+@pytest.mark.parametrize("kind,B,T", [("dptn_av", 1, 64000), ("dptn_av", 3, 32000), ("dptn_wav", 1, 64000),
+                                      ("dptn_mask", 2, 32000), ("dprnn", 1, 32000)])
+def test_forward_is_bitwise_repeatable(V, kind, B, T):
+    """Eight forwards of the same input must agree bit for bit (small batches leave SMs idle and shift the relative
+    timing of producer / MMA / epilogue warps: this is where a missing fence shows up)."""
+    net = prod_net(V, kind)
+    Tv = 25 * T // 16000 if kind == "dptn_av" else None
+    mix, s1, s2, e1, e2 = make_inputs(B, T, Tv=Tv, E=PROD[kind].get("video_emb_size"), seed=99)
+    ref1, ref2 = run(net, kind, mix, e1, e2)
+    ref1, ref2 = ref1.clone(), ref2.clone()
+    for _ in range(7):
+        a1, a2 = run(net, kind, mix, e1, e2)
+        assert torch.equal(a1, ref1) and torch.equal(a2, ref2)
+
+
 def test_extra_batch_keys_are_ignored_and_errors_are_loud(V):
     net = prod_net(V, "dptn_wav")
     mix, *_ = make_inputs(1, 4000, seed=1)

@@ -157,7 +157,11 @@ struct AttBars {
   uint32_t ofull, ofree;                               // [2 wg]
 };
 
-template <int HD>
+// MODE: 0 = resident softmax (<= 3 kv blocks: S stays in TMEM between the max and the exp pass), 1 = two-pass,
+// 2 = two-pass with K / V streamed through the shared-memory ring.  Compile-time so that the hot loops carry no mode
+// branches (the kernel is issue- and instruction-fetch-limited: ncu shows 9 % branch-resolving and 5 % no-instruction
+// stalls).
+template <int HD, int MODE>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CUtensorMap tmapQ32,
                const __grid_constant__ CUtensorMap tmapKV, TcAttnArgs p) {
@@ -172,7 +176,7 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
   const uint32_t sK = sP + 4 * 16384;              // [2] double buffered across items   (resident mode)
   const uint32_t sV = sK + 2 * KV_BYTES;
   const uint32_t sRing = sP + 4 * 16384;           // [ATT_RING] K / V super-blocks      (streaming mode)
-  const bool stream = p.stream != 0;
+  constexpr bool stream = MODE == 2;
   const uint32_t bars = stream ? sRing + ATT_RING * ATT_STAGE_BYTES : sV + KV_BYTES;
   AttBars B;
   B.kfull = bars; B.kfree = bars + 16;             // 2 each
@@ -185,7 +189,7 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
   const uint32_t b_rfull = bars + 320, b_rfree = bars + 320 + 8 * ATT_RING;
   float* s_mx = reinterpret_cast<float*>(smem + (bars + 512 - base));   // row max / row sum exchange, 8 KB
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool resident = p.nblk <= ATT_SUPER;       // all of S of a (tile, head) fits the S region: single S pass
+  constexpr bool resident = MODE == 0;             // all of S of a (tile, head) fits the S region: single S pass
   const int nsuper = (p.nblk + ATT_SUPER - 1) / ATT_SUPER;
 
   if (threadIdx.x == 0) {
@@ -576,6 +580,21 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
   if (warp == 1) tmem_dealloc<1>(tmem, 512);
 }
 
+template <int HD, int MODE>
+static int tc_attention_launch_mode(const CUtensorMap& tmQ, const CUtensorMap& tmQ32, const CUtensorMap& tmKV,
+                                    const TcAttnArgs& a, size_t smem, cudaStream_t st) {
+  auto kern = k_tc_attention<HD, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    VATSS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    configured = true;
+  }
+  const int grid = a.num_items < grid_cap() ? a.num_items : grid_cap();
+  kern<<<grid, ATT_THREADS, smem, st>>>(tmQ, tmQ32, tmKV, a);
+  VATSS_LAUNCH_OK();
+  return 0;
+}
+
 template <int HD>
 static int tc_attention_launch(const __half* qkv, __half* out, SeqMap map, int mode, int B, int S, int C, int N,
                                cudaStream_t st, bool* handled) {
@@ -611,15 +630,11 @@ static int tc_attention_launch(const __half* qkv, __half* out, SeqMap map, int m
     if (make_tmap_f16(&tmQ32, qkv, 4, dims, str, boxq32)) return -1;
     if (make_tmap_f16(&tmKV, qkv, 4, dims, str, boxkv)) return -1;
   }
-  auto kern = k_tc_attention<HD>;
-  static bool configured = false;
-  if (!configured) {
-    VATSS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    configured = true;
-  }
-  const int grid = a.num_items < grid_cap() ? a.num_items : grid_cap();
-  kern<<<grid, ATT_THREADS, smem, st>>>(tmQ, tmQ32, tmKV, a);
-  VATSS_LAUNCH_OK();
+  int rc;
+  if (a.stream) rc = tc_attention_launch_mode<HD, 2>(tmQ, tmQ32, tmKV, a, smem, st);
+  else if (a.nblk <= ATT_SUPER) rc = tc_attention_launch_mode<HD, 0>(tmQ, tmQ32, tmKV, a, smem, st);
+  else rc = tc_attention_launch_mode<HD, 1>(tmQ, tmQ32, tmKV, a, smem, st);
+  if (rc) return rc;
   *handled = true;
   return 0;
 }

@@ -161,7 +161,7 @@ struct AttBars {
 // 2 = two-pass with K / V streamed through the shared-memory ring.  Compile-time so that the hot loops carry no mode
 // branches (the kernel is issue- and instruction-fetch-limited: ncu shows 9 % branch-resolving and 5 % no-instruction
 // stalls).
-template <int HD, int MODE>
+template <int HD, int MODE, bool TRACE>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CUtensorMap tmapQ32,
                const __grid_constant__ CUtensorMap tmapKV, TcAttnArgs p) {
@@ -435,7 +435,7 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
         for (int hh = 0; hh < HPW; ++hh, ++gidx) {
           const int head = grp * HPT + w * HPW + hh;
           const uint32_t par = gidx & 1;
-          long long* T = (p.trace != nullptr && blockIdx.x == 0 && sw == 0 && lane == 0 && gidx >= 8 && gidx < 12)
+          long long* T = (TRACE && blockIdx.x == 0 && sw == 0 && lane == 0 && gidx >= 8 && gidx < 12)   // debug timeline
                              ? p.trace + (gidx - 8) * 32 : nullptr;
           if (T) T[0] = clock64();
           float mx = -INFINITY;
@@ -580,10 +580,11 @@ k_tc_attention(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant_
   if (warp == 1) tmem_dealloc<1>(tmem, 512);
 }
 
-template <int HD, int MODE>
+template <int HD, int MODE, bool TRACE = false>
 static int tc_attention_launch_mode(const CUtensorMap& tmQ, const CUtensorMap& tmQ32, const CUtensorMap& tmKV,
                                     const TcAttnArgs& a, size_t smem, cudaStream_t st) {
-  auto kern = k_tc_attention<HD, MODE>;
+  if (!TRACE && a.trace != nullptr) return tc_attention_launch_mode<HD, MODE, true>(tmQ, tmQ32, tmKV, a, smem, st);
+  auto kern = k_tc_attention<HD, MODE, TRACE>;
   static bool configured = false;
   if (!configured) {
     VATSS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));

@@ -359,6 +359,7 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
             ho[j] = *reinterpret_cast<const uint32_t*>(&o);
           }
           if (valid) *reinterpret_cast<uint4*>(orow + sub * 8) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+          asm volatile("" ::: "memory");   // keep the two 8-unit passes apart (see DESIGN.md 3.5 on scheduling)
         }
         if (T) T[3 * c + 2] = clock64(); else asm volatile("" ::: "memory");
       }

@@ -127,9 +127,11 @@ size_t carve_work(const vatss_model_desc* d, int B, int Tv, int L, int S, void* 
   w.qkv16 = b.take<__half>(dprnn ? 0 : tok * 3 * N);
   w.att16 = b.take<__half>(dprnn ? 0 : tok * N);
   w.rnn16 = b.take<__half>(tok * 2 * H);
-  w.y32 = b.take<float>(tok * 2 * N);
-  w.ola16 = b.take<__half>(fr * 2 * N);
-  w.u32 = b.take<float>(fr * N);
+  // speaker-split output, overlap-add and head output exist only where the fused tail does not apply
+  const bool unfused_tail = mask || !((N == 128 || N == 64) && (d->K == 7 || d->K == 2));
+  w.y32 = b.take<float>(unfused_tail ? tok * 2 * N : 0);
+  w.ola16 = b.take<__half>(unfused_tail ? fr * 2 * N : 0);
+  w.u32 = b.take<float>(unfused_tail ? fr * N : 0);
   w.hT = b.take<float>(mask ? fr * N : 0);
   w.hG = b.take<float>(mask ? fr * N : 0);
   w.proj = b.take<float>(fr * 2 * d->K);

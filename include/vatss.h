@@ -209,6 +209,8 @@ unsigned long long vatss_launch_count(void);
 void vatss_debug_lstm_trace(void* dev_buffer);
 /* debug / experiments: cap the grid of the persistent GEMM and attention kernels (0 = one CTA per SM) */
 void vatss_debug_cta_limit(int ctas);
+/* select the LSTM kernel of the plain fp16 path: 1 = two interleaved half tiles per CTA (default), 0 = one tile */
+void vatss_debug_lstm_pingpong(int on);
 int vatss_profile_begin(void);
 int vatss_profile_end(float* ms_per_stage, int* launches_per_stage, int n_stages);
 

@@ -16,6 +16,12 @@
 //
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA) + TMEM allocator,
 // warps 2..9 gate math (thread = sequence row, 16 hidden units per chunk).
+//
+// Two kernels share this scheme: k_tc_lstm (M = 256 MMAs, one 128-row tile per CTA; also the hi/lo split PRECISE
+// variant for DPRNN) and k_tc_lstm_pp (M = 128 MMAs, two interleaved 64-row half tiles per CTA, further below), which
+// hides the recurrence bubble and is the default for the plain fp16 LSTM.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tc_kernels.cuh"
@@ -390,6 +396,330 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
   if (warp == 1) tmem_dealloc<2>(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------
+// Ping-pong variant: two interleaved 64-row recurrences per CTA.  Default for the plain fp16 LSTM (N = 64 / 128);
+// VATSS_LSTM_PINGPONG=0 or vatss_debug_lstm_pingpong(0) select k_tc_lstm instead (bit-identical results).
+//
+// tcgen05.mma.cta_group::2 with M = 128 takes 64 rows from each CTA and leaves, in each CTA's TMEM, lanes 0-63 with D
+// columns [0, N/2) and lanes 64-127 with D columns [N/2, N), both in TMEM columns [0, N/2) (tools/ubench/tmem_layout.cu).
+// With N = 256 (two 128-column gate chunks per MMA) a half tile of 64 sequences needs 2 x 128 = 256 TMEM columns, so
+// both half tiles A (rows 0-63 of this CTA's 128-row tile) and B (rows 64-127) fit.  While the gate warps work on one
+// half, the recurrent MMAs of the other half's next step run: the recurrence bubble (fence -> arrive -> 8 MMAs ->
+// commit -> tcgen05.ld, ~1400 of 8650 cycles per step) is hidden.
+//   CTA r keeps the complete chunks {r, 2 + r} (all 128 gate columns x K) in shared memory: B rows of pair p.
+//   gate thread: lane quadrant q -> row (q & 1) * 32 + lane of the half tile and chunk 2 p + (q >> 1) of pair p;
+//   the two warps of a quadrant split the chunk's 32 units.
+// ------------------------------------------------------------------------------------------
+template <int NFEAT>
+struct TcLstmPpSmem {
+  static constexpr int KBX = NFEAT / 64;
+  static constexpr int KBT = KBX + 2;
+  static constexpr int W_TILE = 128 * 128;           // 128 B-rows (one chunk) x 128 B
+  static constexpr int W_BYTES = 2 * KBT * W_TILE;   // two chunk pairs
+  static constexpr int X_STAGE = KBX * 16384;
+  static constexpr int H_BYTES = 2 * 16384;
+  static constexpr int OFF_W = 0;
+  static constexpr int OFF_X = OFF_W + W_BYTES;
+  static constexpr int OFF_H = OFF_X + 2 * X_STAGE;
+  static constexpr int OFF_BIAS = OFF_H + H_BYTES;
+  static constexpr int OFF_BAR = OFF_BIAS + 512 * 4;
+  static constexpr int TOTAL = OFF_BAR + 256;
+};
+
+template <int NFEAT, bool TRACE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
+k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapW, TcLstmArgs p) {
+  using L = TcLstmPpSmem<NFEAT>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t base = smem_u32(smem);
+  const uint32_t sW = base + L::OFF_W, sX = base + L::OFF_X, sH = base + L::OFF_H;
+  float* sBias = reinterpret_cast<float*>(smem + L::OFF_BIAS);
+  const uint32_t bars = base + L::OFF_BAR;
+  const uint32_t bar_w = bars;                 // local: weights landed
+  const uint32_t bar_xfull = bars + 8;         // [2] leader: x tiles of both CTAs landed
+  const uint32_t bar_xempty = bars + 24;       // [2] both: MMAs finished reading the x stage
+  const uint32_t bar_accfull = bars + 40;      // [half * 2 + pair] both: gate pre-activations complete
+  const uint32_t bar_accempty = bars + 72;     // [half * 2 + pair] leader: both CTAs' gate warps drained it
+  const uint32_t bar_hfull = bars + 104;       // [half] leader: h_t of that half in shared memory (both CTAs)
+  const uint32_t tmem_slot = bars + 128;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int dir = blockIdx.y;
+  const int tile = (blockIdx.x >> 1) * 2 + (int)rank;
+  const int len = p.len;
+  if ((base & 1023u) != 0) __trap();
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_xfull + 8 * s, 1);
+      mbar_init(bar_xempty + 8 * s, 1);
+      mbar_init(bar_hfull + 8 * s, 16);
+    }
+    for (int c = 0; c < 4; ++c) {
+      mbar_init(bar_accfull + 8 * c, 1);
+      mbar_init(bar_accempty + 8 * c, 16);  // 8 gate warps x 2 CTAs
+    }
+    fence_mbar_init();
+    prefetch_tmap(&tmapX);
+    prefetch_tmap(&tmapW);
+  }
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) sBias[i] = p.bias[dir * 512 + i];
+  for (int i = threadIdx.x; i < (2 * L::X_STAGE + L::H_BYTES) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem + L::OFF_X)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 1) {
+    tmem_alloc<2>(tmem_slot, 512);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + L::OFF_BAR + 128);
+
+  // weights: pair pr -> chunk 2 pr + rank, all 128 gate columns = packed rows (dir, 0, chunk, 64) and (dir, 1, chunk, 64)
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar_w, L::W_BYTES);
+    for (int pr = 0; pr < 2; ++pr) {
+      const int chunk = 2 * pr + (int)rank;
+      for (int kb = 0; kb < L::KBT; ++kb)
+        for (int r2 = 0; r2 < 2; ++r2)
+          tma_load_2d(sW + (pr * L::KBT + kb) * L::W_TILE + r2 * 8192, &tmapW, bar_w, kb * 64,
+                      (dir * 2 + r2) * (LSTM_CHUNKS * 64) + chunk * 64);
+    }
+  }
+  mbar_wait(bar_w, 0);
+  cluster_sync();
+
+  int c0 = 0, c1 = 0, c2 = 0;
+  if (p.mode == 0) {
+    c0 = tile * 128;
+  } else {
+    c1 = (tile % p.kblocks) * p.Kc;
+    c2 = (tile / p.kblocks) * p.Bc;
+  }
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (as in k_tc_lstm)
+    if (lane == 0) {
+      uint32_t xfull_leader[2];
+      for (int s = 0; s < 2; ++s)
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(xfull_leader[s]) : "r"(bar_xfull + 8 * s));
+      const uint32_t box_bytes = (p.mode == 0 ? 128 : p.Kc * p.Bc) * 128;
+      for (int step = 0; step < len; ++step) {
+        const int t = dir == 0 ? step : len - 1 - step;
+        const int s = step & 1, n = step >> 1;
+        mbar_wait(bar_xempty + 8 * s, (n & 1) ^ 1);
+        if (leader) mbar_expect_tx(bar_xfull + 8 * s, 2 * L::KBX * box_bytes);
+        for (int kb = 0; kb < L::KBX; ++kb) {
+          const uint32_t dst = sX + s * L::X_STAGE + kb * 16384;
+          if (p.mode == 0) tma_load_4d_cg2(dst, &tmapX, xfull_leader[s], kb * 64, t, c0, 0);
+          else tma_load_4d_cg2(dst, &tmapX, xfull_leader[s], kb * 64, c1, t, c2);
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  constexpr uint32_t IDESC = idesc_f16(128, 256, 0);
+
+  if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (leader && lane == 0) {
+      auto issue_x = [&](int h, int pr, int s) {
+#pragma unroll
+        for (int k16 = 0; k16 < NFEAT / 16; ++k16) {
+          const int kb = k16 >> 2, kk = k16 & 3;
+          const uint64_t a = smem_desc_sw128_kmajor(sX + s * L::X_STAGE + kb * 16384 + h * 8192) + (uint64_t)(kk * 2);
+          const uint64_t b = smem_desc_sw128_kmajor(sW + (pr * L::KBT + kb) * L::W_TILE) + (uint64_t)(kk * 2);
+          umma_f16<2>(tmem + h * 256 + pr * 128, a, b, IDESC, k16 > 0 ? 1u : 0u);
+        }
+      };
+      auto issue_h = [&](int h, int pr) {
+#pragma unroll
+        for (int k16 = 0; k16 < LSTM_H / 16; ++k16) {
+          const int kb = k16 >> 2, kk = k16 & 3;
+          const uint64_t a = smem_desc_sw128_kmajor(sH + kb * 16384 + h * 8192) + (uint64_t)(kk * 2);
+          const uint64_t b = smem_desc_sw128_kmajor(sW + (pr * L::KBT + L::KBX + kb) * L::W_TILE) + (uint64_t)(kk * 2);
+          umma_f16<2>(tmem + h * 256 + pr * 128, a, b, IDESC, 1u);
+        }
+      };
+      // step 0: x-part only (h_{-1} = 0)
+      mbar_wait(bar_xfull, 0);
+      tc_fence_after();
+      for (int h = 0; h < 2; ++h)
+        for (int pr = 0; pr < 2; ++pr) {
+          issue_x(h, pr, 0);
+          umma_commit_cg2(bar_accfull + 8 * (h * 2 + pr), 3);
+        }
+      umma_commit_cg2(bar_xempty, 3);
+      const bool tr = TRACE && blockIdx.x == 0 && blockIdx.y == 0;
+      for (int step = 1; step < len; ++step) {
+        const int s = step & 1;
+        const uint32_t prev = (uint32_t)(step - 1) & 1u;
+        long long* T = (tr && step >= 8 && step < 12) ? p.trace + (step - 8) * 32 : nullptr;
+        if (T) T[0] = clock64();
+        mbar_wait(bar_xfull + 8 * s, (step >> 1) & 1);
+        tc_fence_after();
+        for (int h = 0; h < 2; ++h) {
+          for (int pr = 0; pr < 2; ++pr) {   // x-part as soon as the gate warps have drained the accumulator (step - 1)
+            mbar_wait(bar_accempty + 8 * (h * 2 + pr), prev);
+            tc_fence_after();
+            issue_x(h, pr, s);
+          }
+          if (h == 1) umma_commit_cg2(bar_xempty + 8 * s, 3);
+          if (T) T[1 + 3 * h] = clock64();
+          mbar_wait(bar_hfull + 8 * h, prev);   // h_{step-1} of this half complete in both CTAs
+          if (T) T[2 + 3 * h] = clock64();
+          tc_fence_after();
+          for (int pr = 0; pr < 2; ++pr) {
+            issue_h(h, pr);
+            umma_commit_cg2(bar_accfull + 8 * (h * 2 + pr), 3);
+          }
+          if (T) T[3 + 3 * h] = clock64();
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 2) {
+    // ------------------------------------------------------------------ gate math
+    const int gw = warp - 2;
+    const int q = warp & 3;            // TMEM lane quadrant this warp may touch
+    const int hs = gw >> 2;            // which 16 of the chunk's 32 units
+    const int pc = q >> 1;             // which chunk of a pair lives in this lane half
+    const int ldo = p.ndir * LSTM_H;
+    // global output row of this thread's sequence in each half tile
+    long long row_base[2], row_tstride = 0;
+    bool valid[2];
+    int rrow[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = h * 64 + (q & 1) * 32 + lane;   // row inside this CTA's 128-row tile
+      rrow[h] = r;
+      if (p.mode == 0) {
+        const long long g = (long long)c0 + r;
+        valid[h] = g < p.G;
+        row_base[h] = g * p.C;
+        row_tstride = 1;
+      } else {
+        const int bl = r / p.Kc, kl = r - bl * p.Kc;
+        valid[h] = (r < p.Kc * p.Bc) && (c2 + bl < p.B) && (c1 + kl < p.C);
+        row_base[h] = (long long)(c2 + bl) * p.S * p.C + (c1 + kl);
+        row_tstride = p.C;
+      }
+    }
+    float cst[2][2][16];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) cst[h][pr][j] = 0.f;
+    uint32_t accempty_leader[4], hfull_leader[2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(accempty_leader[c]) : "r"(bar_accempty + 8 * c));
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(hfull_leader[h]) : "r"(bar_hfull + 8 * h));
+
+    const bool trg = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && gw == 0 && lane == 0;
+    for (int step = 0; step < len; ++step) {
+      const int t = dir == 0 ? step : len - 1 - step;
+      long long* T = (trg && step >= 8 && step < 12) ? p.trace + (step - 8) * 32 + 8 : nullptr;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t hp[2][8];   // packed fp16 h of this half (kept until both pairs' recurrent MMAs have read sH)
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+          const int chunk = 2 * pr + pc;
+          if (T) T[3 * (h * 2 + pr)] = clock64(); else asm volatile("" ::: "memory");
+          mbar_wait(bar_accfull + 8 * (h * 2 + pr), step & 1);
+          if (T) T[3 * (h * 2 + pr) + 1] = clock64(); else asm volatile("" ::: "memory");
+          tc_fence_after();
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + h * 256 + pr * 128 + hs * 16;
+          __half* orow = p.out + (row_base[h] + (long long)t * row_tstride) * ldo + dir * LSTM_H +
+                         chunk * LSTM_UNITS_PER_CHUNK + hs * 16;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            uint32_t gi[8], gf[8], gg[8], go[8];
+            tmem_ld_32x32b_x8(taddr + sub * 8 + 0, gi);
+            tmem_ld_32x32b_x8(taddr + sub * 8 + 32, gf);
+            tmem_ld_32x32b_x8(taddr + sub * 8 + 64, gg);
+            tmem_ld_32x32b_x8(taddr + sub * 8 + 96, go);
+            tmem_ld_wait();
+            if (sub == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0)
+                asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(accempty_leader[h * 2 + pr]) : "memory");
+            }
+            const float4* b4 = reinterpret_cast<const float4*>(sBias + chunk * 128 + hs * 16 + sub * 8);
+            float bi[8], bf[8], bg[8], bo[8];
+            {
+              const float4 i0 = b4[0], i1 = b4[1], f0 = b4[8], f1 = b4[9], g0 = b4[16], g1 = b4[17], o0 = b4[24], o1 = b4[25];
+              bi[0] = i0.x; bi[1] = i0.y; bi[2] = i0.z; bi[3] = i0.w; bi[4] = i1.x; bi[5] = i1.y; bi[6] = i1.z; bi[7] = i1.w;
+              bf[0] = f0.x; bf[1] = f0.y; bf[2] = f0.z; bf[3] = f0.w; bf[4] = f1.x; bf[5] = f1.y; bf[6] = f1.z; bf[7] = f1.w;
+              bg[0] = g0.x; bg[1] = g0.y; bg[2] = g0.z; bg[3] = g0.w; bg[4] = g1.x; bg[5] = g1.y; bg[6] = g1.z; bg[7] = g1.w;
+              bo[0] = o0.x; bo[1] = o0.y; bo[2] = o0.z; bo[3] = o0.w; bo[4] = o1.x; bo[5] = o1.y; bo[6] = o1.z; bo[7] = o1.w;
+            }
+            float hv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float ig = sigmoid_fast(__uint_as_float(gi[j]) + bi[j]);
+              const float fg = sigmoid_fast(__uint_as_float(gf[j]) + bf[j]);
+              const float g_ = tanh_fast(__uint_as_float(gg[j]) + bg[j]);
+              const float og = sigmoid_fast(__uint_as_float(go[j]) + bo[j]);
+              const float cc = fmaf(fg, cst[h][pr][sub * 8 + j], ig * g_);
+              cst[h][pr][sub * 8 + j] = cc;
+              hv[j] = og * tanh_fast(cc);
+            }
+            uint32_t ho[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __half2 a = __floats2half2_rn(hv[2 * j], hv[2 * j + 1]);
+              hp[pr][sub * 4 + j] = *reinterpret_cast<const uint32_t*>(&a);
+              const __half2 o = p.act ? __floats2half2_rn(fmaxf(hv[2 * j], 0.f), fmaxf(hv[2 * j + 1], 0.f)) : a;
+              ho[j] = *reinterpret_cast<const uint32_t*>(&o);
+            }
+            if (valid[h]) *reinterpret_cast<uint4*>(orow + sub * 8) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+            asm volatile("" ::: "memory");
+          }
+          if (T) T[3 * (h * 2 + pr) + 2] = clock64(); else asm volatile("" ::: "memory");
+        }
+        // accfull of the second pair implies every recurrent MMA of this half and step has finished reading sH
+        if (step + 1 < len) {
+#pragma unroll
+          for (int pr = 0; pr < 2; ++pr) {
+            const int k = (2 * pr + pc) * LSTM_UNITS_PER_CHUNK + hs * 16;   // hidden-unit index = K index of the h operand
+            const int kb = k >> 6, ch = (k & 63) >> 3;
+            const uint32_t a0 = sH + kb * 16384 + sw128_offset((uint32_t)rrow[h], (uint32_t)ch);
+            const uint32_t a1 = sH + kb * 16384 + sw128_offset((uint32_t)rrow[h], (uint32_t)ch + 1);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(hp[pr][0]), "r"(hp[pr][1]),
+                         "r"(hp[pr][2]), "r"(hp[pr][3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(hp[pr][4]), "r"(hp[pr][5]),
+                         "r"(hp[pr][6]), "r"(hp[pr][7]) : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(hfull_leader[h]) : "memory");
+          if (T) T[12 + h] = clock64();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 1) tmem_dealloc<2>(tmem, 512);
+}
+
+int g_lstm_pingpong = -1;   // -1: VATSS_LSTM_PINGPONG from the environment on first use (default 1); else 0 / 1
+
 template <int NFEAT, bool PRECISE, bool TRACE = false>
 static int tc_lstm_launch(const __half* x16, const __half* x16lo, const __half* Wpack, const TcLstmArgs& a,
                           cudaStream_t st) {
@@ -417,6 +747,28 @@ static int tc_lstm_launch(const __half* x16, const __half* x16lo, const __half* 
     const uint64_t str[1] = {ktot * 2};
     const uint32_t box[2] = {64, 64};
     if (make_tmap_f16(&tmW, Wpack, 2, dims, str, box)) return -1;
+  }
+  if constexpr (!PRECISE) {
+    if (g_lstm_pingpong < 0) {
+      const char* e = getenv("VATSS_LSTM_PINGPONG");
+      g_lstm_pingpong = e ? atoi(e) : 1;
+    }
+    if (g_lstm_pingpong) {
+      using LP = TcLstmPpSmem<NFEAT>;
+      static_assert(LP::TOTAL <= 227 * 1024, "shared memory budget");
+      auto kpp = a.trace ? k_tc_lstm_pp<NFEAT, true> : k_tc_lstm_pp<NFEAT, false>;
+      static bool configured_pp = false;
+      if (!configured_pp) {
+        VATSS_CUDA_OK(cudaFuncSetAttribute(k_tc_lstm_pp<NFEAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL));
+        VATSS_CUDA_OK(cudaFuncSetAttribute(k_tc_lstm_pp<NFEAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL));
+        configured_pp = true;
+      }
+      const int pairs_pp = (a.num_tiles + 1) / 2;
+      dim3 grid_pp(2 * pairs_pp, a.ndir);
+      kpp<<<grid_pp, LSTM_THREADS, LP::TOTAL, st>>>(tmX, tmW, a);
+      VATSS_LAUNCH_OK();
+      return 0;
+    }
   }
   auto kern = k_tc_lstm<NFEAT, PRECISE, TRACE>;
   static bool configured = false;

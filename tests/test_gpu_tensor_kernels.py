@@ -167,9 +167,13 @@ LSTM_CASES = [
 ]
 
 
+@pytest.mark.parametrize("pingpong", [1, 0], ids=["half-tiles", "one-tile"])
 @pytest.mark.parametrize("mode,B,S,C,N,ndir,act", LSTM_CASES)
-def test_tc_lstm_matches_torch(lib, mode, B, S, C, N, ndir, act):
+def test_tc_lstm_matches_torch(lib, mode, B, S, C, N, ndir, act, pingpong):
+    """Both LSTM kernels: k_tc_lstm_pp (two interleaved 64-row half tiles per CTA, the default) and k_tc_lstm."""
     from speech_separation_b200 import _lib
+
+    lib.vatss_debug_lstm_pingpong(pingpong)
 
     dev = torch.device("cuda:0")
     torch.manual_seed(mode * 100 + B + S + C + N)
@@ -200,6 +204,7 @@ def test_tc_lstm_matches_torch(lib, mode, B, S, C, N, ndir, act):
     assert torch.isfinite(got).all()
     err = (got - ref).norm() / ref.norm()
     print(f"tc_lstm mode={mode} B={B} S={S} C={C} N={N} ndir={ndir}: rel err {err:.3e}, max abs {(got - ref).abs().max():.3e}")
+    lib.vatss_debug_lstm_pingpong(1)
     assert err < 3e-3  # fp16 h feedback + fp16 output + tanh.approx
 
 

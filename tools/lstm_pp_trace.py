@@ -1,11 +1,10 @@
-"""Print a clock64 timeline of CTA 0 of the LSTM kernel (MMA thread and one gate warp) for 4 time steps."""
 import ctypes, sys, torch
 sys.path.insert(0, '/root/repo')
 from speech_separation_b200 import _lib
 lib = _lib.load()
-lib.vatss_debug_lstm_pingpong(0)   # this tool reads the trace layout of k_tc_lstm (tools/lstm_pp_trace.py: k_tc_lstm_pp)
 dev = torch.device('cuda:0')
 def P(t): return ctypes.c_void_p(t.data_ptr())
+lib.vatss_debug_lstm_pingpong(1)
 for mode, B, S, C in [(0, 32, 283, 150), (1, 32, 283, 150)]:
     N, H, ndir = 128, 128, 2
     torch.manual_seed(0)
@@ -27,7 +26,8 @@ for mode, B, S, C in [(0, 32, 283, 150), (1, 32, 283, 150)]:
     t0 = int(t[0, 0])
     print("mode", mode)
     for s in range(4):
-        m = [int(v) - t0 for v in t[s, :7]]
-        g = [int(v) - t0 for v in t[s, 8:21]]
-        print(f" step {8+s}: MMA start {m[0]} xfull+{m[1]-m[0]} | X012 done@{m[2]} hfull wait {m[3]-m[2]} | H012 issued@{m[4]} accempty3 wait {m[5]-m[4]} end@{m[6]}")
-        print("          gate warp: " + " ".join(f"c{c}[wait {g[3*c+1]-g[3*c]} @{g[3*c+1]} math {g[3*c+2]-g[3*c+1]}]" for c in range(4)) + f" harrive@{g[12]}")
+        m = [int(v) - t0 for v in t[s, :8]]
+        g = [int(v) - t0 for v in t[s, 8:24]]
+        print(f" step {8+s}: MMA start@{m[0]} | X(A) done@{m[1]} hfullA wait->{m[2]} H(A) issued@{m[3]} | X(B) done@{m[4]} hfullB wait->{m[5]} H(B) issued@{m[6]}")
+        print("          gates: " + " ".join(f"{'AB'[i//2]}{i%2}[wait {g[3*i+1]-g[3*i]} @{g[3*i+1]} math {g[3*i+2]-g[3*i+1]}]" for i in range(4)) + f" hA@{g[12]} hB@{g[13]}")
+lib.vatss_debug_lstm_pingpong(0)

@@ -17,9 +17,9 @@
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA) + TMEM allocator,
 // warps 2..9 gate math (thread = sequence row, 16 hidden units per chunk).
 //
-// Two kernels share this scheme: k_tc_lstm (M = 256 MMAs, one 128-row tile per CTA; also the hi/lo split PRECISE
-// variant for DPRNN) and k_tc_lstm_pp (M = 128 MMAs, two interleaved 64-row half tiles per CTA, further below), which
-// hides the recurrence bubble and is the default for the plain fp16 LSTM.
+// Two kernels share this scheme: k_tc_lstm (M = 256 MMAs, one 128-row tile per CTA) and k_tc_lstm_pp (M = 128 MMAs,
+// two interleaved 64-row half tiles per CTA, further below), which hides the recurrence bubble and is the default.
+// Both exist in the plain fp16 form and in the hi/lo split PRECISE form used for DPRNN.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -397,7 +397,7 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
 }
 
 // ------------------------------------------------------------------------------------------
-// Ping-pong variant: two interleaved 64-row recurrences per CTA.  Default for the plain fp16 LSTM (N = 64 / 128);
+// Ping-pong variant: two interleaved 64-row recurrences per CTA.  Default (plain fp16 N = 64 / 128 and PRECISE N = 64);
 // VATSS_LSTM_PINGPONG=0 or vatss_debug_lstm_pingpong(0) select k_tc_lstm instead (bit-identical results).
 //
 // tcgen05.mma.cta_group::2 with M = 128 takes 64 rows from each CTA and leaves, in each CTA's TMEM, lanes 0-63 with D
@@ -410,9 +410,9 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
 //   gate thread: lane quadrant q -> row (q & 1) * 32 + lane of the half tile and chunk 2 p + (q >> 1) of pair p;
 //   the two warps of a quadrant split the chunk's 32 units.
 // ------------------------------------------------------------------------------------------
-template <int NFEAT>
+template <int NFEAT, bool PRECISE = false>
 struct TcLstmPpSmem {
-  static constexpr int KBX = NFEAT / 64;
+  static constexpr int KBX = PRECISE ? 2 : NFEAT / 64;   // x k-blocks (PRECISE: [x_hi | x_lo], weights [W_hi | W_lo | W_hh])
   static constexpr int KBT = KBX + 2;
   static constexpr int W_TILE = 128 * 128;           // 128 B-rows (one chunk) x 128 B
   static constexpr int W_BYTES = 2 * KBT * W_TILE;   // two chunk pairs
@@ -426,10 +426,12 @@ struct TcLstmPpSmem {
   static constexpr int TOTAL = OFF_BAR + 256;
 };
 
-template <int NFEAT, bool TRACE>
+template <int NFEAT, bool PRECISE, bool TRACE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
-k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapW, TcLstmArgs p) {
-  using L = TcLstmPpSmem<NFEAT>;
+k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapXlo,
+             const __grid_constant__ CUtensorMap tmapW, TcLstmArgs p) {
+  static_assert(!PRECISE || NFEAT == 64, "the hi/lo split variant is built for 64 input features");
+  using L = TcLstmPpSmem<NFEAT, PRECISE>;
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t base = smem_u32(smem);
   const uint32_t sW = base + L::OFF_W, sX = base + L::OFF_X, sH = base + L::OFF_H;
@@ -516,8 +518,10 @@ k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
         if (leader) mbar_expect_tx(bar_xfull + 8 * s, 2 * L::KBX * box_bytes);
         for (int kb = 0; kb < L::KBX; ++kb) {
           const uint32_t dst = sX + s * L::X_STAGE + kb * 16384;
-          if (p.mode == 0) tma_load_4d_cg2(dst, &tmapX, xfull_leader[s], kb * 64, t, c0, 0);
-          else tma_load_4d_cg2(dst, &tmapX, xfull_leader[s], kb * 64, c1, t, c2);
+          const CUtensorMap* tm = (PRECISE && kb == 1) ? &tmapXlo : &tmapX;   // k-block 1 = x_lo in PRECISE mode
+          const int f0 = PRECISE ? 0 : kb * 64;
+          if (p.mode == 0) tma_load_4d_cg2(dst, tm, xfull_leader[s], f0, t, c0, 0);
+          else tma_load_4d_cg2(dst, tm, xfull_leader[s], f0, c1, t, c2);
         }
       }
     }
@@ -530,12 +534,26 @@ k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
     // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
     if (leader && lane == 0) {
       auto issue_x = [&](int h, int pr, int s) {
+        if constexpr (!PRECISE) {
 #pragma unroll
-        for (int k16 = 0; k16 < NFEAT / 16; ++k16) {
-          const int kb = k16 >> 2, kk = k16 & 3;
-          const uint64_t a = smem_desc_sw128_kmajor(sX + s * L::X_STAGE + kb * 16384 + h * 8192) + (uint64_t)(kk * 2);
-          const uint64_t b = smem_desc_sw128_kmajor(sW + (pr * L::KBT + kb) * L::W_TILE) + (uint64_t)(kk * 2);
-          umma_f16<2>(tmem + h * 256 + pr * 128, a, b, IDESC, k16 > 0 ? 1u : 0u);
+          for (int k16 = 0; k16 < NFEAT / 16; ++k16) {
+            const int kb = k16 >> 2, kk = k16 & 3;
+            const uint64_t a = smem_desc_sw128_kmajor(sX + s * L::X_STAGE + kb * 16384 + h * 8192) + (uint64_t)(kk * 2);
+            const uint64_t b = smem_desc_sw128_kmajor(sW + (pr * L::KBT + kb) * L::W_TILE) + (uint64_t)(kk * 2);
+            umma_f16<2>(tmem + h * 256 + pr * 128, a, b, IDESC, k16 > 0 ? 1u : 0u);
+          }
+        } else {
+          // x_hi W_hi + x_lo W_hi + x_hi W_lo: (A k-block, B k-block) = (0,0), (1,0), (0,1)
+#pragma unroll
+          for (int t3 = 0; t3 < 3; ++t3) {
+            const int akb = t3 == 1 ? 1 : 0, bkb = t3 == 2 ? 1 : 0;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t a = smem_desc_sw128_kmajor(sX + s * L::X_STAGE + akb * 16384 + h * 8192) + (uint64_t)(kk * 2);
+              const uint64_t b = smem_desc_sw128_kmajor(sW + (pr * L::KBT + bkb) * L::W_TILE) + (uint64_t)(kk * 2);
+              umma_f16<2>(tmem + h * 256 + pr * 128, a, b, IDESC, (t3 > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
         }
       };
       auto issue_h = [&](int h, int pr) {
@@ -669,13 +687,13 @@ k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
             float hv[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float ig = sigmoid_fast(__uint_as_float(gi[j]) + bi[j]);
-              const float fg = sigmoid_fast(__uint_as_float(gf[j]) + bf[j]);
-              const float g_ = tanh_fast(__uint_as_float(gg[j]) + bg[j]);
-              const float og = sigmoid_fast(__uint_as_float(go[j]) + bo[j]);
+              const float ig = act_sigmoid<PRECISE>(__uint_as_float(gi[j]) + bi[j]);
+              const float fg = act_sigmoid<PRECISE>(__uint_as_float(gf[j]) + bf[j]);
+              const float g_ = act_tanh<PRECISE>(__uint_as_float(gg[j]) + bg[j]);
+              const float og = act_sigmoid<PRECISE>(__uint_as_float(go[j]) + bo[j]);
               const float cc = fmaf(fg, cst[h][pr][sub * 8 + j], ig * g_);
               cst[h][pr][sub * 8 + j] = cc;
-              hv[j] = og * tanh_fast(cc);
+              hv[j] = og * act_tanh<PRECISE>(cc);
             }
             uint32_t ho[4];
 #pragma unroll
@@ -748,24 +766,24 @@ static int tc_lstm_launch(const __half* x16, const __half* x16lo, const __half* 
     const uint32_t box[2] = {64, 64};
     if (make_tmap_f16(&tmW, Wpack, 2, dims, str, box)) return -1;
   }
-  if constexpr (!PRECISE) {
+  {
     if (g_lstm_pingpong < 0) {
       const char* e = getenv("VATSS_LSTM_PINGPONG");
       g_lstm_pingpong = e ? atoi(e) : 1;
     }
     if (g_lstm_pingpong) {
-      using LP = TcLstmPpSmem<NFEAT>;
+      using LP = TcLstmPpSmem<NFEAT, PRECISE>;
       static_assert(LP::TOTAL <= 227 * 1024, "shared memory budget");
-      auto kpp = a.trace ? k_tc_lstm_pp<NFEAT, true> : k_tc_lstm_pp<NFEAT, false>;
+      auto kpp = a.trace ? k_tc_lstm_pp<NFEAT, PRECISE, true> : k_tc_lstm_pp<NFEAT, PRECISE, false>;
       static bool configured_pp = false;
       if (!configured_pp) {
-        VATSS_CUDA_OK(cudaFuncSetAttribute(k_tc_lstm_pp<NFEAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL));
-        VATSS_CUDA_OK(cudaFuncSetAttribute(k_tc_lstm_pp<NFEAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL));
+        VATSS_CUDA_OK(cudaFuncSetAttribute(k_tc_lstm_pp<NFEAT, PRECISE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL));
+        VATSS_CUDA_OK(cudaFuncSetAttribute(k_tc_lstm_pp<NFEAT, PRECISE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL));
         configured_pp = true;
       }
       const int pairs_pp = (a.num_tiles + 1) / 2;
       dim3 grid_pp(2 * pairs_pp, a.ndir);
-      kpp<<<grid_pp, LSTM_THREADS, LP::TOTAL, st>>>(tmX, tmW, a);
+      kpp<<<grid_pp, LSTM_THREADS, LP::TOTAL, st>>>(tmX, tmXlo, tmW, a);
       VATSS_LAUNCH_OK();
       return 0;
     }

@@ -264,6 +264,46 @@ def test_tc_attention_matches_torch(lib, mode, B, S, C, N, heads, force_simt):
     assert err < 2e-3
 
 
+def test_tc_lstm_kernels_agree_on_random_shapes(lib):
+    """The half-tile (ping-pong) kernel and the one-tile kernel do the same arithmetic: their outputs must be
+    bit-identical on random shapes (single time step, partial tiles, one direction, hi/lo split, both widths)."""
+    import random
+
+    from speech_separation_b200 import _lib
+
+    dev = torch.device("cuda:0")
+    rng = random.Random(5)
+    H = 128
+    try:
+        for it in range(24):
+            mode, N, ndir, act = rng.choice([0, 1]), rng.choice([64, 128]), rng.choice([1, 2]), rng.choice([0, 1])
+            precise = N == 64 and rng.random() < 0.4
+            B, S, C = rng.choice([1, 2, 3, 5, 8]), rng.choice([1, 2, 3, 7, 20, 61]), rng.choice([1, 2, 5, 33, 64, 65, 150])
+            torch.manual_seed(it)
+            rnn = torch.nn.LSTM(N, H, batch_first=True, bidirectional=(ndir == 2))
+            names = ["weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"]
+            keep = [getattr(rnn, n + suf).detach().to(dev).contiguous() for suf in (["", "_reverse"][:ndir]) for n in names]
+            table = (ctypes.c_void_p * 8)(*([t.data_ptr() for t in keep] + [0] * (8 - len(keep))))
+            xf = torch.randn(B, S, C, N, device=dev)
+            x = xf.half()
+            xlo = (xf - x.float()).half() if precise else None
+            wpack = torch.empty(ndir * 512 * ((2 * N if precise else N) + H), dtype=torch.float16, device=dev)
+            bpack = torch.empty(ndir * 512, dtype=torch.float32, device=dev)
+            outs = []
+            for pingpong in (0, 1):
+                lib.vatss_debug_lstm_pingpong(pingpong)
+                out = torch.full((B * S * C, ndir * H), float("nan"), dtype=torch.float16, device=dev)
+                rc = lib.vatss_tc_lstm(_p(x), _p(xlo) if precise else None, table, _p(out), mode, B, S, C, N, ndir, act,
+                                       _p(wpack), _p(bpack), None)
+                _lib.check(rc, "vatss_tc_lstm")
+                torch.cuda.synchronize()
+                outs.append(out)
+            assert torch.isfinite(outs[0].float()).all()
+            assert torch.equal(outs[0], outs[1]), dict(mode=mode, N=N, ndir=ndir, precise=precise, B=B, S=S, C=C)
+    finally:
+        lib.vatss_debug_lstm_pingpong(1)
+
+
 @pytest.mark.parametrize("mode,B,S,C", [(0, 2, 40, 25), (1, 3, 11, 250)])
 def test_tc_lstm_hi_lo_split_variant(lib, mode, B, S, C):
     """PRECISE variant (DPRNN): fp32 weights and inputs, hi/lo fp16 splits inside; must track the fp32 LSTM much

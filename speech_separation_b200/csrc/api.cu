@@ -31,7 +31,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 struct StageRecord { int stage; cudaEvent_t a, b; unsigned long long launches_at_begin, launches; };
 static std::mutex g_prof_mu;
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};   // read by stage_begin/end without the mutex
 static std::vector<StageRecord> g_prof;
 static int g_open[ST_COUNT];
 

@@ -50,6 +50,21 @@ struct StageScope {
   ~StageScope() { stage_end(stage, st); }
 };
 
+// Function attributes (dynamic shared-memory limit) are per DEVICE: `PerDeviceOnce::first()` is true the first time it is
+// asked on each device ordinal (a process may run models on cuda:0 and later on cuda:1).
+struct PerDeviceOnce {
+  unsigned long long mask[4] = {0, 0, 0, 0};   // 256 ordinals; launches of one model come from one host thread
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 255;
+    const unsigned long long bit = 1ull << (dev & 63);
+    const bool f = !(mask[dev >> 6] & bit);
+    mask[dev >> 6] |= bit;
+    return f;
+  }
+};
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // How sequences of a dual-path sub-block map onto rows of a token-major (B,S,C,N) tensor.

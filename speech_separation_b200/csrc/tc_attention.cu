@@ -585,10 +585,9 @@ static int tc_attention_launch_mode(const CUtensorMap& tmQ, const CUtensorMap& t
                                     const TcAttnArgs& a, size_t smem, cudaStream_t st) {
   if (!TRACE && a.trace != nullptr) return tc_attention_launch_mode<HD, MODE, true>(tmQ, tmQ32, tmKV, a, smem, st);
   auto kern = k_tc_attention<HD, MODE, TRACE>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     VATSS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    configured = true;
   }
   const int grid = a.num_items < grid_cap() ? a.num_items : grid_cap();
   kern<<<grid, ATT_THREADS, smem, st>>>(tmQ, tmQ32, tmKV, a);

@@ -76,10 +76,11 @@ int g_cta_limit = 0;   // experiment knob: cap on persistent-kernel grids (0 = a
 int grid_cap() { return (g_cta_limit > 0 && g_cta_limit < num_sms()) ? g_cta_limit : num_sms(); }
 
 int num_sms() {
-  static int n = 0;
+  static int cache[64] = {0};   // per device ordinal
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = cache[dev & 63];
   if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
@@ -529,10 +530,9 @@ static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const
     if (make_tmap_f16(&tmW, W, 2, dims, str, box)) return -1;
   }
   auto kern = k_tc_gemm<NOUT, KDIM, EPI, WSPLIT, RES16>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     VATSS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
   }
   const int grid = args.num_tiles < grid_cap() ? args.num_tiles : grid_cap();
   kern<<<grid, L::THREADS, L::TOTAL, st>>>(tmA, tmW, tmR, args);

@@ -775,11 +775,10 @@ static int tc_lstm_launch(const __half* x16, const __half* x16lo, const __half* 
       using LP = TcLstmPpSmem<NFEAT, PRECISE>;
       static_assert(LP::TOTAL <= 227 * 1024, "shared memory budget");
       auto kpp = a.trace ? k_tc_lstm_pp<NFEAT, PRECISE, true> : k_tc_lstm_pp<NFEAT, PRECISE, false>;
-      static bool configured_pp = false;
-      if (!configured_pp) {
+      static PerDeviceOnce configured_pp;
+      if (configured_pp.first()) {
         VATSS_CUDA_OK(cudaFuncSetAttribute(k_tc_lstm_pp<NFEAT, PRECISE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL));
         VATSS_CUDA_OK(cudaFuncSetAttribute(k_tc_lstm_pp<NFEAT, PRECISE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL));
-        configured_pp = true;
       }
       const int pairs_pp = (a.num_tiles + 1) / 2;
       dim3 grid_pp(2 * pairs_pp, a.ndir);
@@ -789,10 +788,9 @@ static int tc_lstm_launch(const __half* x16, const __half* x16lo, const __half* 
     }
   }
   auto kern = k_tc_lstm<NFEAT, PRECISE, TRACE>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     VATSS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
   }
   const int pairs = (a.num_tiles + 1) / 2;
   dim3 grid(2 * pairs, a.ndir);

@@ -11,6 +11,7 @@ spectrogram models, which are out of scope).  Pass `spectrogram_fn` to get those
 torchaudio when it is installed (as the reference does) and scipy's wav reader otherwise.
 """
 import json
+import random
 import os
 import wave
 from pathlib import Path
@@ -90,10 +91,24 @@ def load_video(path):
 
 
 class SSDataset(torch.utils.data.Dataset):
-    """`<audio_dir>/<part>/{mix,s1,s2}/<id1>_<id2>.wav`, `<embedding_dir>/<id>.npz`, `<video_dir>/<id>.npz`."""
+    """`<audio_dir>/<part>/{mix,s1,s2}/<id1>_<id2>.wav`, `<embedding_dir>/<id>.npz`, `<video_dir>/<id>.npz`.
+
+    Accepts every keyword the reference's dataset configs pass (src/configs/datasets/ss_dataset.yaml ->
+    src/datasets/ss_dataset.py:12-46 -> base_dataset.py:23-54): `limit`, `target_sr`, `encoder`, `shuffle_index`
+    (python `random` with seed 42, then the limit, base_dataset.py:295-314) and `instance_transforms`, applied per key
+    like `preprocess_data` (base_dataset.py:207-233: the "mix" transform first, then every other key except the
+    special "get_spectrogram").  Deliberate divergences, all on keys no waveform model reads:
+    * the per-item log-MelSpectrogram (`mix_spectrogram`, base_dataset.py:115-123) is only computed when an
+      `instance_transforms["get_spectrogram"]` (or `spectrogram_fn`) is given - the reference fails without one;
+    * mouth-crop videos are loaded only with `load_videos=True` (default: when the model needs them, i.e. never on
+      the embedding path); the reference loads them whenever the files exist;
+    * `encoder` (an STFT front-end of the spectrogram models) is accepted and ignored, as in the reference
+      (`self.encoder = None`, base_dataset.py:49).
+    """
 
     def __init__(self, part="train", audio_dir=None, video_dir=None, embedding_dir=None, target_sr=16000, limit=None,
-                 load_videos=False, spectrogram_fn=None, root=None):
+                 load_videos=False, spectrogram_fn=None, root=None, encoder=None, shuffle_index=False,
+                 instance_transforms=None):
         root = Path(root) if root is not None else Path.cwd() / "data"
         self._audio_dir = Path(audio_dir) if audio_dir is not None else root / "audio"
         self._video_dir = Path(video_dir) if video_dir is not None else root / "mouth"
@@ -102,9 +117,34 @@ class SSDataset(torch.utils.data.Dataset):
         self.contains_embedding = self._embedding_dir.exists()
         self.target_sr = target_sr
         self.load_videos = load_videos
+        self.encoder = None
+        self.instance_transforms = instance_transforms
+        if spectrogram_fn is None and instance_transforms is not None and "get_spectrogram" in instance_transforms:
+            mel = instance_transforms["get_spectrogram"]
+            spectrogram_fn = lambda audio: torch.log(mel(audio).clamp(1e-5))  # noqa: E731  (base_dataset.py:161)
         self.spectrogram_fn = spectrogram_fn
         index = self._get_or_load_index("custom" if part is None else part)
-        self._index = index if limit is None else index[:limit]
+        self._index = self._shuffle_and_limit_index(index, limit, shuffle_index)
+
+    @staticmethod
+    def _shuffle_and_limit_index(index, limit, shuffle_index):
+        if shuffle_index:
+            random.seed(42)
+            random.shuffle(index)
+        return index if limit is None else index[:limit]
+
+    def preprocess_data(self, instance_data, special_keys=("get_spectrogram",), single_key=None):
+        if self.instance_transforms is None:
+            return instance_data
+        if single_key is not None:
+            if single_key in self.instance_transforms:
+                instance_data[single_key] = self.instance_transforms[single_key](instance_data[single_key])
+            return instance_data
+        for name in self.instance_transforms.keys():
+            if name in special_keys:
+                continue
+            instance_data[name] = self.instance_transforms[name](instance_data[name])
+        return instance_data
 
     # ---- index (ss_dataset.py:48-116) ----------------------------------------------------------------
     def _get_or_load_index(self, part):
@@ -157,12 +197,14 @@ class SSDataset(torch.utils.data.Dataset):
         if d["s1_embedding_path"] is not None:
             item["s1_embedding"] = load_object(d["s1_embedding_path"])
             item["s2_embedding"] = load_object(d["s2_embedding_path"])
+        raw_mix = item["mix"]
+        item = self.preprocess_data(item, single_key="mix")           # wav augmentation of the mixture first ...
         if self.spectrogram_fn is not None:
-            item["mix_spectrogram"] = self.spectrogram_fn(item["mix"])
+            item["mix_spectrogram"] = self.spectrogram_fn(raw_mix)    # ... the spectrogram still sees the loaded audio
             if item["s1"] is not None:
                 item["s1_spectrogram"] = self.spectrogram_fn(item["s1"])
                 item["s2_spectrogram"] = self.spectrogram_fn(item["s2"])
-        return item
+        return self.preprocess_data(item, special_keys=("get_spectrogram", "mix"))
 
 
 def make_dataloader(dataset, batch_size, num_workers=2, pin_memory=True, drop_last=False):

@@ -68,23 +68,37 @@ class MetricTracker:
 
 
 class _SharedSisnr:
-    """One `vatss_pit_sisnr` pass per batch, shared by every SI-SNR-family metric of the loop."""
+    """One `vatss_pit_sisnr` pass per batch, shared by every SI-SNR-family metric of the loop.
+
+    The cache lives for ONE batch: `Inferencer.process_batch` calls `reset()` before the metrics of a batch are
+    evaluated, and a hit requires the very same tensor objects (identity, not addresses: the caching allocator hands
+    the addresses of a freed batch to the next one, and tensors written by raw-pointer kernels keep `_version` 0).
+    The cache holds references to its key tensors, so their ids cannot be recycled while it is valid.
+    """
 
     def __init__(self):
+        self.reset()
+
+    def reset(self):
         self._key = None
         self._val = None
 
     def summary(self, batch):
-        ts = [batch["s1_pred"], batch["s2_pred"], batch["s1"], batch["s2"], batch.get("mix")]
-        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None for t in ts)
-        if key != self._key:
+        ts = (batch["s1_pred"], batch["s2_pred"], batch["s1"], batch["s2"], batch.get("mix"))
+        hit = self._key is not None and all(a is b for a, b in zip(ts, self._key[0])) and \
+            self._key[1] == tuple(t._version if t is not None else -1 for t in ts)
+        if not hit:
             self._val = pit_sisnr_all(*ts)[2]
-            self._key = key
+            self._key = (ts, tuple(t._version if t is not None else -1 for t in ts))
         return self._val
 
 
 class _AsyncWriter:
-    """Pinned staging + background `torch.save`: the compute stream never waits for the file system."""
+    """Pinned staging + background `torch.save`: the compute stream never waits for the file system.
+
+    On-disk divergence from the reference (src/trainer/inferencer.py:146-166): the saved `.pth` dicts hold CPU
+    tensors (clones of the pinned staging rows); the reference saves clones of the device tensors.  Same keys, shapes,
+    dtype and values; `torch.load(..., map_location=...)` reads both."""
 
     def __init__(self, device, depth=3):
         self.device = torch.device(device)
@@ -148,9 +162,14 @@ class _AsyncWriter:
             raise self.error
 
     def close(self):
-        self.drain()
-        self.jobs.put(None)
-        self.thread.join()
+        """Always stops the worker; a stored writer error is raised after the thread has been joined."""
+        try:
+            self.jobs.join()
+        finally:
+            self.jobs.put(None)
+            self.thread.join()
+        if self.error is not None:
+            raise self.error
 
 
 def _cfg_get(cfg, name, default=None):
@@ -235,6 +254,7 @@ class Inferencer:
         return met(**batch)
 
     def process_batch(self, batch_idx, batch, metrics, part):
+        self._shared.reset()   # the shared SI-SNR summary never outlives its batch
         batch = self.move_batch_to_device(batch)
         batch = self.transform_batch(batch)
         outputs = self.model(**batch)
@@ -266,10 +286,17 @@ class Inferencer:
             with torch.no_grad():
                 for batch_idx, batch in enumerate(dataloader):
                     self.process_batch(batch_idx=batch_idx, batch=batch, part=part, metrics=self.evaluation_metrics)
-        finally:
+        except BaseException as loop_error:
             if self._writer is not None:
-                self._writer.close()
-                self._writer = None
+                writer, self._writer = self._writer, None
+                try:
+                    writer.close()
+                except Exception as writer_error:   # keep the loop's exception, chain the writer's
+                    raise loop_error from writer_error
+            raise
+        if self._writer is not None:
+            writer, self._writer = self._writer, None
+            writer.close()
         return self.evaluation_metrics.result() if self.evaluation_metrics is not None else {}
 
 

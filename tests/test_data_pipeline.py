@@ -83,6 +83,30 @@ def test_ssdataset_index_items_and_batches(tmp_path):
     assert len(SSDataset(part="val", audio_dir=tmp_path / "audio", embedding_dir=tmp_path / "embedding", limit=3)) == 3
 
 
+def test_ssdataset_accepts_the_reference_config_keywords(tmp_path):
+    """src/configs/datasets/ss_dataset.yaml passes `instance_transforms`; BaseDataset also takes `encoder`,
+    `shuffle_index` and `limit` (base_dataset.py:23-54): same shuffle (python random, seed 42), same transform rules."""
+    import random
+
+    _write_corpus(tmp_path)
+    kw = dict(part="val", audio_dir=tmp_path / "audio", embedding_dir=tmp_path / "embedding")
+    plain = SSDataset(**kw)
+    paths = [d["mix_wav_path"] for d in plain._index]
+    want = list(paths)
+    random.seed(42)
+    random.shuffle(want)
+    shuf = SSDataset(shuffle_index=True, limit=3, encoder=object(), **kw)
+    assert [d["mix_wav_path"] for d in shuf._index] == want[:3] and shuf.encoder is None
+    tf = {"mix": lambda x: 2.0 * x, "s1": lambda x: x + 1.0, "get_spectrogram": lambda x: x.abs()[..., :4] + 1.0}
+    ds = SSDataset(instance_transforms=tf, **kw)
+    a, b = plain[1], ds[1]
+    assert torch.equal(b["mix"], 2.0 * a["mix"])                 # applied exactly once (single_key, then skipped)
+    assert torch.equal(b["s1"], a["s1"] + 1.0) and torch.equal(b["s2"], a["s2"])
+    # the spectrogram is taken from the un-augmented waveform the item loader read (base_dataset.py:113-116)
+    assert torch.allclose(b["mix_spectrogram"], torch.log((a["mix"].abs()[..., :4] + 1.0).clamp(1e-5)))
+    assert "s1_spectrogram" in b and "s2_spectrogram" in b
+
+
 def test_ssdataset_without_ground_truth_and_object_formats(tmp_path):
     _write_corpus(tmp_path, n=2, with_gt=False)
     ds = SSDataset(part="val", audio_dir=tmp_path / "audio", embedding_dir=tmp_path / "embedding")

@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from oracle import vatss_oracle as O
-from oracle.gen_golden import PROD, make_inputs
+from oracle.gen_golden import PROD, STATED, make_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -136,8 +136,10 @@ def test_tiny_models_match_reference_golden(V, golden_dir, kind):
     np.testing.assert_allclose(float(loss), float(z["loss"]), rtol=2e-4)
 
 
+# 1-s fixtures + the shapes BASELINE.json states (STATED: 10 s DPTN-AV with Tv = 250 / S = 710, 4 s DPRNN with
+# S = 510, 4 s DPTN-Wav and masking DPTN), all generated by the reference's own modules (oracle/gen_golden.py)
 PROD_CASES = [("dptn_av", 2, 16000), ("dptn_av", 1, 64000), ("dptn_wav", 2, 16000), ("dptn_mask", 2, 16000),
-              ("dprnn", 2, 16000)]
+              ("dprnn", 2, 16000)] + list(STATED)
 
 
 def prod_net(V, kind, engine="auto"):
@@ -361,19 +363,18 @@ def test_loss_edge_cases(V):
 # ---------------------------------------------------------------------------------------------
 # other BASELINE.json configurations
 # ---------------------------------------------------------------------------------------------
-def test_ten_second_utterances_tensor_vs_generic_engine(V):
-    """cfg-3 shape (10 s, S = 710, inter-chunk attention longer than the tcgen05 plan -> fallback kernel):
-    the TENSOR engine must agree with the fp32 GENERIC engine within the waveform tolerance."""
-    B, T, Tv = 2, 160000, 250
-    mix, s1, s2, e1, e2 = make_inputs(B, T, Tv=Tv, E=512, seed=4321)
-    a1, a2 = run(prod_net(V, "dptn_av", "tensor"), "dptn_av", mix, e1, e2)
-    g1, g2 = run(prod_net(V, "dptn_av", "generic"), "dptn_av", mix, e1, e2)
-    assert rel_l2(a1.cpu().numpy(), g1.cpu().numpy()) <= WAVE_TOL
-    assert rel_l2(a2.cpu().numpy(), g2.cpu().numpy()) <= WAVE_TOL
-    m = V.SISNRiMetric()
-    d = float(m(s1_pred=a1, s2_pred=a2, s1=s1.to(dev()), s2=s2.to(dev()), mix=mix.to(dev()))) - \
-        float(m(s1_pred=g1, s2_pred=g2, s1=s1.to(dev()), s2=s2.to(dev()), mix=mix.to(dev())))
-    assert abs(d) <= SNRI_TOL_DB
+def test_ten_second_batch_matches_its_single_utterance_golden(V, golden_dir):
+    """cfg-3 shape (10 s, Tv = 250, S = 710: streamed inter-chunk attention, 710-step inter LSTM) inside a batch: row 0
+    of a batch of 2 must reproduce the reference's single-utterance golden (utterances are independent, and the
+    seeded generator draws batch row 0 first only for B = 1, so the golden inputs are placed in row 0 explicitly)."""
+    z = np.load(os.path.join(golden_dir, "prod_dptn_av_B1_T160000.npz"))
+    mix, s1, s2, e1, e2 = make_inputs(1, 160000, Tv=250, E=512, seed=int(z["input_seed"]))
+    mix2, _, _, e12, e22 = make_inputs(1, 160000, Tv=250, E=512, seed=77)
+    net = prod_net(V, "dptn_av", "auto")
+    a1, a2 = run(net, "dptn_av", torch.cat([mix, mix2]), torch.cat([e1, e12]), torch.cat([e2, e22]))
+    r1, r2 = rel_l2(a1[0].cpu().numpy(), z["s1_pred"][0]), rel_l2(a2[0].cpu().numpy(), z["s2_pred"][0])
+    print(f"10 s, batch 2, row 0 vs reference golden: rel-L2 {r1:.3e} {r2:.3e}")
+    assert r1 <= WAVE_TOL and r2 <= WAVE_TOL
 
 
 def test_training_shape_forward_plus_loss(V):

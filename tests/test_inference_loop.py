@@ -133,3 +133,71 @@ def test_inferencer_gpu_matches_per_batch_calls(tmp_path):
     assert logs["SISNR"] == pytest.approx(want["SISNR"], abs=1e-4)
     assert logs["SISNRi"] == pytest.approx(want["SISNRi"], abs=1e-4)
     assert len(list((tmp_path / "out" / "val").iterdir())) == 6
+
+
+class _FreshBatches:
+    """A dataloader stand-in that builds every batch dict on demand and keeps no reference to it (what a real
+    torch DataLoader does): the previous batch is freed before the next one is moved to the device, so the caching
+    allocator hands the same device addresses to consecutive batches."""
+
+    def __init__(self, n, B, T, seed, scale):
+        self.n, self.B, self.T, self.seed, self.scale = n, B, T, seed, scale
+
+    def make(self, i):
+        b = _batches(1, self.B, self.T, seed=self.seed + i)[0]
+        b["s1"] = b["s1"] * self.scale[i]      # very different levels per batch: a stale summary is far off
+        b["mix"] = b["s1"] + b["s2"]
+        return b
+
+    def __iter__(self):
+        for i in range(self.n):
+            yield self.make(i)
+
+
+@pytest.mark.gpu
+def test_shared_sisnr_summary_never_outlives_its_batch():
+    """Round-1 advisor finding: the shared SI-SNR cache was keyed on device addresses, which the caching allocator
+    recycles from batch to batch (and raw-pointer kernels leave `_version` at 0) -> stale metric values."""
+    import speech_separation_b200 as V
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    kw = dict(num_features=128, video_emb_size=512, hidden_video=128, kernel_size_enc=7, hidden_dim=128, num_blocks=1,
+              chunk_size=150, step_size=75, num_heads=4, dropout=0.1, bidir=True)
+    net = V.DPTNAVWavEncDec(**kw).eval().to(dev)
+    cfg = {"inferencer": {"device_tensors": ["mix", "s1", "s2", "s1_embedding", "s2_embedding"], "from_pretrained": None}}
+    loader = _FreshBatches(5, 2, 16000, seed=100, scale=[1.0, 8.0, 0.1, 3.0, 0.5])
+    mets = [V.SISNRMetric(name="SISNR"), V.SISNRiMetric(name="SISNRi")]
+    inf = Inferencer(net, cfg, dev, {"val": loader}, None, metrics={"inference": mets}, skip_model_load=True)
+    logs = inf.run_inference()["val"]
+    want = {"SISNR": 0.0, "SISNRi": 0.0}
+    per_batch = []
+    for i in range(loader.n):
+        d = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in loader.make(i).items()}
+        d.update(net(**d))
+        per_batch.append(float(mets[1](**d)))
+        want["SISNR"] += mets[0](**d) / loader.n
+        want["SISNRi"] += per_batch[-1] / loader.n
+    assert max(per_batch) - min(per_batch) > 1.0     # the batches really differ
+    assert logs["SISNR"] == pytest.approx(want["SISNR"], abs=1e-4)
+    assert logs["SISNRi"] == pytest.approx(want["SISNRi"], abs=1e-4)
+
+
+def test_shared_sisnr_cache_is_identity_keyed():
+    from speech_separation_b200.inference import _SharedSisnr
+    import speech_separation_b200.inference as I
+
+    calls = []
+    orig = I.pit_sisnr_all
+    I.pit_sisnr_all = lambda *ts: (None, None, calls.append(ts) or len(calls))
+    try:
+        sh = _SharedSisnr()
+        a = {k: torch.zeros(2, 8) for k in ("s1_pred", "s2_pred", "s1", "s2", "mix")}
+        assert sh.summary(a) == 1 and sh.summary(a) == 1            # same tensors: one pass
+        b = {k: v.clone() for k, v in a.items()}
+        assert sh.summary(b) == 2                                   # equal values, other objects: recomputed
+        b["s1"].add_(1.0)
+        assert sh.summary(b) == 3                                   # in-place change (version counter)
+        sh.reset()
+        assert sh.summary(b) == 4                                   # a new batch never hits
+    finally:
+        I.pit_sisnr_all = orig

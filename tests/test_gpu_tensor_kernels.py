@@ -234,10 +234,14 @@ ATT_CASES = [
 ]
 
 
-@pytest.mark.parametrize("force_simt", [0, 1])
+@pytest.mark.parametrize("force_simt", [0, 1, -1], ids=["v2_tmem", "simt", "v1_smem"])
 @pytest.mark.parametrize("mode,B,S,C,N,heads", ATT_CASES)
 def test_tc_attention_matches_torch(lib, mode, B, S, C, N, heads, force_simt):
+    """force_simt 0: tcgen05 kernel v2 (P in TMEM, tc_attn2.cu, the default); 1: SIMT fallback; -1: round-1 tcgen05 kernel."""
     from speech_separation_b200 import _lib
+
+    lib.vatss_debug_attention_version(1 if force_simt < 0 else 2)
+    force_simt = max(force_simt, 0)
 
     dev = torch.device("cuda:0")
     torch.manual_seed(7 * mode + B + S + C + N)
@@ -255,6 +259,7 @@ def test_tc_attention_matches_torch(lib, mode, B, S, C, N, heads, force_simt):
     qd = qkv.to(dev).contiguous()
     out = torch.full((B * S * C, N), float("nan"), dtype=torch.float16, device=dev)
     rc = lib.vatss_tc_attention(_p(qd), _p(out), mode, B, S, C, N, heads, force_simt, None)
+    lib.vatss_debug_attention_version(2)
     _lib.check(rc, "vatss_tc_attention")
     torch.cuda.synchronize()
     got = out.float().reshape(B, S, C, N)

@@ -67,19 +67,22 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (kills this context only) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (kills this context only) instead of hanging the GPU.  The slow path stays tiny
+// (every call site inlines it, and the tcgen05 kernels are instruction-cache bound): no printf unless VATSS_MBAR_DEBUG.
 #ifndef VATSS_MBAR_TIMEOUT_CYCLES
 #define VATSS_MBAR_TIMEOUT_CYCLES (4000000000ll)
 #endif
+__device__ __forceinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+#ifdef VATSS_MBAR_DEBUG
+  printf("vatss: mbarrier timeout block=%d thread=%d bar=0x%x parity=%u\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+#endif
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > VATSS_MBAR_TIMEOUT_CYCLES) {
-      printf("vatss: mbarrier timeout block=%d thread=%d bar=0x%x parity=%u\n", (int)blockIdx.x, (int)threadIdx.x,
-             bar, parity);
-      __trap();
-    }
+    if (clock64() - t0 > VATSS_MBAR_TIMEOUT_CYCLES) mbar_timeout(bar, parity);
   }
 }
 // Warp-collective wait for an issuer warp: the loop exit is a warp vote, so control flow (and everything computed
@@ -88,22 +91,14 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
   if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
   const long long t0 = clock64();
   while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
-    if (clock64() - t0 > VATSS_MBAR_TIMEOUT_CYCLES) {
-      printf("vatss: mbarrier timeout block=%d thread=%d bar=0x%x parity=%u\n", (int)blockIdx.x, (int)threadIdx.x,
-             bar, parity);
-      __trap();
-    }
+    if (clock64() - t0 > VATSS_MBAR_TIMEOUT_CYCLES) mbar_timeout(bar, parity);
   }
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait_cluster(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > VATSS_MBAR_TIMEOUT_CYCLES) {
-      printf("vatss: cluster mbarrier timeout block=%d thread=%d bar=0x%x parity=%u\n", (int)blockIdx.x,
-             (int)threadIdx.x, bar, parity);
-      __trap();
-    }
+    if (clock64() - t0 > VATSS_MBAR_TIMEOUT_CYCLES) mbar_timeout(bar, parity);
   }
 }
 

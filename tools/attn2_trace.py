@@ -6,8 +6,8 @@ from speech_separation_b200 import _lib
 lib = _lib.load()
 dev = torch.device('cuda:0')
 def P(t): return ctypes.c_void_p(t.data_ptr())
-NAMES = ["s_full seen", "max done", "exp done", "P arrive", "mma: P seen", "mma: O free", "mma: PV issued", "mma: S issued",
-         "epi: O seen", "epi: done"]
+NAMES = ["s_full seen", "max done", "exp done", "P arrive", "pv: P seen", "-", "pv: issued", "-", "readout: O seen",
+         "readout: done", "S: begin", "S: kv full", "S: slot free", "S: issued", "tma: kv load issued"]
 for mode, B, S, C in [(0, 32, 283, 150), (1, 32, 283, 150)]:
     N, heads = 128, 4
     torch.manual_seed(0)
@@ -23,5 +23,5 @@ for mode, B, S, C in [(0, 32, 283, 150), (1, 32, 283, 150)]:
     t0 = int(t[0, 0])
     print("mode", mode, "(cycles relative to the first traced job's s_full)")
     for s in range(8):
-        a = [int(v) - t0 for v in t[s, :10]]
-        print(f" job {s}: " + " | ".join(f"{n} {v}" for n, v in zip(NAMES, a)))
+        a = [int(v) - t0 if int(v) else None for v in t[s, :15]]
+        print(f" job {s}: " + " | ".join(f"{n} {v}" for n, v in zip(NAMES, a) if n != "-" and v is not None))

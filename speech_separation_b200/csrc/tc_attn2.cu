@@ -15,10 +15,10 @@
 // resident / two-pass / streaming modes.  K / V blocks stream through a 4-stage TMA ring for every sequence length.
 //
 // Work item = (sequence, 64-feature head group); persistent, one CTA per SM, 12 warps:
-//   warps 0..3    softmax warpgroup 0 (even heads of the group); warps 4..7 softmax warpgroup 1 (odd heads); each
+//   warp 0        TMA producer;  warp 1  S issuer;  warps 2, 3  P V issuers, one per softmax warpgroup
+//   warps 4..7    softmax warpgroup 0 (even heads of the group); warps 8..11 softmax warpgroup 1 (odd heads); each
 //                 thread also reads out the O rows it produced (deferred behind the next job's softmax), merges
 //                 kv blocks / strips, normalises and stores - no separate epilogue role, no statistics hand-off
-//   warps 8, 9    P V issuers, one per softmax warpgroup;  warp 10  S issuer;  warp 11  TMA producer
 // Few roles and compact (not unrolled) softmax loops on purpose: the 16-warp / 5-role version of this kernel spent
 // a third of its issue-stall samples on instruction-cache misses (62 KB of SASS, profiles/r02_*).
 // Each softmax warpgroup owns a ring of TWO S / P slots: S(i + 2) is issued as soon as P V(i) has completed, so the
@@ -144,7 +144,7 @@ k_tc_attn2(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
     prefetch_tmap(&tmapQ32);
     prefetch_tmap(&tmapKV);
   }
-  if (warp == 8) {
+  if (warp == 1) {
     tmem_alloc<1>(tmem_slot, 512);
     tmem_relinquish<1>();
   }
@@ -156,9 +156,9 @@ k_tc_attn2(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
   // Register budget (launch: 384 x 168): the control warpgroup hands registers to the two softmax warpgroups, whose
   // threads keep a whole S row (<= 96 columns) in registers.  Each setmaxnreg sits at the top of its role's branch
   // (ptxas budgets the code that follows it and takes the minimum where branches with different budgets merge).
-  if (warp >= 8) {
+  if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  if (warp == 11) {
+  if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
       uint32_t qn = 0, kvn = 0;
@@ -194,7 +194,7 @@ k_tc_attn2(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
       }
     }
     __syncwarp();
-  } else if (warp == 10) {
+  } else if (warp == 1) {
     // ---------------------------------------------------------------- S issuer (both warpgroups)
     // S(i) of warpgroup w goes to slot (w, i & 1) once P V(i - 2), which read P from that slot, has completed.
     // Warp-uniform control flow, one elected lane issues (umma_*_warp).
@@ -223,11 +223,11 @@ k_tc_attn2(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
       if (w) ++iw1; else ++iw0;
       it.next(p);
     }
-  } else if (warp >= 8) {
+  } else {
     // ---------------------------------------------------------------- P V issuer of softmax warpgroup w
     // O(i) goes to accumulator (w, i & 1): the read-out of O(i - 2) precedes the P(i) arrival in program order of
     // every softmax thread, so no separate "O free" barrier is needed.
-    const int w = __shfl_sync(0xffffffffu, warp, 0) - 8;
+    const int w = __shfl_sync(0xffffffffu, warp, 0) - 2;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t idesc_o = idesc_f16(128, HD, 0) | (1u << 16);      // B (= V) is MN-major
     A2Job<HPG, 2> it;
@@ -253,7 +253,7 @@ k_tc_attn2(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
   } else {
     // ---------------------------------------------------------------- softmax warpgroups (+ their own read-out)
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    const int w = warp >> 2;
+    const int w = (warp >> 2) - 1;
     const int q = warp & 3;                                     // TMEM lane quadrant
     const int r_tile = q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
@@ -351,6 +351,11 @@ k_tc_attn2(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
     };
     // One flat loop over the jobs of this warpgroup plus a final flush iteration, so that the (large) read-out code
     // has a single call site per head state.
+    // Ping-pong of the two warpgroups (FA3 style, named barriers 3 + w): a warpgroup enters the MUFU-heavy part of
+    // a job only after the other one has left its own, so the exponentials of one overlap the loads, hand-offs and
+    // read-outs of the other instead of both competing for the MUFU pipe and then idling together.  Both warpgroups
+    // run the same number of jobs, and every job passes through the barrier pair exactly once.
+    if (w == 1) asm volatile("bar.arrive 3, 256;" ::: "memory");   // warpgroup 0 goes first
     A2Job<HPG, 2> it;
     it.init(p, w);
     int cur_item = -1;
@@ -377,6 +382,7 @@ k_tc_attn2(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
         mbar_wait(s_full + 8 * (2 * w + r), (i >> 1) & 1);
         tc_fence_after();
         A2_MARK(w == 0 && q == 0, i, 0);
+        asm volatile("bar.sync %0, 256;" ::"r"(3 + w) : "memory");
         if (!rag && warp_live) {
           // ---- full tile: this thread owns query row q * 32 + lane.  The whole row (<= 96 columns) is loaded into
           // registers ONCE: one TMEM round trip per job instead of one per 32 columns and pass (those round trips,
@@ -457,6 +463,7 @@ k_tc_attn2(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
           }
         }
         A2_MARK(w == 0 && q == 0, i, 2);
+        asm volatile("bar.arrive %0, 256;" ::"r"(4 - w) : "memory");
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -477,7 +484,7 @@ k_tc_attn2(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<1>(tmem, 512);
+  if (warp == 1) tmem_dealloc<1>(tmem, 512);
 }
 
 template <int HD>

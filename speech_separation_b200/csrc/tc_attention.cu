@@ -639,13 +639,14 @@ static int tc_attention_launch(const __half* qkv, __half* out, SeqMap map, int m
   return 0;
 }
 
-int g_attention_version = 2;
+int g_attention_version = 3;
 
 int launch_attention_f16(const __half* qkv, __half* out, SeqMap map, int mode, int B, int S, int C, int N, int heads,
                          int force_simt, cudaStream_t st) {
   if (map.G == 0) return 0;
   const int hd = N / heads;
   if (!force_simt && N % 64 == 0 && (hd == 16 || hd == 32)) {
+    if (g_attention_version == 3) return launch_attention_v3(qkv, out, map, mode, B, S, C, N, heads, st);
     if (g_attention_version == 2) return launch_attention_v2(qkv, out, map, mode, B, S, C, N, heads, st);
     bool handled = false;
     int rc = hd == 32 ? tc_attention_launch<32>(qkv, out, map, mode, B, S, C, N, st, &handled)

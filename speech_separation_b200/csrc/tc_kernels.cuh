@@ -43,6 +43,8 @@ int launch_attention_f16(const __half* qkv, __half* out, SeqMap map, int mode, i
 // v2 of the tcgen05 attention core (P kept in TMEM, tc_attn2.cu); same contract, N % 64 == 0 and head dim 16 / 32 only
 int launch_attention_v2(const __half* qkv, __half* out, SeqMap map, int mode, int B, int S, int C, int N, int heads,
                         cudaStream_t st);
-extern int g_attention_version;   // 2 (default) or 1 (tc_attention.cu), vatss_debug_attention_version
+int launch_attention_v3(const __half* qkv, __half* out, SeqMap map, int mode, int B, int S, int C, int N, int heads,
+                        cudaStream_t st);
+extern int g_attention_version;   // 3 (default, tc_attn3.cu), 2 (tc_attn2.cu) or 1 (tc_attention.cu)
 
 }  // namespace vatss

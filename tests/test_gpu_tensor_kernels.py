@@ -234,13 +234,60 @@ ATT_CASES = [
 ]
 
 
-@pytest.mark.parametrize("force_simt", [0, 1, -1], ids=["v2_tmem", "simt", "v1_smem"])
-@pytest.mark.parametrize("mode,B,S,C,N,heads", ATT_CASES)
-def test_tc_attention_matches_torch(lib, mode, B, S, C, N, heads, force_simt):
-    """force_simt 0: tcgen05 kernel v2 (P in TMEM, tc_attn2.cu, the default); 1: SIMT fallback; -1: round-1 tcgen05 kernel."""
+def _attention_reference(qkv, mode, B, S, C, N, heads, dev):
+    hd = N // heads
+    x = qkv.float().to(dev)
+    seq = x.reshape(B * S, C, 3 * N) if mode == 0 else x.permute(0, 2, 1, 3).reshape(B * C, S, 3 * N)
+    G, Ls = seq.shape[0], seq.shape[1]
+    q, k, v = (seq[..., i * N:(i + 1) * N].reshape(G, Ls, heads, hd).transpose(1, 2) for i in range(3))
+    p = torch.softmax((q @ k.transpose(-1, -2)) * 0.6931471805599453, dim=-1)  # exp2 scores
+    ref = (p @ v).transpose(1, 2).reshape(G, Ls, N)
+    return ref.reshape(B, S, C, N) if mode == 0 else ref.reshape(B, C, S, N).permute(0, 2, 1, 3)
+
+
+@pytest.mark.parametrize("version", [3, 2])
+@pytest.mark.parametrize("mode,B,S,C,N,heads", [(0, 2, 3, 150, 128, 4), (1, 2, 283, 3, 128, 4), (1, 1, 710, 2, 128, 4),
+                                                (0, 2, 2, 150, 64, 4), (1, 2, 200, 2, 64, 4)])
+def test_tc_attention_growing_logits_force_the_rescale_path(lib, mode, B, S, C, N, heads, version):
+    """Keys late in the sequence get much larger logits than the first kv block: v3 accumulates O in TMEM with the
+    first block's row maximum as reference and must rescale (difference > 2^8); v2 merges job-local statistics."""
     from speech_separation_b200 import _lib
 
-    lib.vatss_debug_attention_version(1 if force_simt < 0 else 2)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11 * mode + S + C + N)
+    hd = N // heads
+    qkv = torch.randn(B, S, C, 3 * N)
+    qkv[..., :N] *= 1.4426950408889634 / hd ** 0.5
+    L = C if mode == 0 else S
+    ramp = torch.linspace(0.3, 6.0, L)                       # key scale grows along the sequence: logits up to +-30
+    if mode == 0:
+        qkv[..., N:2 * N] *= ramp[None, None, :, None]
+    else:
+        qkv[..., N:2 * N] *= ramp[None, :, None, None]
+    qkv = qkv.half()
+    ref = _attention_reference(qkv, mode, B, S, C, N, heads, dev)
+    qd = qkv.to(dev).contiguous()
+    out = torch.full((B * S * C, N), float("nan"), dtype=torch.float16, device=dev)
+    lib.vatss_debug_attention_version(version)
+    rc = lib.vatss_tc_attention(_p(qd), _p(out), mode, B, S, C, N, heads, 0, None)
+    lib.vatss_debug_attention_version(3)
+    _lib.check(rc, "vatss_tc_attention")
+    torch.cuda.synchronize()
+    got = out.float().reshape(B, S, C, N)
+    assert torch.isfinite(got).all()
+    err = ((got - ref).norm() / ref.norm()).item()
+    print(f"attention v{version} rescale case mode={mode} S={S} C={C} N={N}: rel err {err:.3e}")
+    assert err < 2e-3
+
+
+@pytest.mark.parametrize("force_simt", [0, 1, -1, -2], ids=["v3_tmem_acc", "simt", "v1_smem", "v2_tmem"])
+@pytest.mark.parametrize("mode,B,S,C,N,heads", ATT_CASES)
+def test_tc_attention_matches_torch(lib, mode, B, S, C, N, heads, force_simt):
+    """force_simt 0: tcgen05 kernel v3 (P and O in TMEM, tc_attn3.cu, the default); 1: SIMT fallback; -1: round-1 tcgen05
+    kernel (P through shared memory); -2: v2 (P in TMEM, job-local statistics merged in registers)."""
+    from speech_separation_b200 import _lib
+
+    lib.vatss_debug_attention_version({-1: 1, -2: 2}.get(force_simt, 3))
     force_simt = max(force_simt, 0)
 
     dev = torch.device("cuda:0")
@@ -259,7 +306,7 @@ def test_tc_attention_matches_torch(lib, mode, B, S, C, N, heads, force_simt):
     qd = qkv.to(dev).contiguous()
     out = torch.full((B * S * C, N), float("nan"), dtype=torch.float16, device=dev)
     rc = lib.vatss_tc_attention(_p(qd), _p(out), mode, B, S, C, N, heads, force_simt, None)
-    lib.vatss_debug_attention_version(2)
+    lib.vatss_debug_attention_version(3)
     _lib.check(rc, "vatss_tc_attention")
     torch.cuda.synchronize()
     got = out.float().reshape(B, S, C, N)

@@ -17,7 +17,7 @@ from speech_separation_b200 import _lib  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--shapes", default="cfg2")
-ap.add_argument("--versions", default="1,2")
+ap.add_argument("--versions", default="1,3")
 args = ap.parse_args()
 lib = _lib.load()
 dev = torch.device("cuda:0")
@@ -66,7 +66,8 @@ for name, mode, B, S, C, N in SHAPES:
         best = min(ms)
         print(f"{name:14s} v{ver}: {best:.3f} ms (median {sorted(ms)[len(ms) // 2]:.3f}) | {exps / best / 1e6:.0f} G true exp/s "
               f"= {exps / (best * 1e-3) / (148 * 16 * 1.9e9):.2f} of the MUFU floor @1.9 GHz | rel err vs torch {err:.2e}", flush=True)
-    if len(outs) == 2:
-        d = (outs[1].float() - outs[2].float()).abs().max().item()
-        print(f"{name:14s} max |v1 - v2| = {d:.3e}")
-lib.vatss_debug_attention_version(2)
+    if len(outs) >= 2:
+        vs = sorted(outs)
+        d = (outs[vs[0]].float() - outs[vs[-1]].float()).abs().max().item()
+        print(f"{name:14s} max |v{vs[0]} - v{vs[-1]}| = {d:.3e}")
+lib.vatss_debug_attention_version(3)

@@ -85,6 +85,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > VATSS_MBAR_TIMEOUT_CYCLES) mbar_timeout(bar, parity);
   }
 }
+// Wait with back-off for warps that can afford ~100 ns of wake-up latency (softmax / epilogue / producer warps of the
+// attention kernel): polling warps otherwise execute half of all issued instructions and steal issue slots from the
+// warps that have work (ncu: ISETP / BRA / SYNCS / CS2R on top of the instruction mix).
+template <int NS>
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (true) {
+    __nanosleep(NS);
+    if (mbar_try_wait(bar, parity)) return;
+    if ((++spins & 1023u) == 0) {
+      const long long t = clock64();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > VATSS_MBAR_TIMEOUT_CYCLES) mbar_timeout(bar, parity);
+    }
+  }
+}
 // Warp-collective wait for an issuer warp: the loop exit is a warp vote, so control flow (and everything computed
 // after it) stays provably warp-uniform for ptxas.
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {

@@ -9,16 +9,19 @@
 // Per (128-query x <= 96-key x head) job a softmax thread has ~640 cycles of MUFU work but ~2500 cycles of exposed
 // latency (TMEM round trips ~200 cycles each, mbarrier hand-offs, O read-out) - with two warps per scheduler neither
 // the MUFU pipe (40 %) nor the issue slots (45 %) are busy.  The cure is occupancy, and registers are what limits it:
-//   * softmax threads are LEAN (<= 80 registers): one 32-column TMEM chunk at a time, no O state.  O is not read out
-//     per job: the P V MMAs of all kv blocks of a (query tile, head) accumulate in TMEM.  The reference maximum is
-//     the row maximum of the first block; a later block only forces a rescale of O (done by the softmax thread that
-//     owns the row, after the previous P V has completed) when its maximum exceeds the reference by more than 2^8 -
-//     exact softmax, the rescale is a rare slow path (FA4's conditional rescaling).
+//   * softmax threads are LEAN (<= 80 registers): one 32-column TMEM chunk at a time, loaded ONCE (no separate
+//     maximum pass), no O state.  O is not read out per job: the P V MMAs of all kv blocks of a (query tile, head)
+//     accumulate in TMEM.  The reference is the maximum of the first 32-column chunk of the row; a later chunk only
+//     forces a rescale (of O - after the previous P V has completed -, of the row sum and of the P chunks already
+//     written, all by the softmax thread that owns the row) when it exceeds the reference by more than 2^8: exact
+//     softmax, the rescale is a rare slow path (FA4's conditional rescaling, at chunk granularity).
 //   * FOUR softmax warpgroups = two independent pipelines per CTA (even / odd items of the CTA's list), each with its
 //     own TMA ring and MMA issuer; inside a pipeline warpgroup w handles head w of the current head pair.
 //   * one epilogue warpgroup reads O once per (query tile, head), normalises and stores.
-// 24 warps: 0, 1 TMA producers; 2, 3 MMA issuers (S(i + 1) right behind P V(i): the in-order tensor pipe protects the
-// aliased S / P slot); 4..7 epilogue; 8..23 softmax.  TMEM (512 columns): S / P slot of softmax warpgroup sw at 96 sw,
+// 24 warps: 0..15 softmax; 16..19 epilogue; 20, 21 TMA producers; 22, 23 MMA issuers (S(i + 1) right behind P V(i): the
+// in-order tensor pipe protects the aliased S / P slot).  The issuers carry the highest warp ids: the scheduler favours
+// the highest id among eligible warps, and next to four MUFU-bound softmax warps a low-id issuer starves (the
+// P ready -> P V -> S -> S full round trip was 2300 cycles with the issuers as warps 2, 3).  TMEM (512 columns): S / P slot of softmax warpgroup sw at 96 sw,
 // its O accumulator at 384 + 32 sw.  A ragged last query tile (<= 32 rows) is loaded into all four lane quadrants;
 // quadrant q handles a strip of the kv block (zeros elsewhere in its P rows) and the epilogue merges the four partial
 // results (each with its own reference and row sum) through shared memory.
@@ -29,6 +32,11 @@
 namespace vatss {
 
 using namespace ptx;
+
+#ifndef A3_BACKOFF_NS
+#define A3_BACKOFF_NS 40
+#endif
+#define a3_wait mbar_wait_backoff<A3_BACKOFF_NS>
 
 struct Attn3Args {
   int mode;       // 0 intra, 1 inter
@@ -43,7 +51,16 @@ struct Attn3Args {
   int nstg;       // K / V ring stages per pipeline (2 or 3)
   SeqMap map;
   __half* out;    // (tokens, N)
+  long long* trace;   // optional clock64 timeline of CTA 0 (debug), NULL in production
 };
+
+// debug timeline: jobs [A3_T0, A3_T0 + 8) of softmax warpgroup 0 in CTA 0, 16 slots per job
+constexpr uint32_t A3_T0 = 24;
+#define A3_MARK(cond, i, k)                                                                    \
+  do {                                                                                         \
+    if (TRACE && blockIdx.x == 0 && (cond) && (i) >= A3_T0 && (i) < A3_T0 + 8 && lane == 0)    \
+      p.trace[((i) - A3_T0) * 16 + (k)] = clock64();                                           \
+  } while (0)
 
 constexpr int A3_THREADS = 768;
 constexpr uint32_t A3_SLOT = 96;
@@ -102,7 +119,7 @@ struct A3Job {
   }
 };
 
-template <int HD>
+template <int HD, bool TRACE>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CUtensorMap tmapQ32,
            const __grid_constant__ CUtensorMap tmapKV, Attn3Args p) {
@@ -139,7 +156,7 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
     prefetch_tmap(&tmapQ32);
     prefetch_tmap(&tmapKV);
   }
-  if (warp == 2) {
+  if (warp == 22) {
     tmem_alloc<1>(tmem_slot, 512);
     tmem_relinquish<1>();
   }
@@ -148,10 +165,10 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
 
-  if (warp < 2) {
-    // ---------------------------------------------------------------- TMA producer of pipeline `warp`
+  if (warp == 20 || warp == 21) {
+    // ---------------------------------------------------------------- TMA producer of pipeline (warp - 20)
     if (lane == 0) {
-      const int pl = warp;
+      const int pl = warp - 20;
       const uint32_t sQ = base + pl * PLB, sKV = sQ + 2 * A3_QBYTES;
       const uint32_t q_full = bar_pl + 80 * pl, q_free = q_full + 16, kv_full = q_full + 32, kv_free = q_full + 56;
       uint32_t qn = 0, kvn = 0;
@@ -168,7 +185,7 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
         };
         for (int m = 0; m < p.mtiles; ++m, ++qn) {
           const uint32_t qb = qn & 1;
-          mbar_wait(q_free + 8 * qb, ((qn >> 1) & 1) ^ 1);
+          a3_wait(q_free + 8 * qb, ((qn >> 1) & 1) ^ 1);
           mbar_expect_tx(q_full + 8 * qb, A3_QBYTES);
           if (p.rag && m == p.mtiles - 1) {
             for (int k = 0; k < 4; ++k) load_rows(&tmapQ32, sQ + qb * A3_QBYTES + k * 4096, q_full + 8 * qb, colq, m * 128);
@@ -178,7 +195,7 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
           for (int hp = 0; hp < HPG / 2; ++hp)
             for (int j = 0; j < p.nblk; ++j, ++kvn) {
               const uint32_t st = kvn % (uint32_t)p.nstg;
-              mbar_wait(kv_free + 8 * st, ((kvn / (uint32_t)p.nstg) & 1) ^ 1);
+              a3_wait(kv_free + 8 * st, ((kvn / (uint32_t)p.nstg) & 1) ^ 1);
               mbar_expect_tx(kv_full + 8 * st, 2 * KVB);
               load_rows(&tmapKV, sKV + st * 2 * KVB, kv_full + 8 * st, colk, j * p.NB);
               load_rows(&tmapKV, sKV + st * 2 * KVB + KVB, kv_full + 8 * st, colv, j * p.NB);
@@ -187,11 +204,11 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
       }
     }
     __syncwarp();
-  } else if (warp < 4) {
-    // ---------------------------------------------------------------- MMA issuer of pipeline (warp - 2)
+  } else if (warp >= 22) {
+    // ---------------------------------------------------------------- MMA issuer of pipeline (warp - 22)
     // Warp-uniform control flow, one elected lane issues (umma_*_warp).  Jobs alternate between the two warpgroups
     // of the pipeline; the S of a warpgroup's next job is issued right behind the P V of its current one.
-    const int pl = __shfl_sync(0xffffffffu, warp, 0) - 2;
+    const int pl = __shfl_sync(0xffffffffu, warp, 0) - 22;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t sQ = base + pl * PLB, sKV = sQ + 2 * A3_QBYTES;
     const uint32_t q_full = bar_pl + 80 * pl, q_free = q_full + 16, kv_full = q_full + 32, kv_free = q_full + 56;
@@ -223,9 +240,12 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
       const uint32_t w = pi.w, sw = 2 * pl + w, bsw = bar_sw + BSW * sw;
       const uint32_t i = w ? ip1 : ip0, k = w ? kg1 : kg0;
       const int head = 2 * pi.hp + w;
+      A3_MARK(sw == 0, i, 3);
       mbar_wait_warp(bsw + 8, i & 1);                                                   // p_ready
+      A3_MARK(sw == 0, i, 4);
       if (pi.j == 0) mbar_wait_warp(bsw + 32, (k & 1) ^ 1);                             // o_free: previous group read out
       tc_fence_after();
+      A3_MARK(sw == 0, i, 5);
       const uint32_t vbase = sKV + (pi.kvn % nstg) * 2 * KVB + KVB + (uint32_t)(head * HD * 2);
       const uint64_t vd = a3_desc_mnmajor(vbase);
       const int nv = min(p.NB, p.len - pi.j * p.NB);
@@ -239,11 +259,13 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
         if (w) ++kg1; else ++kg0;
       }
       if (w == 1) umma_commit_warp(kv_free + 8 * (pi.kvn % nstg));                      // last MMA on this K / V stage
+      A3_MARK(sw == 0, i, 6);
       if (w) ++ip1; else ++ip0;
       pi.next(p);
       if (si.valid) issue_s();
+      A3_MARK(sw == 0, i, 7);
     }
-  } else if (warp < 8) {
+  } else if (warp >= 16) {
     // ---------------------------------------------------------------- epilogue warpgroup
     // Fixed round-robin over the four softmax warpgroups (their group counts are known), one (tile, head) at a time.
     const int q = warp & 3;
@@ -269,7 +291,7 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
         for (int w = 0; w < 2; ++w) {
           const uint32_t sw = 2 * pl + w, bsw = bar_sw + BSW * sw;
           const int head = 2 * it[pl].hp + w;
-          mbar_wait(bsw + 24, k & 1);                                                   // g_full
+          a3_wait(bsw + 24, k & 1);                                                   // g_full
           tc_fence_after();
           uint32_t o[HD];
           if constexpr (HD == 32) tmem_ld_32x32b_x32(t_lane + A3_OCOL + sw * 32, o);
@@ -278,7 +300,7 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bsw + 32);                                         // o_free
-          mbar_wait(bsw + 40 + 8 * (k & 1), (k >> 1) & 1);                              // st_ready: (reference, sum) written
+          a3_wait(bsw + 40 + 8 * (k & 1), (k >> 1) & 1);                              // st_ready: (reference, sum) written
           const float2 ml = stat[(sw * 2 + (k & 1)) * 128 + r_tile];
           if (!rag) {
             if (qi < p.len) {
@@ -342,7 +364,7 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
     }
   } else {
     // ---------------------------------------------------------------- softmax warpgroups
-    const int sw = (warp - 8) >> 2;
+    const int sw = warp >> 2;
     const int pl = sw >> 1, w = sw & 1;
     const int q = warp & 3;                                     // TMEM lane quadrant
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
@@ -356,6 +378,7 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
     A3Job<HPG, 2> it;
     it.init(p, pl, w);
     float mref = 0.f, l = 0.f;                                  // reference (log2 domain) and row sum of the open group
+    bool have_ref = false;
     uint32_t k = 0;                                             // (tile, head) group index of this warpgroup
 #pragma unroll 1
     for (uint32_t i = 0; it.valid; ++i) {
@@ -365,64 +388,76 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
       // this thread's columns: the whole block, or its strip of the ragged tile
       const int c0 = rag ? 8 * u_first : 0;
       const int ncol = !warp_live ? 0 : (rag ? max(0, min(nv - c0, 8 * u_cnt)) : nv);
-      mbar_wait(bsw, i & 1);                                                            // s_full
+      A3_MARK(sw == 0 && q == 0, i, 8);
+      a3_wait(bsw, i & 1);                                                            // s_full
       tc_fence_after();
+      A3_MARK(sw == 0 && q == 0, i, 0);
       uint32_t v[32];
       const int nfull = ncol >> 5, rem = ncol & 31;
-      // ---- pass 1: maximum over this thread's columns
-      float mx = -1e30f;
-#pragma unroll 1
-      for (int u = 0; u < nfull; ++u) {
-        tmem_ld_32x32b_x32(t_s + c0 + 32 * u, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) mx = a3_max3(mx, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-      }
-      if (rem) {
-        tmem_ld_32x32b_x32(t_s + c0 + 32 * nfull, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, e < rem ? __uint_as_float(v[e]) : -1e30f);
-      }
-      // ---- reference of the group: first block's maximum; rescale O only when a later block exceeds it by 2^8
-      if (it.j == 0) {
-        mref = mx; l = 0.f;
-      } else {
-        const bool need = mx > mref + A3_RESCALE;
-        if (__any_sync(0xffffffffu, need)) {
-          const float mnew = need ? mx : mref;
-          const float f = a3_ex2(mref - mnew);                  // 1 for the rows that keep their reference
-          mbar_wait(bsw + 16, (i - 1) & 1);                     // pv_done: the previous block's P V has completed
-          tc_fence_after();
-          uint32_t o[HD];
-          if constexpr (HD == 32) tmem_ld_32x32b_x32(t_o, o);
-          else tmem_ld_32x32b_x16(t_o, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < HD; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
-          if constexpr (HD == 32) { tmem_st_32x32b_x16(t_o, o); tmem_st_32x32b_x16(t_o + 16, o + 16); }
-          else tmem_st_32x32b_x16(t_o, o);
-          l *= f;
-          mref = mnew;
-        }
-      }
-      // ---- ragged tile: the P row is zero outside this thread's strip
+      // ---- ragged tile: the P row is zero outside this thread's strip.  The strip (<= 24 columns, one chunk) is
+      // loaded first: the zero fill overwrites it in TMEM.
       if (rag) {
+        if (rem) tmem_ld_32x32b_x32(t_s + c0, v);
+        tmem_ld_wait();
         uint32_t z[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) z[e] = 0u;
 #pragma unroll
         for (int kk = 0; kk < 3; ++kk) tmem_st_32x32b_x16(t_s + 16 * kk, z);           // packed columns [0, 48)
-        tmem_st_wait();                                          // (the strip itself is written below)
+        tmem_st_wait();
       }
-      // ---- pass 2: P = exp2(s - reference) as packed fp16 over S in place, fp32 row sum.  The P of columns
-      // [c, c + 32) lands in packed columns [c / 2, c / 2 + 16): S columns that have been consumed already.
+      if (it.j == 0) { l = 0.f; have_ref = false; }
+      // The reference of a (tile, head) is the maximum of the FIRST 32-column chunk this thread sees; every later chunk
+      // (same or later kv block) is checked against it and only forces a rescale - of O, of the row sum and of the
+      // P chunks of this job already written - when it exceeds the reference by more than 2^8.  One TMEM load per
+      // chunk: no separate maximum pass.
+      auto check_reference = [&](float cmax, int u_done) {
+        if (!have_ref) { mref = cmax; have_ref = true; return; }
+        const bool need = cmax > mref + A3_RESCALE;
+        if (__any_sync(0xffffffffu, need)) {
+          const float mnew = need ? cmax : mref;
+          const float f = a3_ex2(mref - mnew);                  // 1 for the rows that keep their reference
+          if (it.j > 0) {                                       // O holds the previous kv blocks of this group
+            a3_wait(bsw + 16, (i - 1) & 1);                     // pv_done: the previous block's P V has completed
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0o = 0; c0o < HD; c0o += 16) {            // 16 columns at a time: v[] stays live around this
+              uint32_t o[16];
+              tmem_ld_32x32b_x16(t_o + c0o, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
+              tmem_st_32x32b_x16(t_o + c0o, o);
+            }
+          }
+          const __half2 f2 = __float2half2_rn(f);
+#pragma unroll 1
+          for (int uu = 0; uu < u_done; ++uu) {                 // P chunks of this job written with the old reference
+            uint32_t pp[16];
+            tmem_ld_32x32b_x16(t_s + ((c0 + 32 * uu) >> 1), pp);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const __half2 h = __hmul2(*reinterpret_cast<const __half2*>(&pp[e]), f2);
+              pp[e] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            tmem_st_32x32b_x16(t_s + ((c0 + 32 * uu) >> 1), pp);
+          }
+          l *= f;
+          mref = mnew;
+        }
+      };
+      // ---- P = exp2(s - reference) as packed fp16 over S in place, fp32 row sum.  The P of columns [c, c + 32)
+      // lands in packed columns [c / 2, c / 2 + 16): S columns that have been consumed already.
       float sum = 0.f, sum1 = 0.f;
-      // (ragged tile: the strip, <= 24 columns, is still in v from pass 1 - the zero fill has overwritten it in TMEM)
 #pragma unroll 1
       for (int u = 0; u < nfull; ++u) {
         tmem_ld_32x32b_x32(t_s + c0 + 32 * u, v);
         tmem_ld_wait();
+        float cmax = -1e30f;
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) cmax = a3_max3(cmax, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+        check_reference(cmax, u);
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
@@ -432,12 +467,18 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
           pk[e] = a3_pack(e0, e1);
         }
         tmem_st_32x32b_x16(t_s + ((c0 + 32 * u) >> 1), pk);
+        l += sum + sum1;
+        sum = sum1 = 0.f;
       }
       if (rem) {
         if (!rag) {
           tmem_ld_32x32b_x32(t_s + c0 + 32 * nfull, v);
           tmem_ld_wait();
         }
+        float cmax = -1e30f;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) cmax = fmaxf(cmax, e < rem ? __uint_as_float(v[e]) : -1e30f);
+        check_reference(cmax, nfull);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (rem > 16 * h) {
@@ -454,10 +495,11 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
             tmem_st_32x32b_x8(t_s + ((c0 + 32 * nfull + 16 * h) >> 1), pk);
           }
         }
+        l += sum + sum1;
       }
-      l += sum + sum1;
+      A3_MARK(sw == 0 && q == 0, i, 1);
       const bool last_blk = it.j == p.nblk - 1;
-      if (last_blk) stat[(k & 1) * 128] = make_float2(mref, l);
+      if (last_blk) stat[(k & 1) * 128] = make_float2(have_ref ? mref : -1e30f, l);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -465,13 +507,14 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
         if (last_blk) mbar_arrive(bsw + 40 + 8 * (k & 1));                              // st_ready
         mbar_arrive(bsw + 8);                                                           // p_ready
       }
+      A3_MARK(sw == 0 && q == 0, i, 2);
       if (last_blk) ++k;
       it.next(p);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<1>(tmem, 512);
+  if (warp == 22) tmem_dealloc<1>(tmem, 512);
 }
 
 template <int HD>
@@ -483,6 +526,7 @@ static int attn3_launch(const __half* qkv, __half* out, SeqMap map, int mode, in
   a.mtiles = (a.len + 127) / 128;
   a.num_items = map.G * a.groups;
   a.rag = a.len - (a.mtiles - 1) * 128 <= 32;
+  a.trace = g_lstm_trace;
   const size_t fixed = 2 * 2 * A3_QBYTES + 4 * 2 * 128 * 8 + 4 * (HD + 2) * 32 * 4 + 1024;
   a.nstg = 3;
   size_t smem = fixed + 2 * (size_t)a.nstg * 2 * a.NB * 128;
@@ -508,11 +552,14 @@ static int attn3_launch(const __half* qkv, __half* out, SeqMap map, int mode, in
     if (make_tmap_f16(&tmKV, qkv, 4, dims, str, boxkv)) return -1;
   }
   static PerDeviceOnce configured;
-  if (configured.first())
-    VATSS_CUDA_OK(cudaFuncSetAttribute(k_tc_attn3<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+  if (configured.first()) {
+    VATSS_CUDA_OK(cudaFuncSetAttribute(k_tc_attn3<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    VATSS_CUDA_OK(cudaFuncSetAttribute(k_tc_attn3<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+  }
   const int items2 = (a.num_items + 1) / 2;      // two pipelines per CTA
   const int grid = items2 < grid_cap() ? items2 : grid_cap();
-  k_tc_attn3<HD><<<grid, A3_THREADS, smem, st>>>(tmQ, tmQ32, tmKV, a);
+  if (a.trace) k_tc_attn3<HD, true><<<grid, A3_THREADS, smem, st>>>(tmQ, tmQ32, tmKV, a);
+  else k_tc_attn3<HD, false><<<grid, A3_THREADS, smem, st>>>(tmQ, tmQ32, tmKV, a);
   VATSS_LAUNCH_OK();
   return 0;
 }

@@ -6,8 +6,17 @@ from speech_separation_b200 import _lib
 lib = _lib.load()
 dev = torch.device('cuda:0')
 def P(t): return ctypes.c_void_p(t.data_ptr())
-NAMES = ["s_full seen", "max done", "exp done", "P arrive", "pv: P seen", "-", "pv: issued", "-", "readout: O seen",
-         "readout: done", "S: begin", "S: kv full", "S: slot free", "S: issued", "tma: kv load issued"]
+import argparse
+ap = argparse.ArgumentParser()
+ap.add_argument("--version", type=int, default=3)
+args = ap.parse_args()
+lib.vatss_debug_attention_version(args.version)
+if args.version == 2:
+    NAMES = ["s_full seen", "max done", "exp done", "P arrive", "pv: P seen", "-", "pv: issued", "-", "readout: O seen",
+             "readout: done", "S: begin", "S: kv full", "S: slot free", "S: issued", "tma: kv load issued"]
+else:
+    NAMES = ["s_full seen", "softmax done", "P arrived", "issuer: waits P", "issuer: P seen", "issuer: O free", "issuer: PV issued",
+             "issuer: next S issued", "softmax: waits S"]
 for mode, B, S, C in [(0, 32, 283, 150), (1, 32, 283, 150)]:
     N, heads = 128, 4
     torch.manual_seed(0)

@@ -3,6 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|eager]
                     [--batch 32] [--seconds 4] [--engine auto|generic|tensor]
+                    [--total-utterances 1024 --micro-batch 16]   (cfg-3: strong scaling of a fixed job over the ranks)
+                    [--loss]                                     (cfg-5: forward + PIT SI-SNR loss, data-parallel mean)
 
 One "step" = one forward pass of DPTN-AV (src/configs/model/dptn_wav_av.yaml) over one batch of
 synthetic 16 kHz mixtures + synthetic lip embeddings, followed by the PIT SI-SNRi reduction.
@@ -28,6 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SR = 16000
+CPU_SAMPLE_BATCH = 4     # the reference's CPU path is timed at a reduced batch of 4 utterances per step
 MODEL_KW = dict(num_features=128, video_emb_size=512, hidden_video=128, kernel_size_enc=7, hidden_dim=128,
                 num_blocks=6, chunk_size=150, step_size=75, num_heads=4, dropout=0.1, bidir=True)
 # the other BASELINE.json configurations (src/configs/model/{dptn_wav,dptn,dprnn}.yaml)
@@ -94,9 +97,15 @@ def stage_bytes(B, T, model="dptn_av", f16res=False):
     return {k: 12 * tok * v for k, v in per_sub.items()}
 
 
-# DRAM traffic per launch measured by ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum) on the headline
-# workload (profiles/r01_ncu_full_final_summary.json): equals the algorithmic bytes, i.e. no wasted re-reads
-NCU_TRAFFIC_BYTES = {"attention": 1.368e9, "lstm_recurrent": 1.322e9}
+def ncu_traffic():
+    """DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture) of the
+    headline workload's kernels, from profiles/ncu_traffic.json - a file written next to the capture it comes from,
+    which names the commit and the kernel.  Not hard-coded here: a number from another kernel generation must not
+    survive silently.  Missing / unreadable file or stage -> None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except (OSError, ValueError):
+        return {}
 
 
 def make_batch(B, T, seed):
@@ -203,6 +212,11 @@ def main():
     ap.add_argument("--model", default="dptn_av", choices=["dptn_av"] + sorted(OTHER_MODELS),
                     help="dptn_av = the headline config; the others are the remaining BASELINE.json models")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--total-utterances", type=int, default=0,
+                    help="cfg-3: a fixed job of this many utterances, sharded over the ranks (strong scaling)")
+    ap.add_argument("--micro-batch", type=int, default=16)
+    ap.add_argument("--loss", action="store_true", help="cfg-5: every step also computes the PIT SI-SNR loss")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -215,13 +229,23 @@ def main():
                           + (f"synthetic lip embeddings (B,512,{25 * T // SR}), " if args.model == "dptn_av" else "")
                           + "random-init weights seed 42, + PIT SI-SNRi reduction",
               "batch_per_gpu": B, "seconds": args.seconds, "sharding": f"utterance x{max(world, args.gpus)}",
-              "l2": "256 MiB buffer written between timed steps (L2 flush); per-step activations >> 126 MB L2"}
+              "l2": "256 MiB buffer written between timed steps (L2 flush); per-step activations >> 126 MB L2",
+              "reference_arm_sample": f"--impl reference and cpu_baseline time {CPU_SAMPLE_BATCH} utterance(s) x "
+                                      f"{args.seconds:g} s of this workload per step on the host cores (BASELINE.md 3.1)"}
+    if args.total_utterances:
+        config["workload"] = (f"{wname} inference, {args.total_utterances} x {args.seconds:g} s 16 kHz sharded by utterance over "
+                              f"the ranks, micro-batches of {args.micro_batch}, NCCL all-reduce of the SI-SNRi sums per step, "
+                              "synthetic lip embeddings, random-init weights seed 42")
+        config["total_utterances"] = args.total_utterances
+        config["micro_batch"] = args.micro_batch
+    if args.loss:
+        config["workload"] += " + PIT SI-SNR loss (SiSNRWavLoss), data-parallel mean over the ranks"
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        # bounded sample: 1 utterance per step keeps K steps within minutes on the host cores
-        val, ms, info = cpu_reference_arm(max(args.steps, 1), min(args.warmup, 1), 1, T, args.model)
+        # bounded sample: CPU_SAMPLE_BATCH utterances per step keep K steps within minutes on the host cores
+        val, ms, info = cpu_reference_arm(max(args.steps, 1), min(args.warmup, 1), CPU_SAMPLE_BATCH, T, args.model)
         print(json.dumps({"metric": METRIC.replace("dptn_av", args.model), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -266,7 +290,7 @@ def main():
 
     import speech_separation_b200 as V
     from speech_separation_b200 import _lib
-    from speech_separation_b200.sharding import reduce_sisnr, sisnr_sums
+    from speech_separation_b200.sharding import reduce_sisnr, separate_in_micro_batches, shard_range, sisnr_sums
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -283,17 +307,35 @@ def main():
         net = getattr(V, OTHER_MODELS[args.model][0])(**OTHER_MODELS[args.model][1])
     net = net.eval().to(dev).set_engine(args.engine)
     metric = V.SISNRiMetric()
+    loss_fn = V.SiSNRWavLoss()
+    sharded_job = args.total_utterances > 0
+    if sharded_job:     # cfg-3: this rank's contiguous shard of the fixed job, streamed through one workspace
+        lo, hi = shard_range(args.total_utterances, rank, world)
+        B = hi - lo
     mix_h, s1_h, s2_h, e1_h, e2_h = (t.pin_memory() for t in make_batch(B, T, 1234 + rank))
     mix, s1, s2, e1, e2 = (t.to(dev) for t in (mix_h, s1_h, s2_h, e1_h, e2_h))
     out_h = [torch.empty(B, T).pin_memory() for _ in range(2)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def fwd(m, a, b):
+        if sharded_job:
+            return separate_in_micro_batches(net, m, a if av else None, b if av else None, micro_batch=args.micro_batch)
         return net(mix=m, s1_embedding=a, s2_embedding=b) if av else net(mix=m)
+
+    def step_loss(out):
+        """cfg-5: batch-level PIT SI-SNR loss of this rank's batch; data-parallel mean over the ranks (NCCL)."""
+        loss = loss_fn(s1_pred=out["s1_pred"], s2_pred=out["s2_pred"], s1=s1, s2=s2)["loss"]
+        if world > 1:
+            loss = loss.clone()
+            dist.all_reduce(loss)
+            loss = loss / world
+        return loss
 
     def step_resident():
         out = fwd(mix, e1, e2)
         rows, rows_loss, _ = V.pit_sisnr_all(out["s1_pred"], out["s2_pred"], s1, s2, mix)
+        if args.loss:
+            step_loss(out)
         return reduce_sisnr(sisnr_sums(rows, rows_loss)) if world > 1 else rows
 
     def step_e2e():
@@ -304,6 +346,8 @@ def main():
         out_h[0].copy_(out["s1_pred"], non_blocking=True)
         out_h[1].copy_(out["s2_pred"], non_blocking=True)
         val = metric(s1_pred=out["s1_pred"], s2_pred=out["s2_pred"], s1=s1, s2=s2, mix=m)
+        if args.loss:
+            return float(step_loss(out))
         return float(val)  # device -> host read of the step's metric (synchronises)
 
     def barrier():
@@ -365,7 +409,7 @@ def main():
         return 0
 
     n = max(world, 1)
-    audio_s_per_step = n * B * T / SR
+    audio_s_per_step = (args.total_utterances if sharded_job else n * B) * T / SR
     ms_per_step = total_ms / args.steps
     value = audio_s_per_step / (ms_per_step / 1e3)
     e2e_value = audio_s_per_step / (e2e_ms / args.steps / 1e3)
@@ -400,7 +444,8 @@ def main():
     roofline = {"bound": "hbm" if hbm_bound else "tensor", "kernel": dom,
                 "achieved": d["gbs"] if hbm_bound else d["tflops"], "peak": peak_bw if hbm_bound else peak_tf,
                 "unit": "GB/s" if hbm_bound else "TFLOP/s", "frac": d["hbm_frac"] if hbm_bound else d["tensor_frac"],
-                "traffic": NCU_TRAFFIC_BYTES.get(dom) if headline else None,
+                "traffic": (ncu_traffic().get("kernels", {}).get(dom, {}).get("dram_bytes_per_launch") if headline else None),
+                "traffic_source": (ncu_traffic().get("source") if headline else None),
                 "algorithmic_bytes_per_launch": by.get(dom, 0) / dom_launches,
                 "algorithmic_flops_per_launch": fl.get(dom, 0) / dom_launches,
                 "peak_source": ("MEASURED_PEAKS.json hbm_gbs / bf16_tflops_sustained" if peaks
@@ -413,15 +458,39 @@ def main():
                 "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()}}
 
     line = {"metric": METRIC.replace("dptn_av", args.model), "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if sharded_job else "weak", "vs_baseline": None,
             "dtype": "f32" if args.engine == "generic" or not _engine_is_tensor(lib, net) else "f16",
             "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(mix_h.numel() + (e1_h.numel() + e2_h.numel() if av else 0)) * 4,
-                    "d2h_bytes_per_step": int(2 * B * T) * 4 + 4},
+                    "d2h_bytes_per_step": int(2 * B * T) * 4 + 4,
+                    "note": "bytes of rank 0; mixture + lip embeddings host->device and both separated waveforms + the "
+                            "metric device->host every step; the ground-truth sources s1, s2 (metric inputs only) stay resident"},
             "gpu_launches": int(launches), "roofline": roofline, "si_snri_db": snri, "wall_s_timed": wall}
+    if world == 1 and not args.no_eager_baseline and not sharded_job:
+        # the reference's own torch.nn modules on this GPU (cuDNN LSTM, fused MHA, cuBLAS; fp32 with
+        # torch's default TF32 flags) - the "existing Blackwell library kernels" bar, 3 steps after 2 warm-ups
+        try:
+            from oracle import torch_port
+            ea, eb_ = (e1, e2) if av else (None, None)
+            for _ in range(2):
+                torch_port.forward(net, mix, ea, eb_)
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(3):
+                torch_port.forward(net, mix, ea, eb_)
+            t1.record()
+            torch.cuda.synchronize()
+            ems = t0.elapsed_time(t1) / 3
+            line["eager_gpu_baseline"] = {"value": B * T / SR / (ems * 1e-3), "unit": UNIT, "ms_per_step": ems,
+                                          "what": "the same torch.nn modules (oracle/torch_port.py) in eager PyTorch on this GPU, "
+                                                  "forward only, fp32 / TF32 defaults, 3 steps after 2 warm-ups"}
+        except Exception as e:   # a baseline must never take the bench line down
+            line["eager_gpu_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
-        _, _, info = cpu_reference_arm(2, 1, 1, T, args.model)
+        _, _, info = cpu_reference_arm(2, 1, CPU_SAMPLE_BATCH, T, args.model)
         line["cpu_baseline"] = info
     print(json.dumps(line))
     if world > 1:

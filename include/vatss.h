@@ -104,6 +104,10 @@ enum {
 
 const char* vatss_last_error(void);
 int vatss_abi_version(void);
+/* NULL when the model runs on the tcgen05 TENSOR engine (or engine = GENERIC was requested); otherwise the reason why
+ * engine = AUTO / TENSOR falls back to the fp32 SIMT engine (a ~20x slower path: the Python face warns once).
+ * No reference counterpart: the reference has one execution path (src/model/dptn_wav.py:171-194). */
+const char* vatss_engine_fallback_reason(const vatss_model_desc* d);
 
 /* Geometry helpers (exact integer index maths of the reference).
  *   L = (T-K)/(K/2)+1      nn.Conv1d output length        src/model/dptn_wav.py:153

@@ -73,6 +73,7 @@ EXPORTS = {
                       [ctypes.c_int] * 7 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "vatss_tc_attention": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 7 + [ctypes.c_void_p]),
     "vatss_launch_count": (ctypes.c_ulonglong, []),
+    "vatss_engine_fallback_reason": (ctypes.c_char_p, [ctypes.POINTER(ModelDesc)]),
     "vatss_debug_lstm_trace": (None, [ctypes.c_void_p]),
     "vatss_debug_cta_limit": (None, [ctypes.c_int]),
     "vatss_debug_lstm_pingpong": (None, [ctypes.c_int]),

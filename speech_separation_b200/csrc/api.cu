@@ -282,6 +282,12 @@ extern "C" {
 const char* vatss_last_error(void) { return g_err.c_str(); }
 int vatss_abi_version(void) { return VATSS_ABI_VERSION; }
 
+const char* vatss_engine_fallback_reason(const vatss_model_desc* d) {
+  if (d == nullptr || d->engine == VATSS_ENGINE_GENERIC || tensor_engine_selected(d)) return nullptr;
+  const char* why = tensor_engine_unsupported_reason(d);
+  return why ? why : "DPRNN with num_features != 64 needs engine=\"tensor\" explicitly (precision, DESIGN.md 4)";
+}
+
 int vatss_frames(const vatss_model_desc* d, int T) {
   if (check_desc(d)) return -1;
   return T < d->K ? 0 : (T - d->K) / stride_of(d) + 1;

@@ -274,92 +274,96 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
     float* xbuf = reinterpret_cast<float*>(smem + x_off);
     const float2* stat = reinterpret_cast<const float2*>(smem + stat_off);
     const long long row_pitch = (long long)p.map.t_stride * p.N;
-    A3Job<HPG, 2> it[2];            // group walkers of the two pipelines (warpgroup 0's jobs; w is added below)
-    it[0].init(p, 0, 0); it[1].init(p, 1, 0);
-    uint32_t kg[2] = {0, 0};
+    // Order: (item slot t of the CTA, (tile, head pair) group, pipeline, warpgroup) - the two pipelines alternate group by
+    // group.  Runtime loops over pipeline and warpgroup keep a single copy of the read-out code.
+    const int groups_per_item = p.mtiles * (HPG / 2);
 #pragma unroll 1
-    while (it[0].valid || it[1].valid) {
+    for (int t = 0;; ++t) {
+      const int item0 = blockIdx.x + 2 * t * gridDim.x;
+      if (item0 >= p.num_items) break;
+#pragma unroll 1
+      for (int gi = 0; gi < groups_per_item; ++gi) {
+        const int m = gi / (HPG / 2), hp = gi - m * (HPG / 2);
+        const bool rag = p.rag && m == p.mtiles - 1;
+        const int qi = m * 128 + (rag ? lane : r_tile);
+        const uint32_t k = (uint32_t)(t * groups_per_item + gi);        // group index inside each warpgroup's stream
+#pragma unroll 1
+        for (int pl = 0; pl < 2; ++pl) {
+          const int item = item0 + pl * gridDim.x;
+          if (item >= p.num_items) continue;
+          const int g = item / p.groups, grp = item - g * p.groups;
+          const long long off0 = p.map.row(g, 0) * p.N + grp * 64 + qi * row_pitch;
+#pragma unroll 1
+          for (int w = 0; w < 2; ++w) {
+            const int head = 2 * hp + w;
+            const uint32_t sw = 2 * pl + w, bsw = bar_sw + BSW * sw;
+            a3_wait(bsw + 24, k & 1);                                                   // g_full
+            tc_fence_after();
+            uint32_t o[HD];
+            if constexpr (HD == 32) tmem_ld_32x32b_x32(t_lane + A3_OCOL + sw * 32, o);
+            else tmem_ld_32x32b_x16(t_lane + A3_OCOL + sw * 32, o);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bsw + 32);                                         // o_free
+            a3_wait(bsw + 40 + 8 * (k & 1), (k >> 1) & 1);                              // st_ready: (reference, sum) written
+            const float2 ml = stat[(sw * 2 + (k & 1)) * 128 + r_tile];
+            if (!rag) {
+              if (qi < p.len) {
+                const float inv = 1.f / ml.y;
+                uint4* dst = reinterpret_cast<uint4*>(p.out + off0 + head * HD);
 #pragma unroll
-      for (int pl = 0; pl < 2; ++pl) {
-        if (!it[pl].valid) continue;
-        const int g = it[pl].item / p.groups, grp = it[pl].item - g * p.groups;
-        const bool rag = p.rag && it[pl].m == p.mtiles - 1;
-        const int qi = it[pl].m * 128 + (rag ? lane : r_tile);
-        const long long off0 = p.map.row(g, 0) * p.N + grp * 64 + qi * row_pitch;
-        const uint32_t k = kg[pl];
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          const uint32_t sw = 2 * pl + w, bsw = bar_sw + BSW * sw;
-          const int head = 2 * it[pl].hp + w;
-          a3_wait(bsw + 24, k & 1);                                                   // g_full
-          tc_fence_after();
-          uint32_t o[HD];
-          if constexpr (HD == 32) tmem_ld_32x32b_x32(t_lane + A3_OCOL + sw * 32, o);
-          else tmem_ld_32x32b_x16(t_lane + A3_OCOL + sw * 32, o);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bsw + 32);                                         // o_free
-          a3_wait(bsw + 40 + 8 * (k & 1), (k >> 1) & 1);                              // st_ready: (reference, sum) written
-          const float2 ml = stat[(sw * 2 + (k & 1)) * 128 + r_tile];
-          if (!rag) {
-            if (qi < p.len) {
-              const float inv = 1.f / ml.y;
-              uint4* dst = reinterpret_cast<uint4*>(p.out + off0 + head * HD);
-#pragma unroll
-              for (int c = 0; c < HD / 8; ++c) {
-                uint4 wd;
-                wd.x = a3_pack(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
-                wd.y = a3_pack(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
-                wd.z = a3_pack(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
-                wd.w = a3_pack(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
-                dst[c] = wd;
+                for (int c = 0; c < HD / 8; ++c) {
+                  uint4 wd;
+                  wd.x = a3_pack(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+                  wd.y = a3_pack(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+                  wd.z = a3_pack(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+                  wd.w = a3_pack(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+                  dst[c] = wd;
+                }
               }
-            }
-          } else {
-            // four strip partials of row `lane` live in the four quadrants: merge through shared memory, then
-            // quadrant q finishes features [q HD/4, (q+1) HD/4) of the row
+            } else {
+              // four strip partials of row `lane` live in the four quadrants: merge through shared memory, then
+              // quadrant q finishes features [q HD/4, (q+1) HD/4) of the row
 #pragma unroll
-            for (int c = 0; c < HD; ++c) xbuf[q * XW + c * 32 + lane] = __uint_as_float(o[c]);
-            xbuf[q * XW + HD * 32 + lane] = ml.x;
-            xbuf[q * XW + (HD + 1) * 32 + lane] = ml.y;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            float mt = -1e30f;
+              for (int c = 0; c < HD; ++c) xbuf[q * XW + c * 32 + lane] = __uint_as_float(o[c]);
+              xbuf[q * XW + HD * 32 + lane] = ml.x;
+              xbuf[q * XW + (HD + 1) * 32 + lane] = ml.y;
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              float mt = -1e30f;
 #pragma unroll
-            for (int s = 0; s < 4; ++s) mt = fmaxf(mt, xbuf[s * XW + HD * 32 + lane]);
-            float wt[4], lt = 0.f;
+              for (int s = 0; s < 4; ++s) mt = fmaxf(mt, xbuf[s * XW + HD * 32 + lane]);
+              float wt[4], lt = 0.f;
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-              wt[s] = a3_ex2(xbuf[s * XW + HD * 32 + lane] - mt);
-              lt += xbuf[s * XW + (HD + 1) * 32 + lane] * wt[s];
-            }
-            const float inv = 1.f / lt;
-            float f[HD / 4];
-#pragma unroll
-            for (int c = 0; c < HD / 4; ++c) {
-              float acc = 0.f;
-#pragma unroll
-              for (int s = 0; s < 4; ++s) acc += xbuf[s * XW + (q * (HD / 4) + c) * 32 + lane] * wt[s];
-              f[c] = acc * inv;
-            }
-            if (qi < p.len) {
-              __half* dst = p.out + off0 + head * HD + q * (HD / 4);
-              if constexpr (HD == 32) {
-                uint4 wd;
-                wd.x = a3_pack(f[0], f[1]); wd.y = a3_pack(f[2], f[3]); wd.z = a3_pack(f[4], f[5]); wd.w = a3_pack(f[6], f[7]);
-                *reinterpret_cast<uint4*>(dst) = wd;
-              } else {
-                uint2 wd;
-                wd.x = a3_pack(f[0], f[1]); wd.y = a3_pack(f[2], f[3]);
-                *reinterpret_cast<uint2*>(dst) = wd;
+              for (int s = 0; s < 4; ++s) {
+                wt[s] = a3_ex2(xbuf[s * XW + HD * 32 + lane] - mt);
+                lt += xbuf[s * XW + (HD + 1) * 32 + lane] * wt[s];
               }
+              const float inv = 1.f / lt;
+              float f[HD / 4];
+#pragma unroll
+              for (int c = 0; c < HD / 4; ++c) {
+                float acc = 0.f;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) acc += xbuf[s * XW + (q * (HD / 4) + c) * 32 + lane] * wt[s];
+                f[c] = acc * inv;
+              }
+              if (qi < p.len) {
+                __half* dst = p.out + off0 + head * HD + q * (HD / 4);
+                if constexpr (HD == 32) {
+                  uint4 wd;
+                  wd.x = a3_pack(f[0], f[1]); wd.y = a3_pack(f[2], f[3]); wd.z = a3_pack(f[4], f[5]); wd.w = a3_pack(f[6], f[7]);
+                  *reinterpret_cast<uint4*>(dst) = wd;
+                } else {
+                  uint2 wd;
+                  wd.x = a3_pack(f[0], f[1]); wd.y = a3_pack(f[2], f[3]);
+                  *reinterpret_cast<uint2*>(dst) = wd;
+                }
+              }
+              asm volatile("bar.sync 1, 128;" ::: "memory");   // xbuf is reused by the next ragged read-out
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // xbuf is reused by the next ragged read-out
           }
         }
-        ++kg[pl];
-        // advance the walker to the next (tile, head pair): skip the remaining kv blocks of this one
-        for (int jj = 0; jj < p.nblk; ++jj) it[pl].next(p);
       }
     }
   } else {
@@ -448,51 +452,52 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
         }
       };
       // ---- P = exp2(s - reference) as packed fp16 over S in place, fp32 row sum.  The P of columns [c, c + 32)
-      // lands in packed columns [c / 2, c / 2 + 16): S columns that have been consumed already.
-      float sum = 0.f, sum1 = 0.f;
+      // lands in packed columns [c / 2, c / 2 + 16): S columns that have been consumed already.  One loop over the
+      // chunks (the last one may be partial) with a single call site of the reference check: code size matters here.
+      const int nchunk = nfull + (rem ? 1 : 0);
 #pragma unroll 1
-      for (int u = 0; u < nfull; ++u) {
-        tmem_ld_32x32b_x32(t_s + c0 + 32 * u, v);
-        tmem_ld_wait();
-        float cmax = -1e30f;
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) cmax = a3_max3(cmax, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-        check_reference(cmax, u);
-        uint32_t pk[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float e0 = a3_ex2(__uint_as_float(v[2 * e]) - mref);
-          const float e1 = a3_ex2(__uint_as_float(v[2 * e + 1]) - mref);
-          sum += e0; sum1 += e1;
-          pk[e] = a3_pack(e0, e1);
-        }
-        tmem_st_32x32b_x16(t_s + ((c0 + 32 * u) >> 1), pk);
-        l += sum + sum1;
-        sum = sum1 = 0.f;
-      }
-      if (rem) {
+      for (int u = 0; u < nchunk; ++u) {
+        const int cnt = u < nfull ? 32 : rem;
         if (!rag) {
-          tmem_ld_32x32b_x32(t_s + c0 + 32 * nfull, v);
+          tmem_ld_32x32b_x32(t_s + c0 + 32 * u, v);
           tmem_ld_wait();
         }
         float cmax = -1e30f;
+        if (cnt == 32) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) cmax = fmaxf(cmax, e < rem ? __uint_as_float(v[e]) : -1e30f);
-        check_reference(cmax, nfull);
+          for (int e = 0; e < 32; e += 2) cmax = a3_max3(cmax, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+        } else {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (rem > 16 * h) {
-            uint32_t pk[8];
+          for (int e = 0; e < 32; ++e) cmax = fmaxf(cmax, e < cnt ? __uint_as_float(v[e]) : -1e30f);
+        }
+        check_reference(cmax, u);
+        float sum = 0.f, sum1 = 0.f;
+        if (cnt == 32) {
+          uint32_t pk[16];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float e0 = a3_ex2(__uint_as_float(v[16 * h + 2 * e]) - mref);
-              float e1 = a3_ex2(__uint_as_float(v[16 * h + 2 * e + 1]) - mref);
-              e0 = (16 * h + 2 * e < rem) ? e0 : 0.f;
-              e1 = (16 * h + 2 * e + 1 < rem) ? e1 : 0.f;
-              sum += e0; sum1 += e1;
-              pk[e] = a3_pack(e0, e1);
+          for (int e = 0; e < 16; ++e) {
+            const float e0 = a3_ex2(__uint_as_float(v[2 * e]) - mref);
+            const float e1 = a3_ex2(__uint_as_float(v[2 * e + 1]) - mref);
+            sum += e0; sum1 += e1;
+            pk[e] = a3_pack(e0, e1);
+          }
+          tmem_st_32x32b_x16(t_s + ((c0 + 32 * u) >> 1), pk);
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (cnt > 16 * h) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float e0 = a3_ex2(__uint_as_float(v[16 * h + 2 * e]) - mref);
+                float e1 = a3_ex2(__uint_as_float(v[16 * h + 2 * e + 1]) - mref);
+                e0 = (16 * h + 2 * e < cnt) ? e0 : 0.f;
+                e1 = (16 * h + 2 * e + 1 < cnt) ? e1 : 0.f;
+                sum += e0; sum1 += e1;
+                pk[e] = a3_pack(e0, e1);
+              }
+              tmem_st_32x32b_x8(t_s + ((c0 + 32 * u + 16 * h) >> 1), pk);
             }
-            tmem_st_32x32b_x8(t_s + ((c0 + 32 * nfull + 16 * h) >> 1), pk);
           }
         }
         l += sum + sum1;

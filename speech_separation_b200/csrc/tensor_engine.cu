@@ -141,17 +141,20 @@ size_t carve_work(const vatss_model_desc* d, int B, int Tv, int L, int S, void* 
 
 }  // namespace
 
-bool tensor_engine_supports(const vatss_model_desc* d) {
-  if (d->H != 128) return false;
-  if (d->N != 128 && d->N != 64) return false;
-  if (d->kind == VATSS_KIND_DPRNN && d->N != 64) return false;   // hi/lo split LSTM exists for 64 input features
+// NULL when the tcgen05 kernels cover this model, else why they do not (reported once by the Python face: falling
+// back to the fp32 SIMT engine is a ~20x performance cliff and must not be silent)
+const char* tensor_engine_unsupported_reason(const vatss_model_desc* d) {
+  if (d->H != 128) return "hidden_dim != 128 (the persistent LSTM kernel holds 512 x (N + 128) fp16 weights per CTA pair)";
+  if (d->N != 128 && d->N != 64) return "num_features not in {64, 128}";
+  if (d->kind == VATSS_KIND_DPRNN && d->N != 64) return "DPRNN: the hi/lo split LSTM exists for num_features = 64 only";
   if (d->kind != VATSS_KIND_DPRNN) {
     const int hd = d->N / d->heads;
-    if (d->N % d->heads != 0 || (hd != 16 && hd != 32)) return false;
+    if (d->N % d->heads != 0 || (hd != 16 && hd != 32)) return "attention head dim not in {16, 32}";
   }
-  if (d->num_blocks > 32) return false;
-  return true;
+  if (d->num_blocks > 32) return "more than 32 dual-path blocks";
+  return nullptr;
 }
+bool tensor_engine_supports(const vatss_model_desc* d) { return tensor_engine_unsupported_reason(d) == nullptr; }
 
 size_t tensor_engine_packed_bytes(const vatss_model_desc* d) { return carve_packed(d, nullptr, nullptr); }
 

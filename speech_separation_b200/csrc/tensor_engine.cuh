@@ -5,6 +5,7 @@
 namespace vatss {
 
 bool tensor_engine_supports(const vatss_model_desc* d);
+const char* tensor_engine_unsupported_reason(const vatss_model_desc* d);   // NULL if supported
 size_t tensor_engine_packed_bytes(const vatss_model_desc* d);
 size_t tensor_engine_workspace_bytes(const vatss_model_desc* d, int B, int T, int Tv, int L, int S);
 int tensor_engine_pack(const vatss_model_desc* d, const float* const* params, void* packed, cudaStream_t st);

@@ -20,6 +20,7 @@ is out of scope, tensors come back detached.  Attention dropout
 in the reference's train() mode) is not applied.
 """
 import ctypes
+import warnings
 
 import torch
 from torch import nn
@@ -161,6 +162,11 @@ class _DualPathEncDec(nn.Module):
                 t = t.float().contiguous()
             keep.append(t)
             table[i] = t.data_ptr()
+        why = lib.vatss_engine_fallback_reason(ctypes.byref(self._desc))
+        if why is not None and not getattr(self, "_warned_fallback", False):
+            self._warned_fallback = True
+            warnings.warn(f"{type(self).__name__}: the tcgen05 tensor engine does not cover this model ({why.decode()}); "
+                          "running on the fp32 SIMT engine, which is roughly 20x slower", RuntimeWarning, stacklevel=3)
         nbytes = lib.vatss_packed_weight_bytes(ctypes.byref(self._desc))
         packed = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
         _lib.check(lib.vatss_pack_weights(ctypes.byref(self._desc), table, len(names), packed.data_ptr(),

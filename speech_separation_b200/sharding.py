@@ -2,8 +2,9 @@
 
 Utterances are independent in the forward pass, so rank r of W processes the contiguous range
 [r*n/W, (r+1)*n/W) with replicated weights and no data-path collective.  The only exchange is
-an all-reduce(sum) of a 9-element fp64 vector of SI-SNR sums (NCCL over NVLink on GPUs, gloo
-in the CPU tests).  Host-side logic only; the tensors it reduces are produced by
+an all-reduce(sum) of a 12-element fp64 vector (six per-pair SI-SNR sums, the per-utterance-PIT
+SI-SNRi sum, the count, four per-pair loss sums: 96 bytes, one `ncclAllReduce` over NVLink on GPUs,
+gloo in the CPU tests).  Host-side logic only; the tensors it reduces are produced by
 `vatss_pit_sisnr`.
 """
 import torch

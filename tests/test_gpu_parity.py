@@ -412,3 +412,18 @@ def test_micro_batched_shard_equals_single_batch(V):
     lo, hi = shard_range(6, 0, 1)
     part = separate_in_micro_batches(net, mix[lo:hi].to(dev()), e1[lo:hi].to(dev()), e2[lo:hi].to(dev()), micro_batch=4)
     assert torch.equal(full["s1_pred"], part["s1_pred"]) and torch.equal(full["s2_pred"], part["s2_pred"])
+
+
+def test_engine_fallback_is_loud(V, golden_dir):
+    """engine="auto" dropping to the fp32 SIMT engine is a ~20x performance cliff: it warns once, with the reason."""
+    import warnings
+
+    z, net = build_tiny(V, golden_dir, "dptn_wav")
+    with pytest.warns(RuntimeWarning, match="fp32 SIMT engine"):
+        run(net, "dptn_wav", torch.from_numpy(z["mix"]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")                       # second call: silent; production shapes: never
+        run(net, "dptn_wav", torch.from_numpy(z["mix"]))
+        mix, _, _, e1, e2 = make_inputs(1, 8000, Tv=12, E=512, seed=3)
+        run(prod_net(V, "dptn_av"), "dptn_av", mix, e1, e2)
+        run(prod_net(V, "dptn_av", "generic"), "dptn_av", mix, e1, e2)   # explicitly requested: no warning

@@ -215,7 +215,7 @@ void vatss_debug_lstm_trace(void* dev_buffer);
 void vatss_debug_cta_limit(int ctas);
 /* select the LSTM kernel of the plain fp16 path: 1 = two interleaved half tiles per CTA (default), 0 = one tile */
 void vatss_debug_lstm_pingpong(int on);
-/* select the tcgen05 attention kernel: 2 = P kept in TMEM (tc_attn2.cu, default), 1 = round-1 kernel (tc_attention.cu) */
+/* select the tcgen05 attention kernel: 3 = P and O kept in TMEM (tc_attn3.cu, default), 1 = round-1 kernel (tc_attention.cu) */
 void vatss_debug_attention_version(int v);
 int vatss_profile_begin(void);
 int vatss_profile_end(float* ms_per_stage, int* launches_per_stage, int n_stages);

@@ -647,7 +647,6 @@ int launch_attention_f16(const __half* qkv, __half* out, SeqMap map, int mode, i
   const int hd = N / heads;
   if (!force_simt && N % 64 == 0 && (hd == 16 || hd == 32)) {
     if (g_attention_version == 3) return launch_attention_v3(qkv, out, map, mode, B, S, C, N, heads, st);
-    if (g_attention_version == 2) return launch_attention_v2(qkv, out, map, mode, B, S, C, N, heads, st);
     bool handled = false;
     int rc = hd == 32 ? tc_attention_launch<32>(qkv, out, map, mode, B, S, C, N, st, &handled)
                       : tc_attention_launch<16>(qkv, out, map, mode, B, S, C, N, st, &handled);

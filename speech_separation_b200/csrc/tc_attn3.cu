@@ -4,11 +4,11 @@
 //
 // q arrives pre-scaled by log2(e)/sqrt(hd) (folded into the in-projection at weight-pack time): P = exp2(s - ref).
 //
-// What the two predecessors taught (profiles/r02_attn_*): v1 (tc_attention.cu, P through shared memory) and v2
-// (tc_attn2.cu, P in TMEM, two fat softmax warpgroups that also read out O) both sit at 0.22 - 0.32 of the MUFU floor.
-// Per (128-query x <= 96-key x head) job a softmax thread has ~640 cycles of MUFU work but ~2500 cycles of exposed
-// latency (TMEM round trips ~200 cycles each, mbarrier hand-offs, O read-out) - with two warps per scheduler neither
-// the MUFU pipe (40 %) nor the issue slots (45 %) are busy.  The cure is occupancy, and registers are what limits it:
+// Lineage (profiles/r02_attn*): v1 (tc_attention.cu, P through shared memory) and a first TMEM design with two fat
+// softmax warpgroups that also read out O ("v2", removed) both sat at 0.22 - 0.32 of the MUFU floor.  Per
+// (128-query x <= 96-key x head) job a softmax thread has ~640 cycles of MUFU work but ~2500 cycles of exposed latency
+// (TMEM round trips ~200 cycles each, mbarrier hand-offs, O read-out) - with two warps per scheduler neither the MUFU
+// pipe (40 %) nor the issue slots (45 %) are busy.  The cure is occupancy, and registers are what limits it:
 //   * softmax threads are LEAN (<= 80 registers): one 32-column TMEM chunk at a time, loaded ONCE (no separate
 //     maximum pass), no O state.  O is not read out per job: the P V MMAs of all kv blocks of a (query tile, head)
 //     accumulate in TMEM.  The reference is the maximum of the first 32-column chunk of the row; a later chunk only
@@ -25,6 +25,12 @@
 // its O accumulator at 384 + 32 sw.  A ragged last query tile (<= 32 rows) is loaded into all four lane quadrants;
 // quadrant q handles a strip of the kv block (zeros elsewhere in its P rows) and the epilogue merges the four partial
 // results (each with its own reference and row sum) through shared memory.
+// What still bounds it (tools/attn3_trace.py): S and P of a warpgroup share one TMEM slot, so S(i + 1) follows P V(i) and
+// every job ends with a ~2000-cycle round trip through the issuer (tcgen05 instructions cost ~100 cycles each to issue).
+// Tried and rejected: kv blocks of 64 keys with P in separate TMEM columns so that S(i + 1) is issued while job i is still
+// being exponentiated ("v4": 0.74 / 0.99 ms against 0.62 / 0.81 - more, smaller jobs load the issuer further); ping-pong
+// barriers between the two warpgroups of a pipeline (0.69 / 0.89); a second S slot per warpgroup needs 2 x 96 columns per
+// warpgroup and leaves room for two warpgroups only (0.81 / 1.06).
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tc_kernels.cuh"

@@ -40,11 +40,10 @@ int launch_pack_lstm(const float* Wih, const float* Whh, const float* bih, const
 int launch_attention_f16(const __half* qkv, __half* out, SeqMap map, int mode, int B, int S, int C, int N, int heads,
                          int force_simt, cudaStream_t st);
 
-// v2 of the tcgen05 attention core (P kept in TMEM, tc_attn2.cu); same contract, N % 64 == 0 and head dim 16 / 32 only
-int launch_attention_v2(const __half* qkv, __half* out, SeqMap map, int mode, int B, int S, int C, int N, int heads,
-                        cudaStream_t st);
+// v3 of the tcgen05 attention core (P and O kept in TMEM, four lean softmax warpgroups, tc_attn3.cu); same contract,
+// N % 64 == 0 and head dim 16 / 32 only
 int launch_attention_v3(const __half* qkv, __half* out, SeqMap map, int mode, int B, int S, int C, int N, int heads,
                         cudaStream_t st);
-extern int g_attention_version;   // 3 (default, tc_attn3.cu), 2 (tc_attn2.cu) or 1 (tc_attention.cu)
+extern int g_attention_version;   // 3 (default, tc_attn3.cu) or 1 (round-1 kernel, tc_attention.cu)
 
 }  // namespace vatss

@@ -1,22 +1,13 @@
-"""clock64 timeline of CTA 0 of the v2 attention kernel: 8 consecutive jobs of softmax warpgroup 0 (its softmax warp
-of quadrant 0, its MMA issuer and the epilogue warp of quadrant 0)."""
+"""clock64 timeline of CTA 0 of the attention kernel (tc_attn3.cu): 8 consecutive jobs of softmax warpgroup 0 (its
+softmax warp of quadrant 0 and the MMA issuer of its pipeline)."""
 import ctypes, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from speech_separation_b200 import _lib
 lib = _lib.load()
 dev = torch.device('cuda:0')
 def P(t): return ctypes.c_void_p(t.data_ptr())
-import argparse
-ap = argparse.ArgumentParser()
-ap.add_argument("--version", type=int, default=3)
-args = ap.parse_args()
-lib.vatss_debug_attention_version(args.version)
-if args.version == 2:
-    NAMES = ["s_full seen", "max done", "exp done", "P arrive", "pv: P seen", "-", "pv: issued", "-", "readout: O seen",
-             "readout: done", "S: begin", "S: kv full", "S: slot free", "S: issued", "tma: kv load issued"]
-else:
-    NAMES = ["s_full seen", "softmax done", "P arrived", "issuer: waits P", "issuer: P seen", "issuer: O free", "issuer: PV issued",
-             "issuer: next S issued", "softmax: waits S"]
+NAMES = ["s_full seen", "softmax done", "P arrived", "issuer: waits P", "issuer: P seen", "issuer: O free", "issuer: PV issued",
+         "issuer: next S issued", "softmax: waits S"]
 for mode, B, S, C in [(0, 32, 283, 150), (1, 32, 283, 150)]:
     N, heads = 128, 4
     torch.manual_seed(0)

@@ -188,12 +188,21 @@ int launch_fold_spk(const float* wfold, const float* Wspk, const float* bspk, in
   return 0;
 }
 
+// Round 2: the round-1 kernel (one frame per warp iteration, 2K full warp reductions of 5 shuffles each) moved 0.70 GB
+// in 0.65 ms = 0.17 of the HBM roof: 16 resident warps per SM with 1 KB in flight each, and 2K x 10 shuffle / add
+// instructions per frame.  Now every warp iteration covers FR = 4 consecutive frames with all of their gathers
+// (FR x 3 row loads) issued before the first use, and the 2K per-lane partial sums are reduced by a TRANSPOSING
+// butterfly: at step d a lane keeps the half of its values whose index bit matches its lane bit and receives the
+// partner's partials of that half (16 -> 8 -> 4 -> 2 -> 1 values, 16 shuffles instead of 2K x 5); after five steps
+// lane 2q holds output q.
 template <int N, int K>
 __global__ void __launch_bounds__(128)
 k_tail_fused(const __half* __restrict__ px, const float* __restrict__ enc, const float* __restrict__ w2,
              const float* __restrict__ c2, const float* __restrict__ wdT, const float* __restrict__ cfold, int S, int C,
              int P, int L, int padl, int Lo, long long frames, float* __restrict__ proj) {
   constexpr int CH = N / 32;   // channels per lane (4 or 2)
+  constexpr int FR = 4;        // frames per warp iteration
+  static_assert(2 * K <= 16, "the transposing reduction carries 16 values");
   const int lane = threadIdx.x & 31, n0 = lane * CH;
   float wa[2][K][CH], wd[K][CH];
 #pragma unroll
@@ -204,66 +213,107 @@ k_tail_fused(const __half* __restrict__ px, const float* __restrict__ enc, const
       wa[1][k][i] = w2[(K + k) * N + n0 + i];
       wd[k][i] = wdT[k * N + n0 + i];
     }
-  // lane k < 2K finally holds output (spk = k / K, k % K): its constants
-  const float cbias = lane < 2 * K ? c2[lane] : 0.f;
-  const float cconst = lane < 2 * K ? cfold[lane % K] : 0.f;
+  // lane 2q (q < 2K) finally holds output q = (spk = q / K, tap q % K): its constants
+  const int qout = lane >> 1;
+  const bool owner = (lane & 1) == 0 && qout < 2 * K;
+  const float cbias = owner ? c2[qout] : 0.f;
+  const float cconst = owner ? cfold[qout % K] : 0.f;
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long row = warp0; row < frames; row += nwarps) {
-    const int b = (int)(row / L);
-    const int t = (int)(row - (long long)b * L) - padl;
-    float o[CH], e[CH];
+  for (long long row0 = warp0 * FR; row0 < frames; row0 += nwarps * FR) {
+    float o[FR][CH], e[FR][CH];
+    int nrows[FR];
+    // ---- all gathers of the FR frames first
 #pragma unroll
-    for (int i = 0; i < CH; ++i) o[i] = 0.f;
-    if constexpr (CH == 4) {
-      const float4 v = *reinterpret_cast<const float4*>(enc + row * N + n0);
-      e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w;
-    } else {
-      const float2 v = *reinterpret_cast<const float2*>(enc + row * N + n0);
-      e[0] = v.x; e[1] = v.y;
-    }
-    int nrows = 0;
-    if (t >= 0 && t < Lo) {
-      int s_lo = t - C + 1 + P - 1;
-      s_lo = s_lo <= 0 ? 0 : s_lo / P;
-      int s_hi = t / P;
-      if (s_hi > S - 1) s_hi = S - 1;
-      nrows = s_hi - s_lo + 1;
-      for (int s = s_lo; s <= s_hi; ++s) {
-        const __half* src = px + (((long long)b * S + s) * C + (t - P * s)) * N + n0;
+    for (int f = 0; f < FR; ++f) {
+      const long long row = row0 + f;
+      nrows[f] = 0;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) { o[f][i] = 0.f; e[f][i] = 0.f; }
+      if (row < frames) {
+        const int b = (int)(row / L);
+        const int t = (int)(row - (long long)b * L) - padl;
         if constexpr (CH == 4) {
-          const uint2 v = *reinterpret_cast<const uint2*>(src);
-          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-          const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-          o[0] += a.x; o[1] += a.y; o[2] += c.x; o[3] += c.y;
+          const float4 v = __ldg(reinterpret_cast<const float4*>(enc + row * N + n0));
+          e[f][0] = v.x; e[f][1] = v.y; e[f][2] = v.z; e[f][3] = v.w;
         } else {
-          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(src));
-          o[0] += a.x; o[1] += a.y;
+          const float2 v = __ldg(reinterpret_cast<const float2*>(enc + row * N + n0));
+          e[f][0] = v.x; e[f][1] = v.y;
+        }
+        if (t >= 0 && t < Lo) {
+          int s_lo = t - C + 1 + P - 1;
+          s_lo = s_lo <= 0 ? 0 : s_lo / P;
+          int s_hi = t / P;
+          if (s_hi > S - 1) s_hi = S - 1;
+          nrows[f] = s_hi - s_lo + 1;
+          // two rows for the 50 % overlap of the reference configs: both loads are issued unconditionally (the second
+          // one re-reads the first row when there is only one) so that nothing depends on a data-dependent loop
+          const bool two = s_hi > s_lo;
+          const __half* src0 = px + (((long long)b * S + s_lo) * C + (t - P * s_lo)) * N + n0;
+          const __half* src1 = two ? px + (((long long)b * S + s_lo + 1) * C + (t - P * (s_lo + 1))) * N + n0 : src0;
+          const float w1 = two ? 1.f : 0.f;
+          if constexpr (CH == 4) {
+            const uint2 v0 = __ldg(reinterpret_cast<const uint2*>(src0));
+            const uint2 v1 = __ldg(reinterpret_cast<const uint2*>(src1));
+            const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&v0.x));
+            const float2 c0 = __half22float2(*reinterpret_cast<const __half2*>(&v0.y));
+            const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&v1.x));
+            const float2 c1 = __half22float2(*reinterpret_cast<const __half2*>(&v1.y));
+            o[f][0] = fmaf(w1, a1.x, a0.x); o[f][1] = fmaf(w1, a1.y, a0.y);
+            o[f][2] = fmaf(w1, c1.x, c0.x); o[f][3] = fmaf(w1, c1.y, c0.y);
+          } else {
+            const float2 a0 = __half22float2(__ldg(reinterpret_cast<const __half2*>(src0)));
+            const float2 a1 = __half22float2(__ldg(reinterpret_cast<const __half2*>(src1)));
+            o[f][0] = fmaf(w1, a1.x, a0.x); o[f][1] = fmaf(w1, a1.y, a0.y);
+          }
+          for (int s = s_lo + 2; s <= s_hi; ++s) {       // (more than two rows only for overlaps above 50 %)
+            const __half* src = px + (((long long)b * S + s) * C + (t - P * s)) * N + n0;
+            if constexpr (CH == 4) {
+              const uint2 v = __ldg(reinterpret_cast<const uint2*>(src));
+              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+              const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+              o[f][0] += a.x; o[f][1] += a.y; o[f][2] += c.x; o[f][3] += c.y;
+            } else {
+              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(src));
+              o[f][0] += a.x; o[f][1] += a.y;
+            }
+          }
         }
       }
     }
-    // per-lane partial sums of the 2K outputs, then a transposing butterfly: after the five steps lane q holds the
-    // full sum of output q (q < 2K)
-    float acc[2 * K];
+    // ---- per frame: per-lane partials of the 2K outputs, transposing butterfly, store
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      float pe = 0.f, p0 = 0.f, p1 = 0.f;
+    for (int f = 0; f < FR; ++f) {
+      float acc[16];
 #pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        pe = fmaf(wd[k][i], e[i], pe);
-        p0 = fmaf(wa[0][k][i], o[i], p0);
-        p1 = fmaf(wa[1][k][i], o[i], p1);
+      for (int k = 0; k < K; ++k) {
+        float pe = 0.f, p0 = 0.f, p1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          pe = fmaf(wd[k][i], e[f][i], pe);
+          p0 = fmaf(wa[0][k][i], o[f][i], p0);
+          p1 = fmaf(wa[1][k][i], o[f][i], p1);
+        }
+        acc[k] = p0 + pe;
+        acc[K + k] = p1 + pe;
       }
-      acc[k] = p0 + pe;
-      acc[K + k] = p1 + pe;
-    }
-    float outv = 0.f;
 #pragma unroll
-    for (int q = 0; q < 2 * K; ++q) {
-      const float v = warp_sum(acc[q]);
-      if (lane == q) outv = v;
+      for (int k = 2 * K; k < 16; ++k) acc[k] = 0.f;
+      // step d = 16, 8, 4, 2: keep the half selected by the lane bit, add the partner's partials of that half
+#pragma unroll
+      for (int h = 8; h >= 1; h >>= 1) {
+        const bool up = (lane & (2 * h)) != 0;       // lane bit 4, 3, 2, 1
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+          const float keep = up ? acc[h + i] : acc[i];
+          const float send = up ? acc[i] : acc[h + i];
+          acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * h);
+        }
+      }
+      const float outv = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 1);
+      const long long row = row0 + f;
+      if (owner && row < frames) proj[row * (2 * K) + qout] = outv + (float)nrows[f] * cbias + cconst;
     }
-    if (lane < 2 * K) proj[row * (2 * K) + lane] = outv + (float)nrows * cbias + cconst;
   }
 }
 
@@ -274,7 +324,7 @@ int launch_tail_fused(const __half* px, const float* enc, const float* w2, const
   if (frames == 0) return 0;
   const int Lo = (S - 1) * P + C;
   const int padl = (L - Lo) / 2;
-  const int blocks = (int)(ceil_div(frames, 4) < 148 * 16 ? ceil_div(frames, 4) : 148 * 16);
+  const int blocks = (int)(ceil_div(frames, 16) < 148 * 12 ? ceil_div(frames, 16) : 148 * 12);
 #define VATSS_TAIL_FUSED(NN, KK)                                                                                      \
   if (N == NN && K == KK) {                                                                                           \
     k_tail_fused<NN, KK><<<blocks, 128, 0, st>>>(px, enc, w2, c2, wdT, cfold, S, C, P, L, padl, Lo, frames, proj);    \

@@ -104,17 +104,18 @@ __device__ __forceinline__ uint32_t a3_pack(float lo, float hi) {
 template <int HPG, int STEP>
 struct A3Job {
   int item, m, hp, j, w, w0, stride;
-  uint32_t qn, kvn;
+  uint32_t qn, kst, kph;      // Q tiles consumed; K / V ring stage and phase of the current kv block (no divisions)
   bool valid;
   __device__ __forceinline__ void init(const Attn3Args& p, int pl, int first_w) {
     stride = 2 * gridDim.x;
     item = blockIdx.x + pl * gridDim.x;
-    m = hp = j = 0; w = w0 = first_w; qn = kvn = 0; valid = item < p.num_items;
+    m = hp = j = 0; w = w0 = first_w; qn = kst = kph = 0; valid = item < p.num_items;
   }
   __device__ __forceinline__ void next(const Attn3Args& p) {
     w += STEP;
     if (w < 2) return;
-    w = w0; ++kvn;
+    w = w0;
+    if (++kst == (uint32_t)p.nstg) { kst = 0; kph ^= 1u; }
     if (++j < p.nblk) return;
     j = 0;
     if (++hp < HPG / 2) return;
@@ -177,7 +178,7 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
       const int pl = warp - 20;
       const uint32_t sQ = base + pl * PLB, sKV = sQ + 2 * A3_QBYTES;
       const uint32_t q_full = bar_pl + 80 * pl, q_free = q_full + 16, kv_full = q_full + 32, kv_free = q_full + 56;
-      uint32_t qn = 0, kvn = 0;
+      uint32_t qn = 0, st = 0, ph = 0;
       for (int item = blockIdx.x + pl * gridDim.x; item < p.num_items; item += 2 * gridDim.x) {
         const int g = item / p.groups, grp = item - g * p.groups;
         const int colq = grp * 64, colk = p.N + grp * 64, colv = 2 * p.N + grp * 64;
@@ -199,12 +200,12 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
             load_rows(&tmapQ, sQ + qb * A3_QBYTES, q_full + 8 * qb, colq, m * 128);
           }
           for (int hp = 0; hp < HPG / 2; ++hp)
-            for (int j = 0; j < p.nblk; ++j, ++kvn) {
-              const uint32_t st = kvn % (uint32_t)p.nstg;
-              a3_wait(kv_free + 8 * st, ((kvn / (uint32_t)p.nstg) & 1) ^ 1);
+            for (int j = 0; j < p.nblk; ++j) {
+              a3_wait(kv_free + 8 * st, ph ^ 1);
               mbar_expect_tx(kv_full + 8 * st, 2 * KVB);
               load_rows(&tmapKV, sKV + st * 2 * KVB, kv_full + 8 * st, colk, j * p.NB);
               load_rows(&tmapKV, sKV + st * 2 * KVB + KVB, kv_full + 8 * st, colv, j * p.NB);
+              if (++st == (uint32_t)p.nstg) { st = 0; ph ^= 1u; }
             }
         }
       }
@@ -215,12 +216,15 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
     // Warp-uniform control flow, one elected lane issues (umma_*_warp).  Jobs alternate between the two warpgroups
     // of the pipeline; the S of a warpgroup's next job is issued right behind the P V of its current one.
     const int pl = __shfl_sync(0xffffffffu, warp, 0) - 22;
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    // The CTA owns all 512 TMEM columns, so the allocation starts at column 0, lane 0 (checked): with a literal base
+    // every tcgen05 operand of the issuer is computed from warp-uniform values (kernel parameters, blockIdx, loop
+    // counters) and ptxas can keep it in uniform registers instead of moving it over with R2UR before each MMA.
+    if (tmem != 0) __trap();
+    const uint32_t tmem_u = 0;
     const uint32_t sQ = base + pl * PLB, sKV = sQ + 2 * A3_QBYTES;
     const uint32_t q_full = bar_pl + 80 * pl, q_free = q_full + 16, kv_full = q_full + 32, kv_free = q_full + 56;
     const uint32_t idesc_s = idesc_f16(128, p.NB, 0);
     const uint32_t idesc_o = idesc_f16(128, HD, 0) | (1u << 16);      // B (= V) is MN-major
-    const uint32_t nstg = (uint32_t)p.nstg;
     A3Job<HPG, 1> si, pi;
     si.init(p, pl, 0); pi.init(p, pl, 0);
     uint32_t ip0 = 0, ip1 = 0;      // P V jobs issued per warpgroup
@@ -229,10 +233,10 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
       const uint32_t w = si.w, sw = 2 * pl + w, bsw = bar_sw + BSW * sw;
       const int head = 2 * si.hp + w;
       if (si.hp == 0 && si.j == 0 && w == 0) mbar_wait_warp(q_full + 8 * (si.qn & 1), (si.qn >> 1) & 1);
-      if (w == 0) mbar_wait_warp(kv_full + 8 * (si.kvn % nstg), (si.kvn / nstg) & 1);
+      if (w == 0) mbar_wait_warp(kv_full + 8 * si.kst, si.kph);
       tc_fence_after();
       const uint64_t qd = smem_desc_sw128_kmajor(sQ + (si.qn & 1) * A3_QBYTES) + ((uint32_t)(head * HD * 2) >> 4);
-      const uint64_t kd = smem_desc_sw128_kmajor(sKV + (si.kvn % nstg) * 2 * KVB) + ((uint32_t)(head * HD * 2) >> 4);
+      const uint64_t kd = smem_desc_sw128_kmajor(sKV + si.kst * 2 * KVB) + ((uint32_t)(head * HD * 2) >> 4);
 #pragma unroll
       for (int k16 = 0; k16 < HD / 16; ++k16)
         umma_f16_warp<1>(tmem_u + sw * A3_SLOT, qd + 2 * k16, kd + 2 * k16, idesc_s, k16 > 0 ? 1u : 0u);
@@ -252,7 +256,7 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
       if (pi.j == 0) mbar_wait_warp(bsw + 32, (k & 1) ^ 1);                             // o_free: previous group read out
       tc_fence_after();
       A3_MARK(sw == 0, i, 5);
-      const uint32_t vbase = sKV + (pi.kvn % nstg) * 2 * KVB + KVB + (uint32_t)(head * HD * 2);
+      const uint32_t vbase = sKV + pi.kst * 2 * KVB + KVB + (uint32_t)(head * HD * 2);
       const uint64_t vd = a3_desc_mnmajor(vbase);
       const int nv = min(p.NB, p.len - pi.j * p.NB);
       const int nk = (nv + 15) >> 4;                            // P columns beyond the sequence are never multiplied
@@ -264,7 +268,7 @@ k_tc_attn3(const __grid_constant__ CUtensorMap tmapQ, const __grid_constant__ CU
         umma_commit_warp(bsw + 24);                                                     // g_full
         if (w) ++kg1; else ++kg0;
       }
-      if (w == 1) umma_commit_warp(kv_free + 8 * (pi.kvn % nstg));                      // last MMA on this K / V stage
+      if (w == 1) umma_commit_warp(kv_free + 8 * pi.kst);                               // last MMA on this K / V stage
       A3_MARK(sw == 0, i, 6);
       if (w) ++ip1; else ++ip0;
       pi.next(p);

@@ -77,6 +77,7 @@ EXPORTS = {
     "vatss_debug_lstm_trace": (None, [ctypes.c_void_p]),
     "vatss_debug_cta_limit": (None, [ctypes.c_int]),
     "vatss_debug_lstm_pingpong": (None, [ctypes.c_int]),
+    "vatss_debug_lstm_groups": (None, [ctypes.c_int]),
     "vatss_debug_attention_version": (None, [ctypes.c_int]),
     "vatss_profile_begin": (ctypes.c_int, []),
     "vatss_profile_end": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int), ctypes.c_int]),

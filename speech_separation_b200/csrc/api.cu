@@ -429,6 +429,7 @@ int vatss_tc_attention(const void* qkv16, void* out16, int mode, int B, int S, i
 void vatss_debug_lstm_trace(void* dev_buffer) { vatss::g_lstm_trace = (long long*)dev_buffer; }
 void vatss_debug_cta_limit(int ctas) { vatss::g_cta_limit = ctas; }
 void vatss_debug_lstm_pingpong(int on) { vatss::g_lstm_pingpong = on; }
+void vatss_debug_lstm_groups(int groups) { vatss::g_lstm_groups = groups; }
 void vatss_debug_attention_version(int v) { vatss::g_attention_version = v == 1 ? 1 : 3; }
 
 unsigned long long vatss_launch_count(void) { return g_launches.load(); }

@@ -426,7 +426,27 @@ struct TcLstmPpSmem {
   static constexpr int TOTAL = OFF_BAR + 256;
 };
 
-template <int NFEAT, bool PRECISE, bool TRACE>
+//
+// GROUPS (row groups per CTA).  The gate math is MUFU-bound and a MUFU warp instruction costs the same whatever the
+// number of active lanes, so the unit of gate work is a ROW GROUP: 32 sequences = one warp-wide TMEM lane quadrant.
+// GROUPS = 4 is the tile above (slots (half, lane-half e) = four different groups).  When there are fewer groups than
+// 4 x SMs (the inter-chunk phase: 150 chunk positions x B utterances x 2 directions), a CTA takes only 3 or 2 groups
+// and a group occupies BOTH 32-row slots of a half tile: the TMA box is loaded twice, the recurrent state h is written
+// to both rows, so lanes 0-31 and 32-63 (and 64-95 / 96-127 for the other chunk of the pair) carry the same
+// pre-activations and the four lane quadrants = four SM sub-partitions share the group's hidden units (8 instead of 16
+// per thread and chunk).  Gate time per step is then proportional to GROUPS (3: half A = two groups, half B = one
+// duplicated group; 2: both halves duplicated) and the recurrence spreads over up to twice as many SMs.  Results are
+// bit-identical for every GROUPS (a row's accumulator does not depend on its neighbours).
+//   slot geometry for GROUPS < 4: slot (h, e) = rows h*64 + e*32 .. +31 of the CTA's operand tiles; a group is
+//   intra: 32 consecutive sequences, inter: Kc <= 32 chunk positions of one utterance (one TMA box per slot).
+template <int GROUPS>
+__device__ __forceinline__ int lstm_slot_group(int tile, int h, int e) {
+  if (GROUPS == 4) return tile * 4 + h * 2 + e;
+  if (GROUPS == 3) return tile * 3 + (h == 0 ? e : 2);
+  return tile * 2 + h;
+}
+
+template <int NFEAT, bool PRECISE, bool TRACE, int GROUPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
 k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapXlo,
              const __grid_constant__ CUtensorMap tmapW, TcLstmArgs p) {
@@ -510,7 +530,17 @@ k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
       uint32_t xfull_leader[2];
       for (int s = 0; s < 2; ++s)
         asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(xfull_leader[s]) : "r"(bar_xfull + 8 * s));
-      const uint32_t box_bytes = (p.mode == 0 ? 128 : p.Kc * p.Bc) * 128;
+      const uint32_t box_bytes = GROUPS == 4 ? (p.mode == 0 ? 128 : p.Kc * p.Bc) * 128
+                                             : 4 * (p.mode == 0 ? 32 : p.Kc) * 128;   // four slot boxes
+      int sa[4], sb[4];   // GROUPS < 4: per slot, intra: first sequence / inter: first chunk position and utterance
+      if constexpr (GROUPS < 4) {
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          const int gid = lstm_slot_group<GROUPS>(tile, sl >> 1, sl & 1);
+          if (p.mode == 0) { sa[sl] = gid * 32; sb[sl] = 0; }
+          else { sa[sl] = (gid % p.kblocks) * p.Kc; sb[sl] = gid / p.kblocks; }   // gid past the end: b >= B, zero fill
+        }
+      }
       for (int step = 0; step < len; ++step) {
         const int t = dir == 0 ? step : len - 1 - step;
         const int s = step & 1, n = step >> 1;
@@ -520,8 +550,16 @@ k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
           const uint32_t dst = sX + s * L::X_STAGE + kb * 16384;
           const CUtensorMap* tm = (PRECISE && kb == 1) ? &tmapXlo : &tmapX;   // k-block 1 = x_lo in PRECISE mode
           const int f0 = PRECISE ? 0 : kb * 64;
-          if (p.mode == 0) tma_load_4d_cg2(dst, tm, xfull_leader[s], f0, t, c0, 0);
-          else tma_load_4d_cg2(dst, tm, xfull_leader[s], f0, c1, t, c2);
+          if constexpr (GROUPS == 4) {
+            if (p.mode == 0) tma_load_4d_cg2(dst, tm, xfull_leader[s], f0, t, c0, 0);
+            else tma_load_4d_cg2(dst, tm, xfull_leader[s], f0, c1, t, c2);
+          } else {
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {
+              if (p.mode == 0) tma_load_4d_cg2(dst + sl * 4096, tm, xfull_leader[s], f0, t, sa[sl], 0);
+              else tma_load_4d_cg2(dst + sl * 4096, tm, xfull_leader[s], f0, sa[sl], t, sb[sl]);
+            }
+          }
         }
       }
     }
@@ -617,16 +655,31 @@ k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
     for (int h = 0; h < 2; ++h) {
       const int r = h * 64 + (q & 1) * 32 + lane;   // row inside this CTA's 128-row tile
       rrow[h] = r;
-      if (p.mode == 0) {
-        const long long g = (long long)c0 + r;
-        valid[h] = g < p.G;
-        row_base[h] = g * p.C;
-        row_tstride = 1;
+      if constexpr (GROUPS == 4) {
+        if (p.mode == 0) {
+          const long long g = (long long)c0 + r;
+          valid[h] = g < p.G;
+          row_base[h] = g * p.C;
+          row_tstride = 1;
+        } else {
+          const int bl = r / p.Kc, kl = r - bl * p.Kc;
+          valid[h] = (r < p.Kc * p.Bc) && (c2 + bl < p.B) && (c1 + kl < p.C);
+          row_base[h] = (long long)(c2 + bl) * p.S * p.C + (c1 + kl);
+          row_tstride = p.C;
+        }
       } else {
-        const int bl = r / p.Kc, kl = r - bl * p.Kc;
-        valid[h] = (r < p.Kc * p.Bc) && (c2 + bl < p.B) && (c1 + kl < p.C);
-        row_base[h] = (long long)(c2 + bl) * p.S * p.C + (c1 + kl);
-        row_tstride = p.C;
+        const int gid = lstm_slot_group<GROUPS>(tile, h, q & 1);
+        if (p.mode == 0) {
+          const long long g = (long long)gid * 32 + lane;
+          valid[h] = g < p.G;
+          row_base[h] = g * p.C;
+          row_tstride = 1;
+        } else {
+          const int bb = gid / p.kblocks, kk = (gid % p.kblocks) * p.Kc + lane;
+          valid[h] = (lane < p.Kc) && (kk < p.C) && (bb < p.B);
+          row_base[h] = (long long)bb * p.S * p.C + kk;
+          row_tstride = p.C;
+        }
       }
     }
     float cst[2][2][16];
@@ -650,6 +703,7 @@ k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
       long long* T = (trg && step >= 8 && step < 12) ? p.trace + (step - 8) * 32 + 8 : nullptr;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
+        const bool dup = GROUPS == 2 || (GROUPS == 3 && h == 1);   // this half holds one group twice (constant after unrolling)
         uint32_t hp[2][8];   // packed fp16 h of this half (kept until both pairs' recurrent MMAs have read sH)
 #pragma unroll
         for (int pr = 0; pr < 2; ++pr) {
@@ -663,19 +717,21 @@ k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
                          chunk * LSTM_UNITS_PER_CHUNK + hs * 16;
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
+            if (dup && sub == 1) break;   // a duplicated group: this lane half owns 8 of the 16 units, one pass
+            const int uo = dup ? (q & 1) * 8 : sub * 8;
             uint32_t gi[8], gf[8], gg[8], go[8];
-            tmem_ld_32x32b_x8(taddr + sub * 8 + 0, gi);
-            tmem_ld_32x32b_x8(taddr + sub * 8 + 32, gf);
-            tmem_ld_32x32b_x8(taddr + sub * 8 + 64, gg);
-            tmem_ld_32x32b_x8(taddr + sub * 8 + 96, go);
+            tmem_ld_32x32b_x8(taddr + uo + 0, gi);
+            tmem_ld_32x32b_x8(taddr + uo + 32, gf);
+            tmem_ld_32x32b_x8(taddr + uo + 64, gg);
+            tmem_ld_32x32b_x8(taddr + uo + 96, go);
             tmem_ld_wait();
-            if (sub == 1) {
+            if (sub == 1 || dup) {
               tc_fence_before();
               __syncwarp();
               if (lane == 0)
                 asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(accempty_leader[h * 2 + pr]) : "memory");
             }
-            const float4* b4 = reinterpret_cast<const float4*>(sBias + chunk * 128 + hs * 16 + sub * 8);
+            const float4* b4 = reinterpret_cast<const float4*>(sBias + chunk * 128 + hs * 16 + uo);
             float bi[8], bf[8], bg[8], bo[8];
             {
               const float4 i0 = b4[0], i1 = b4[1], f0 = b4[8], f1 = b4[9], g0 = b4[16], g1 = b4[17], o0 = b4[24], o1 = b4[25];
@@ -703,7 +759,7 @@ k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
               const __half2 o = p.act ? __floats2half2_rn(fmaxf(hv[2 * j], 0.f), fmaxf(hv[2 * j + 1], 0.f)) : a;
               ho[j] = *reinterpret_cast<const uint32_t*>(&o);
             }
-            if (valid[h]) *reinterpret_cast<uint4*>(orow + sub * 8) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+            if (valid[h]) *reinterpret_cast<uint4*>(orow + uo) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
             asm volatile("" ::: "memory");
           }
           if (T) T[3 * (h * 2 + pr) + 2] = clock64(); else asm volatile("" ::: "memory");
@@ -714,12 +770,23 @@ k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
           for (int pr = 0; pr < 2; ++pr) {
             const int k = (2 * pr + pc) * LSTM_UNITS_PER_CHUNK + hs * 16;   // hidden-unit index = K index of the h operand
             const int kb = k >> 6, ch = (k & 63) >> 3;
-            const uint32_t a0 = sH + kb * 16384 + sw128_offset((uint32_t)rrow[h], (uint32_t)ch);
-            const uint32_t a1 = sH + kb * 16384 + sw128_offset((uint32_t)rrow[h], (uint32_t)ch + 1);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(hp[pr][0]), "r"(hp[pr][1]),
-                         "r"(hp[pr][2]), "r"(hp[pr][3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(hp[pr][4]), "r"(hp[pr][5]),
-                         "r"(hp[pr][6]), "r"(hp[pr][7]) : "memory");
+            if (!dup) {
+              const uint32_t a0 = sH + kb * 16384 + sw128_offset((uint32_t)rrow[h], (uint32_t)ch);
+              const uint32_t a1 = sH + kb * 16384 + sw128_offset((uint32_t)rrow[h], (uint32_t)ch + 1);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(hp[pr][0]), "r"(hp[pr][1]),
+                           "r"(hp[pr][2]), "r"(hp[pr][3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(hp[pr][4]), "r"(hp[pr][5]),
+                           "r"(hp[pr][6]), "r"(hp[pr][7]) : "memory");
+            } else {
+              // this thread's 8 units of the sequence go to both copies of the row (slots e = 0 and e = 1)
+              const uint32_t che = (uint32_t)ch + (uint32_t)(q & 1);
+              const uint32_t a0 = sH + kb * 16384 + sw128_offset((uint32_t)(h * 64 + lane), che);
+              const uint32_t a1 = sH + kb * 16384 + sw128_offset((uint32_t)(h * 64 + 32 + lane), che);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(hp[pr][0]), "r"(hp[pr][1]),
+                           "r"(hp[pr][2]), "r"(hp[pr][3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(hp[pr][0]), "r"(hp[pr][1]),
+                           "r"(hp[pr][2]), "r"(hp[pr][3]) : "memory");
+            }
           }
           fence_proxy_async();
           __syncwarp();
@@ -737,19 +804,77 @@ k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
 }
 
 int g_lstm_pingpong = -1;   // -1: VATSS_LSTM_PINGPONG from the environment on first use (default 1); else 0 / 1
+int g_lstm_groups = -1;     // -1: VATSS_LSTM_GROUPS from the environment (default 0 = automatic); 2 / 3 / 4 force it
+
+// Row groups per CTA of k_tc_lstm_pp for `ngroups` groups per direction: the fewest machine waves x time per step.
+// Time per step measured on B200 (tools/lstm_groups_bench.py, 283 steps): 4.02 / 3.32 / 2.95 us for 4 / 3 / 2 groups -
+// about 0.54 us of gate math per group on top of the 64 M = 128 MMAs of a step, which cost the same for every GROUPS.
+static int pick_lstm_groups(int ngroups, int ndir) {
+  if (g_lstm_groups < 0) {
+    const char* e = getenv("VATSS_LSTM_GROUPS");
+    g_lstm_groups = e ? atoi(e) : 0;
+  }
+  if (g_lstm_groups >= 2 && g_lstm_groups <= 4) return g_lstm_groups;
+  const int sms = num_sms();
+  int best = 4;
+  long long best_cost = -1;
+  for (int g = 4; g >= 2; --g) {
+    const int tiles = (ngroups + g - 1) / g;
+    const int ctas = 2 * ((tiles + 1) / 2) * ndir;
+    const long long waves = (ctas + sms - 1) / sms;
+    const long long cost = waves * (g == 4 ? 4020 : g == 3 ? 3320 : 2950);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = g; }
+  }
+  return best;
+}
+
+template <int NFEAT, bool PRECISE, int GROUPS>
+static int tc_lstm_pp_launch(const CUtensorMap& tmX, const CUtensorMap& tmXlo, const CUtensorMap& tmW,
+                             const TcLstmArgs& a, cudaStream_t st) {
+  using LP = TcLstmPpSmem<NFEAT, PRECISE>;
+  static_assert(LP::TOTAL <= 227 * 1024, "shared memory budget");
+  auto kpp = a.trace ? k_tc_lstm_pp<NFEAT, PRECISE, true, GROUPS> : k_tc_lstm_pp<NFEAT, PRECISE, false, GROUPS>;
+  static PerDeviceOnce configured_pp;
+  if (configured_pp.first()) {
+    VATSS_CUDA_OK(cudaFuncSetAttribute(k_tc_lstm_pp<NFEAT, PRECISE, true, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL));
+    VATSS_CUDA_OK(cudaFuncSetAttribute(k_tc_lstm_pp<NFEAT, PRECISE, false, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL));
+  }
+  const int pairs_pp = (a.num_tiles + 1) / 2;
+  dim3 grid_pp(2 * pairs_pp, a.ndir);
+  kpp<<<grid_pp, LSTM_THREADS, LP::TOTAL, st>>>(tmX, tmXlo, tmW, a);
+  VATSS_LAUNCH_OK();
+  return 0;
+}
 
 template <int NFEAT, bool PRECISE, bool TRACE = false>
-static int tc_lstm_launch(const __half* x16, const __half* x16lo, const __half* Wpack, const TcLstmArgs& a,
+static int tc_lstm_launch(const __half* x16, const __half* x16lo, const __half* Wpack, TcLstmArgs a,
                           cudaStream_t st) {
   if (!TRACE && a.trace != nullptr) return tc_lstm_launch<NFEAT, PRECISE, true>(x16, x16lo, Wpack, a, st);
   using L = TcLstmSmem<NFEAT, PRECISE>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
+  if (g_lstm_pingpong < 0) {
+    const char* e = getenv("VATSS_LSTM_PINGPONG");
+    g_lstm_pingpong = e ? atoi(e) : 1;
+  }
+  // row groups per CTA (k_tc_lstm_pp only); groups < 4 use one TMA box per 32-row slot
+  int groups = 4;
+  if (g_lstm_pingpong) {
+    const int kc_s = a.mode == 0 ? 32 : (a.C + (a.C + 31) / 32 - 1) / ((a.C + 31) / 32);   // <= 32 chunk positions
+    const int kb_s = a.mode == 0 ? 1 : (a.C + kc_s - 1) / kc_s;
+    const int ngroups = a.mode == 0 ? (a.G + 31) / 32 : kb_s * a.B;
+    groups = pick_lstm_groups(ngroups, a.ndir);
+    // the 4-group tile of the inter phase packs Kc x Bc rows densely; keep it unless spreading was chosen
+    if (groups < 4) {
+      if (a.mode == 1) { a.Kc = kc_s; a.Bc = 1; a.kblocks = kb_s; }
+      a.num_tiles = (ngroups + groups - 1) / groups;
+    }
+  }
   CUtensorMap tmX, tmXlo, tmW;
   auto make_x = [&](CUtensorMap* tm, const __half* ptr) -> int {
     if (a.mode == 0) {
       const uint64_t dims[4] = {(uint64_t)NFEAT, (uint64_t)a.C, (uint64_t)a.G, 1};
       const uint64_t str[3] = {(uint64_t)NFEAT * 2, (uint64_t)a.C * NFEAT * 2, (uint64_t)a.G * a.C * NFEAT * 2};
-      const uint32_t box[4] = {64, 1, 128, 1};
+      const uint32_t box[4] = {64, 1, groups < 4 ? 32u : 128u, 1};
       return make_tmap_f16(tm, ptr, 4, dims, str, box);
     }
     const uint64_t dims[4] = {(uint64_t)NFEAT, (uint64_t)a.C, (uint64_t)a.S, (uint64_t)a.B};
@@ -766,26 +891,10 @@ static int tc_lstm_launch(const __half* x16, const __half* x16lo, const __half* 
     const uint32_t box[2] = {64, 64};
     if (make_tmap_f16(&tmW, Wpack, 2, dims, str, box)) return -1;
   }
-  {
-    if (g_lstm_pingpong < 0) {
-      const char* e = getenv("VATSS_LSTM_PINGPONG");
-      g_lstm_pingpong = e ? atoi(e) : 1;
-    }
-    if (g_lstm_pingpong) {
-      using LP = TcLstmPpSmem<NFEAT, PRECISE>;
-      static_assert(LP::TOTAL <= 227 * 1024, "shared memory budget");
-      auto kpp = a.trace ? k_tc_lstm_pp<NFEAT, PRECISE, true> : k_tc_lstm_pp<NFEAT, PRECISE, false>;
-      static PerDeviceOnce configured_pp;
-      if (configured_pp.first()) {
-        VATSS_CUDA_OK(cudaFuncSetAttribute(k_tc_lstm_pp<NFEAT, PRECISE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL));
-        VATSS_CUDA_OK(cudaFuncSetAttribute(k_tc_lstm_pp<NFEAT, PRECISE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL));
-      }
-      const int pairs_pp = (a.num_tiles + 1) / 2;
-      dim3 grid_pp(2 * pairs_pp, a.ndir);
-      kpp<<<grid_pp, LSTM_THREADS, LP::TOTAL, st>>>(tmX, tmXlo, tmW, a);
-      VATSS_LAUNCH_OK();
-      return 0;
-    }
+  if (g_lstm_pingpong) {
+    if (groups == 2) return tc_lstm_pp_launch<NFEAT, PRECISE, 2>(tmX, tmXlo, tmW, a, st);
+    if (groups == 3) return tc_lstm_pp_launch<NFEAT, PRECISE, 3>(tmX, tmXlo, tmW, a, st);
+    return tc_lstm_pp_launch<NFEAT, PRECISE, 4>(tmX, tmXlo, tmW, a, st);
   }
   auto kern = k_tc_lstm<NFEAT, PRECISE, TRACE>;
   static PerDeviceOnce configured;

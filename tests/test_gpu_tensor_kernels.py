@@ -342,8 +342,10 @@ def test_tc_lstm_kernels_agree_on_random_shapes(lib):
             wpack = torch.empty(ndir * 512 * ((2 * N if precise else N) + H), dtype=torch.float16, device=dev)
             bpack = torch.empty(ndir * 512, dtype=torch.float32, device=dev)
             outs = []
-            for pingpong in (0, 1):
+            # one-tile kernel, then the half-tile kernel with 4 / 3 / 2 row groups per CTA and its automatic choice
+            for pingpong, groups in ((0, 0), (1, 4), (1, 3), (1, 2), (1, 0)):
                 lib.vatss_debug_lstm_pingpong(pingpong)
+                lib.vatss_debug_lstm_groups(groups)
                 out = torch.full((B * S * C, ndir * H), float("nan"), dtype=torch.float16, device=dev)
                 rc = lib.vatss_tc_lstm(_p(x), _p(xlo) if precise else None, table, _p(out), mode, B, S, C, N, ndir, act,
                                        _p(wpack), _p(bpack), None)
@@ -351,9 +353,43 @@ def test_tc_lstm_kernels_agree_on_random_shapes(lib):
                 torch.cuda.synchronize()
                 outs.append(out)
             assert torch.isfinite(outs[0].float()).all()
-            assert torch.equal(outs[0], outs[1]), dict(mode=mode, N=N, ndir=ndir, precise=precise, B=B, S=S, C=C)
+            for k, o in enumerate(outs[1:]):
+                assert torch.equal(outs[0], o), dict(variant=k + 1, mode=mode, N=N, ndir=ndir, precise=precise, B=B, S=S, C=C)
     finally:
         lib.vatss_debug_lstm_pingpong(1)
+        lib.vatss_debug_lstm_groups(0)
+
+
+@pytest.mark.parametrize("groups", [2, 3])
+@pytest.mark.parametrize("mode,B,S,C,N,ndir,act", LSTM_CASES)
+def test_tc_lstm_spread_groups_match_dense_tiles(lib, mode, B, S, C, N, ndir, act, groups):
+    """k_tc_lstm_pp with 2 / 3 row groups per CTA (a group duplicated over both 32-row slots of a half tile, so that the
+    inter-chunk recurrence spreads over more SMs) is bit-identical to the dense 4-group tiles, partial groups included."""
+    from speech_separation_b200 import _lib
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(7 + mode + B + S + C)
+    H = 128
+    rnn = torch.nn.LSTM(N, H, batch_first=True, bidirectional=(ndir == 2))
+    names = ["weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"]
+    keep = [getattr(rnn, n + suf).detach().to(dev).contiguous() for suf in (["", "_reverse"][:ndir]) for n in names]
+    table = (ctypes.c_void_p * 8)(*([t.data_ptr() for t in keep] + [None] * (8 - len(keep))))
+    x = torch.randn(B, S, C, N, device=dev).half()
+    wpack = torch.empty(ndir * 512 * (N + H), dtype=torch.float16, device=dev)
+    bpack = torch.empty(ndir * 512, dtype=torch.float32, device=dev)
+    outs = []
+    try:
+        for g in (4, groups):
+            lib.vatss_debug_lstm_groups(g)
+            out = torch.full((B * S * C, ndir * H), float("nan"), dtype=torch.float16, device=dev)
+            rc = lib.vatss_tc_lstm(_p(x), None, table, _p(out), mode, B, S, C, N, ndir, act, _p(wpack), _p(bpack), None)
+            _lib.check(rc, "vatss_tc_lstm")
+            torch.cuda.synchronize()
+            outs.append(out)
+    finally:
+        lib.vatss_debug_lstm_groups(0)
+    assert torch.isfinite(outs[0].float()).all()
+    assert torch.equal(outs[0], outs[1])
 
 
 @pytest.mark.parametrize("mode,B,S,C", [(0, 2, 40, 25), (1, 3, 11, 250)])

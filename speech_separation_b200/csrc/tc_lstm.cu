@@ -75,7 +75,9 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+// sigmoid(2 x): the packed weights and biases of the i, f, o gates carry the factor 0.5 (exact in fp16 / fp32, see
+// k_pack_lstm), so the accumulator already holds half the pre-activation and the pre-scaling multiply is gone
+__device__ __forceinline__ float sigmoid_fast(float xh) { return fmaf(0.5f, tanh_fast(xh), 0.5f); }
 // ~1e-6-accurate variants (two MUFU ops each: ex2 + rcp) for the PRECISE kernel
 __device__ __forceinline__ float sigmoid_acc(float x) {
   float e, r;
@@ -956,6 +958,7 @@ int launch_tc_lstm(const __half* x16, const __half* x16lo, const __half* Wpack, 
 //   packed row (dir, rank, c, j): gate = 2*rank + j/32, unit = 32*c + j%32, source row = gate*128 + unit
 //   columns [0,N) = W_ih row, [N, N+128) = W_hh row
 //   bias_pack[dir][128*c + 32*gate + u] = b_ih + b_hh of (gate, unit 32*c+u)   (accumulator-column order)
+//   plain fp16 path (precise = 0): rows and biases of the sigmoid gates i, f, o are stored times 0.5 (sigmoid_fast)
 // ------------------------------------------------------------------------------------------
 __global__ void k_pack_lstm(const float* __restrict__ Wih, const float* __restrict__ Whh,
                             const float* __restrict__ bih, const float* __restrict__ bhh, int N, int dir, int precise,
@@ -966,6 +969,8 @@ __global__ void k_pack_lstm(const float* __restrict__ Wih, const float* __restri
   const int rank = prow / 256, c = (prow % 256) / 64, j = prow % 64;
   const int gate = 2 * rank + j / 32, unit = 32 * c + j % 32;
   const int src = gate * LSTM_H + unit;
+  // plain fp16 path: sigmoid(x) = 0.5 + 0.5 tanh(x / 2) - the halving of the i, f, o pre-activations is folded in here
+  const float gscale = (!precise && gate != 2) ? 0.5f : 1.0f;
   __half* dst = Wpack + ((size_t)dir * 512 + prow) * ktot;
   for (int k = threadIdx.x; k < ktot; k += blockDim.x) {
     float v;
@@ -974,9 +979,9 @@ __global__ void k_pack_lstm(const float* __restrict__ Wih, const float* __restri
       const float w = Wih[(size_t)src * N + (k - N)];
       v = w - __half2float(__float2half_rn(w));
     } else v = Whh[(size_t)src * LSTM_H + (k - nx)];
-    dst[k] = __float2half_rn(v);
+    dst[k] = __float2half_rn(v * gscale);
   }
-  if (threadIdx.x == 0) bias_pack[dir * 512 + 128 * c + 32 * gate + unit % 32] = bih[src] + bhh[src];
+  if (threadIdx.x == 0) bias_pack[dir * 512 + 128 * c + 32 * gate + unit % 32] = (bih[src] + bhh[src]) * gscale;
 }
 
 int launch_pack_lstm(const float* Wih, const float* Whh, const float* bih, const float* bhh, int N, int dir,

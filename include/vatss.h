@@ -218,6 +218,9 @@ void vatss_debug_lstm_pingpong(int on);
 /* row groups (32 sequences) per CTA of the half-tile LSTM kernel: 0 = automatic (fewest waves x gate time), 2 / 3 = a
  * group occupies both 32-row slots of a half tile so the recurrence spreads over more SMs, 4 = dense 128-row tiles */
 void vatss_debug_lstm_groups(int groups);
+/* fused tail of the post-conv heads: 1 = rows staged through shared memory by bulk copies (default where the chunk
+ * overlap is 50 %), 0 = the gather kernel (bit-identical results; cross-check) */
+void vatss_debug_tail_staged(int on);
 /* select the tcgen05 attention kernel: 3 = P and O kept in TMEM (tc_attn3.cu, default), 1 = round-1 kernel (tc_attention.cu) */
 void vatss_debug_attention_version(int v);
 int vatss_profile_begin(void);

@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvatss_b200.so")
+# VATSS_LIB_OVERRIDE: experiments only (tools/build_variant.sh) - another build of the same library
+LIB_PATH = os.environ.get("VATSS_LIB_OVERRIDE") or os.path.join(_HERE, "libvatss_b200.so")
 
 KIND = {"dptn_av": 0, "dptn_wav": 1, "dptn_mask": 2, "dprnn": 3}
 ENGINE = {"auto": 0, "generic": 1, "tensor": 2, "tensor-f16res": 3}
@@ -78,6 +79,7 @@ EXPORTS = {
     "vatss_debug_cta_limit": (None, [ctypes.c_int]),
     "vatss_debug_lstm_pingpong": (None, [ctypes.c_int]),
     "vatss_debug_lstm_groups": (None, [ctypes.c_int]),
+    "vatss_debug_tail_staged": (None, [ctypes.c_int]),
     "vatss_debug_attention_version": (None, [ctypes.c_int]),
     "vatss_profile_begin": (ctypes.c_int, []),
     "vatss_profile_end": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int), ctypes.c_int]),

@@ -2,7 +2,11 @@
 // ConvTranspose1d decoder.  HBM-bound row-streaming kernels.
 // Reference: src/model/dptn_wav.py:47-59,186-194; src/model/dptn.py:129-141,189;
 //            src/model/dprnn.py:145-163.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "ptx.cuh"
+#include "tc_kernels.cuh"
 
 namespace vatss {
 
@@ -317,6 +321,186 @@ k_tail_fused(const __half* __restrict__ px, const float* __restrict__ enc, const
   }
 }
 
+// ----------------------------------------------------------------------------------------
+// Staged form of k_tail_fused for the reference's 50 % overlap (C = 2 P).  k_tail_fused is latency-bound: its gathers
+// hang off 168-register threads (12 warps per SM, ncu: 29 % issue activity, long-scoreboard stalls, 0.22 of the HBM
+// roof).  Here the rows come through shared memory: a WORK UNIT is one hop of one utterance - the P frames
+// t in [j P, (j + 1) P) - whose sources are three CONTIGUOUS row ranges (the encoder frames, rows [P, 2P) of chunk
+// j - 1 and rows [0, P) of chunk j), fetched by a producer thread with three 1-D bulk copies (cp.async.bulk, mbarrier
+// completion) into a two-stage ring while the eight compute warps work on the previous unit: same per-frame
+// arithmetic as k_tail_fused (lane = 4 channels, folded weights in registers, transposing butterfly), no index
+// arithmetic per frame.  Units j = -1 and j = S + 1 carry the frames of the centred pad (encoder term only).
+// ----------------------------------------------------------------------------------------
+constexpr int TS_WARPS = 8;                 // compute warps
+constexpr int TS_THREADS = 32 * (TS_WARPS + 1);
+constexpr int TS_STAGES = 2;
+
+template <int N, int K>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+k_tail_staged(const __half* __restrict__ px, const float* __restrict__ enc, const float* __restrict__ w2,
+              const float* __restrict__ c2, const float* __restrict__ wdT, const float* __restrict__ cfold, int B, int S,
+              int P, int L, int padl, float* __restrict__ proj) {
+  using namespace ptx;
+  constexpr int CH = N / 32;
+  constexpr int FR = 4;
+  static_assert(2 * K <= 16, "the transposing reduction carries 16 values");
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t enc_bytes = (uint32_t)P * N * 4, px_bytes = (uint32_t)P * N * 2;
+  const uint32_t stage_bytes = enc_bytes + 2 * px_bytes;
+  const uint32_t base = smem_u32(smem);
+  const uint32_t bars = base + TS_STAGES * stage_bytes;      // full[TS_STAGES], empty[TS_STAGES]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = 2 * P;
+  const int upu = S + 3;                                      // units per utterance: j = -1 .. S + 1
+  const long long units = (long long)B * upu;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TS_STAGES; ++s) {
+      mbar_init(bars + 8 * s, 1);
+      mbar_init(bars + 8 * (TS_STAGES + s), TS_WARPS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  // unit u -> utterance b, hop j, its frames [l0, l0 + F) and the offset `off` of the first one inside the hop
+  auto unit_geometry = [&](long long u, int& b, int& j, int& l0, int& F, int& off) {
+    b = (int)(u / upu);
+    j = (int)(u - (long long)b * upu) - 1;
+    const int lb = padl + j * P;
+    l0 = lb < 0 ? 0 : lb;
+    const int le = lb + P < L ? lb + P : L;
+    F = le - l0;
+    off = l0 - lb;
+  };
+  if (warp == TS_WARPS) {
+    // ---------------------------------------------------------------- producer
+    if (lane == 0) {
+      int i = 0;
+      for (long long u = blockIdx.x; u < units; u += gridDim.x, ++i) {
+        const int s = i % TS_STAGES, ph = (i / TS_STAGES) & 1;
+        int b, j, l0, F, off;
+        unit_geometry(u, b, j, l0, F, off);
+        mbar_wait(bars + 8 * (TS_STAGES + s), ph ^ 1);
+        const bool lo_ok = j >= 1 && j <= S, hi_ok = j >= 0 && j <= S - 1;
+        const uint32_t fe = (uint32_t)F * N * 4, fp = (uint32_t)F * N * 2;
+        const uint32_t dst = base + s * stage_bytes;
+        mbar_expect_tx(bars + 8 * s, F > 0 ? fe + (lo_ok ? fp : 0) + (hi_ok ? fp : 0) : 0);
+        if (F > 0) {
+          bulk_load_1d(dst, enc + ((long long)b * L + l0) * N, fe, bars + 8 * s);
+          if (lo_ok) bulk_load_1d(dst + enc_bytes, px + (((long long)b * S + j - 1) * C + P + off) * N, fp, bars + 8 * s);
+          if (hi_ok) bulk_load_1d(dst + enc_bytes + px_bytes, px + (((long long)b * S + j) * C + off) * N, fp, bars + 8 * s);
+        }
+      }
+    }
+    return;
+  }
+  // ------------------------------------------------------------------ compute warps
+  const int n0 = lane * CH;
+  float wa[2][K][CH], wd[K][CH];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      wa[0][k][i] = w2[k * N + n0 + i];
+      wa[1][k][i] = w2[(K + k) * N + n0 + i];
+      wd[k][i] = wdT[k * N + n0 + i];
+    }
+  const int qout = lane >> 1;
+  const bool owner = (lane & 1) == 0 && qout < 2 * K;
+  const float cbias = owner ? c2[qout] : 0.f;
+  const float cconst = owner ? cfold[qout % K] : 0.f;
+  int it = 0;
+  for (long long u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+    const int s = it % TS_STAGES, ph = (it / TS_STAGES) & 1;
+    int b, j, l0, F, off;
+    unit_geometry(u, b, j, l0, F, off);
+    const bool lo_ok = j >= 1 && j <= S, hi_ok = j >= 0 && j <= S - 1;
+    const float nrows = (float)((lo_ok ? 1 : 0) + (hi_ok ? 1 : 0));
+    const unsigned char* st = smem + s * stage_bytes;
+    const float* sE = reinterpret_cast<const float*>(st);
+    const __half* sLo = reinterpret_cast<const __half*>(st + enc_bytes);
+    const __half* sHi = reinterpret_cast<const __half*>(st + enc_bytes + px_bytes);
+    mbar_wait(bars + 8 * s, ph);
+    // groups of FR frames, dealt round-robin with a per-unit rotation so that no warp always gets the extra group
+    const int ngroups = (F + FR - 1) / FR;
+    for (int g = (warp + it * 3) % TS_WARPS; g < ngroups; g += TS_WARPS) {
+      float o[FR][CH], e[FR][CH];
+#pragma unroll
+      for (int f = 0; f < FR; ++f) {
+        const int fi = g * FR + f;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) { o[f][i] = 0.f; e[f][i] = 0.f; }
+        if (fi < F) {
+          if constexpr (CH == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(sE + fi * N + n0);
+            e[f][0] = v.x; e[f][1] = v.y; e[f][2] = v.z; e[f][3] = v.w;
+            if (lo_ok) {
+              const uint2 r = *reinterpret_cast<const uint2*>(sLo + fi * N + n0);
+              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+              const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+              o[f][0] = a.x; o[f][1] = a.y; o[f][2] = c.x; o[f][3] = c.y;
+            }
+            if (hi_ok) {
+              const uint2 r = *reinterpret_cast<const uint2*>(sHi + fi * N + n0);
+              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+              const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+              o[f][0] += a.x; o[f][1] += a.y; o[f][2] += c.x; o[f][3] += c.y;
+            }
+          } else {
+            const float2 v = *reinterpret_cast<const float2*>(sE + fi * N + n0);
+            e[f][0] = v.x; e[f][1] = v.y;
+            if (lo_ok) {
+              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(sLo + fi * N + n0));
+              o[f][0] = a.x; o[f][1] = a.y;
+            }
+            if (hi_ok) {
+              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(sHi + fi * N + n0));
+              o[f][0] += a.x; o[f][1] += a.y;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < FR; ++f) {
+        float acc[16];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          float pe = 0.f, p0 = 0.f, p1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            pe = fmaf(wd[k][i], e[f][i], pe);
+            p0 = fmaf(wa[0][k][i], o[f][i], p0);
+            p1 = fmaf(wa[1][k][i], o[f][i], p1);
+          }
+          acc[k] = p0 + pe;
+          acc[K + k] = p1 + pe;
+        }
+#pragma unroll
+        for (int k = 2 * K; k < 16; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int h = 8; h >= 1; h >>= 1) {
+          const bool up = (lane & (2 * h)) != 0;
+#pragma unroll
+          for (int i = 0; i < h; ++i) {
+            const float keep = up ? acc[h + i] : acc[i];
+            const float send = up ? acc[i] : acc[h + i];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * h);
+          }
+        }
+        const float outv = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 1);
+        const int fi = g * FR + f;
+        if (owner && fi < F) proj[((long long)b * L + l0 + fi) * (2 * K) + qout] = outv + nrows * cbias + cconst;
+      }
+    }
+    // the stage was written by the async proxy and read with ordinary loads: order those reads before the bulk copy
+    // that the arrival allows
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + 8 * (TS_STAGES + s));   // this warp has finished reading the stage
+  }
+}
+
+int g_tail_staged = -1;   // -1: VATSS_TAIL_STAGED from the environment (default 1); 0 keeps the gather kernel (cross-check)
+
 // whole tail after the last dual-path block for the post-conv heads; returns 1 when (N, K) has no instance
 int launch_tail_fused(const __half* px, const float* enc, const float* w2, const float* c2, const float* wdT,
                       const float* cfold, int B, int S, int C, int P, int L, int N, int K, float* proj, cudaStream_t st) {
@@ -324,6 +508,32 @@ int launch_tail_fused(const __half* px, const float* enc, const float* w2, const
   if (frames == 0) return 0;
   const int Lo = (S - 1) * P + C;
   const int padl = (L - Lo) / 2;
+  // staged kernel: 50 % overlap, the centred pad fits one hop on either side, the ring fits shared memory
+  {
+    if (g_tail_staged < 0) { const char* e = getenv("VATSS_TAIL_STAGED"); g_tail_staged = e ? atoi(e) : 1; }
+    const int staged_on = g_tail_staged;
+    const size_t ring = (size_t)TS_STAGES * P * N * 8 + 64;
+    if (staged_on && C == 2 * P && padl >= 0 && padl <= P && L - padl - Lo >= 0 && L - padl - Lo <= P &&
+        ring <= 200 * 1024 && (P * N) % 8 == 0) {
+      const long long units = (long long)B * (S + 3);
+      const int grid = (int)(units < num_sms() ? units : num_sms());
+#define VATSS_TAIL_STAGED(NN, KK)                                                                                     \
+      if (N == NN && K == KK) {                                                                                       \
+        static PerDeviceOnce configured;                                                                              \
+        if (configured.first())                                                                                       \
+          VATSS_CUDA_OK(cudaFuncSetAttribute(k_tail_staged<NN, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                             200 * 1024));                                                            \
+        k_tail_staged<NN, KK><<<grid, TS_THREADS, ring, st>>>(px, enc, w2, c2, wdT, cfold, B, S, P, L, padl, proj);   \
+        VATSS_LAUNCH_OK();                                                                                            \
+        return 0;                                                                                                     \
+      }
+      VATSS_TAIL_STAGED(128, 7)
+      VATSS_TAIL_STAGED(64, 7)
+      VATSS_TAIL_STAGED(64, 2)
+      VATSS_TAIL_STAGED(128, 2)
+#undef VATSS_TAIL_STAGED
+    }
+  }
   const int blocks = (int)(ceil_div(frames, 16) < 148 * 12 ? ceil_div(frames, 16) : 148 * 12);
 #define VATSS_TAIL_FUSED(NN, KK)                                                                                      \
   if (N == NN && K == KK) {                                                                                           \

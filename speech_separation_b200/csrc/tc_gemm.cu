@@ -336,7 +336,55 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
       // (LayerNorm epilogues have one chunk per tile: slot / phase of chunk 0)
       const int as = (i * L::NCH) % L::ACC_SLOTS, aph = ((i * L::NCH) / L::ACC_SLOTS) & 1;
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + as * L::CH;
-      if constexpr (EPI == TC_EPI_F16 || EPI == TC_EPI_F32) {
+      if constexpr (EPI == TC_EPI_F16 && L::NCH > 1 && L::EPW == 8 && L::CH == 128) {
+        // Wide fp16 tile (QKV, 3 chunks of 128 columns): the two 32-column pieces a warp owns in a chunk are handled
+        // together - both tcgen05.ld in flight, one hand-back of the slot, both staging tiles (2 x 2 KB of this warp's
+        // staging area) written before one __syncwarp - so a warp exposes half as many TMEM / shared-memory round trips.
+        const int half = (warp - 2) >> 2;
+        uint32_t* st = reinterpret_cast<uint32_t*>(stage);
+        const int wsw = (lane >> 1) & 3;
+#pragma unroll 1
+        for (int ch = 0; ch < L::NCH; ++ch) {
+          const int jj = i * L::NCH + ch, cs = jj % L::ACC_SLOTS;
+          const int c0 = ch * L::CH + half * 32;          // pieces [c0, c0 + 32) and [c0 + 64, c0 + 96)
+          mbar_wait(bar_accfull + 8 * cs, (jj / L::ACC_SLOTS) & 1);
+          tc_fence_after();
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + cs * L::CH + half * 32, r0);
+          tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + cs * L::CH + half * 32 + 64, r1);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(bar_accempty + 8 * cs);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t a[4], b[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = 8 * j + 2 * e;
+              const __half2 ha = __floats2half2_rn(__uint_as_float(r0[c]) + sBias[c0 + c], __uint_as_float(r0[c + 1]) + sBias[c0 + c + 1]);
+              const __half2 hb = __floats2half2_rn(__uint_as_float(r1[c]) + sBias[c0 + 64 + c],
+                                                   __uint_as_float(r1[c + 1]) + sBias[c0 + 64 + c + 1]);
+              a[e] = *reinterpret_cast<const uint32_t*>(&ha);
+              b[e] = *reinterpret_cast<const uint32_t*>(&hb);
+            }
+            *reinterpret_cast<uint4*>(st + lane * 16 + ((j ^ wsw) << 2)) = make_uint4(a[0], a[1], a[2], a[3]);
+            *reinterpret_cast<uint4*>(st + 512 + lane * 16 + ((j ^ wsw) << 2)) = make_uint4(b[0], b[1], b[2], b[3]);
+          }
+          __syncwarp();
+          __half* g = p.out16 + row0 * p.ldo16 + c0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int r = k * 8 + (lane >> 2), c = lane & 3;
+            const uint4 x = *reinterpret_cast<const uint4*>(st + r * 16 + ((c ^ ((r >> 1) & 3)) << 2));
+            const uint4 y = *reinterpret_cast<const uint4*>(st + 512 + r * 16 + ((c ^ ((r >> 1) & 3)) << 2));
+            if (r < rows_valid) {
+              *reinterpret_cast<uint4*>(g + (long long)r * p.ldo16 + c * 8) = x;
+              *reinterpret_cast<uint4*>(g + (long long)r * p.ldo16 + 64 + c * 8) = y;
+            }
+          }
+          __syncwarp();
+        }
+      } else if constexpr (EPI == TC_EPI_F16 || EPI == TC_EPI_F32) {
         const int half = (warp - 2) >> 2;       // which of the (EPW / 4) warps of this lane quadrant
         int cur = -1;
 #pragma unroll 1

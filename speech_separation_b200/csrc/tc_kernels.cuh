@@ -14,6 +14,7 @@ int grid_cap();            // num_sms() or the debug cap set through vatss_debug
 extern int g_cta_limit;
 extern int g_lstm_pingpong;
 extern int g_lstm_groups;
+extern int g_tail_staged;
 extern long long* g_lstm_trace;   // debug trace buffer of k_tc_lstm (NULL in production)
 
 // out = A[M,K] (fp16, row pitch lda) x W[NOUT,K]^T (fp16) + bias, then

@@ -249,6 +249,29 @@ def test_forward_is_bitwise_repeatable(V, kind, B, T):
         assert torch.equal(a1, ref1) and torch.equal(a2, ref2)
 
 
+@pytest.mark.parametrize("kind,B,T", [("dptn_av", 3, 64000), ("dptn_av", 2, 16037), ("dptn_wav", 2, 32011), ("dprnn", 1, 32000)])
+def test_staged_tail_equals_gather_tail(V, kind, B, T):
+    """k_tail_staged (rows through shared memory by bulk copies, one hop of one utterance per work unit) against
+    k_tail_fused (per-frame gathers): same operands, same order of additions - bit-identical waveforms, including
+    the frames of the centred pad and lengths that leave a ragged last hop."""
+    from speech_separation_b200 import _lib
+
+    lib = _lib.load()
+    net = prod_net(V, kind)
+    Tv = 25 * T // 16000 if kind == "dptn_av" else None
+    mix, s1, s2, e1, e2 = make_inputs(B, T, Tv=Tv, E=PROD[kind].get("video_emb_size"), seed=7)
+    outs = []
+    try:
+        for staged in (0, 1):
+            lib.vatss_debug_tail_staged(staged)
+            a1, a2 = run(net, kind, mix, e1, e2)
+            outs.append((a1.clone(), a2.clone()))
+    finally:
+        lib.vatss_debug_tail_staged(1)
+    assert torch.isfinite(outs[0][0]).all()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_extra_batch_keys_are_ignored_and_errors_are_loud(V):
     net = prod_net(V, "dptn_wav")
     mix, *_ = make_inputs(1, 4000, seed=1)

@@ -13,45 +13,77 @@ namespace vatss {
 // visual compression: vis[b,t,j] = sum_e emb_{j/(N/2)}[b,e,t] * Wv[j%(N/2),e] + bv[j%(N/2)]
 // (nn.Linear(E, N/2) applied to both lip-embedding streams, then concat; dptn_wav.py:173-179)
 // ----------------------------------------------------------------------------------------
-// One CTA = (utterance b, stream, 32 video frames): the (E x 32) slab of the embedding is read with frames
-// contiguous (coalesced), W in 64-column slabs; each thread accumulates 8 outputs of one frame.
-constexpr int VC_T = 32, VC_E = 64;
+// One CTA = (utterance b, stream, 64 video frames) x 64 outputs, 256 threads with a 4 x 4 register tile each.  The
+// embedding slab arrives frames-contiguous (coalesced), W is transposed into [e][j] on the way into shared memory, so
+// both operands of the inner product are 16-byte shared-memory reads (2 reads per 16 FMAs; the round-1 kernel read
+// one W value per FMA and was bound by the shared-memory pipe: 108 us for 0.4 GFLOP).
+constexpr int VC_T = 64, VC_E = 32, VC_J = 64;
 __global__ void __launch_bounds__(256)
 k_visual_compress(const float* __restrict__ emb1, const float* __restrict__ emb2, const float* __restrict__ Wv,
                   const float* __restrict__ bv, int E, int Tv, int N, float* __restrict__ vis) {
-  __shared__ float sE[VC_E][VC_T + 1];
-  __shared__ float sW[64][VC_E + 1];
-  const int half = N / 2;                    // outputs per stream (<= 64 per pass)
+  __shared__ __align__(16) float sE[VC_E][VC_T];
+  __shared__ __align__(16) float sW[VC_E][VC_J + 4];
+  const int half = N / 2;                    // outputs per stream
   const int t0 = blockIdx.x * VC_T, which = blockIdx.y, b = blockIdx.z;
   const float* emb = (which == 0 ? emb1 : emb2) + (size_t)b * E * Tv;
-  const int tl = threadIdx.x & 31, jg = threadIdx.x >> 5;   // frame, group of 8 outputs
-  for (int j0 = 0; j0 < half; j0 += 64) {
-    float acc[8];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // frames 4 tx .. 4 tx + 3, outputs 4 ty .. 4 ty + 3
+  for (int j0 = 0; j0 < half; j0 += VC_J) {
+    float acc[4][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int e0 = 0; e0 < E; e0 += VC_E) {
-      for (int i = threadIdx.x; i < VC_E * VC_T; i += blockDim.x) {
-        const int e = i / VC_T, t = i - e * VC_T;
-        sE[e][t] = (e0 + e < E && t0 + t < Tv) ? emb[(size_t)(e0 + e) * Tv + t0 + t] : 0.f;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[i][k] = 0.f;
+    // global -> registers -> shared memory, the next slab's loads issued before this slab's arithmetic: every load of
+    // a slab is in flight at once (a load feeding a shared-memory store inside the copy loop exposed one full memory
+    // latency per element: that, not the arithmetic, was the 108 us)
+    constexpr int RE = VC_E * VC_T / 256, RW = VC_J * VC_E / 256;
+    float re[RE], rw[RW];
+    auto gload = [&](int e0) {
+#pragma unroll
+      for (int k = 0; k < RE; ++k) {
+        const int i = threadIdx.x + 256 * k, e = i / VC_T, t = i - e * VC_T;
+        re[k] = (e0 + e < E && t0 + t < Tv) ? __ldg(emb + (size_t)(e0 + e) * Tv + t0 + t) : 0.f;
       }
-      for (int i = threadIdx.x; i < 64 * VC_E; i += blockDim.x) {
-        const int j = i / VC_E, e = i - j * VC_E;
-        sW[j][e] = (j0 + j < half && e0 + e < E) ? Wv[(size_t)(j0 + j) * E + e0 + e] : 0.f;
+#pragma unroll
+      for (int k = 0; k < RW; ++k) {
+        const int i = threadIdx.x + 256 * k, j = i / VC_E, e = i - j * VC_E;
+        rw[k] = (j0 + j < half && e0 + e < E) ? __ldg(Wv + (size_t)(j0 + j) * E + e0 + e) : 0.f;
+      }
+    };
+    gload(0);
+    for (int e0 = 0; e0 < E; e0 += VC_E) {
+#pragma unroll
+      for (int k = 0; k < RE; ++k) {
+        const int i = threadIdx.x + 256 * k, e = i / VC_T, t = i - e * VC_T;
+        sE[e][t] = re[k];
+      }
+#pragma unroll
+      for (int k = 0; k < RW; ++k) {
+        const int i = threadIdx.x + 256 * k, j = i / VC_E, e = i - j * VC_E;
+        sW[e][j] = rw[k];
       }
       __syncthreads();
+      if (e0 + VC_E < E) gload(e0 + VC_E);
 #pragma unroll 8
       for (int e = 0; e < VC_E; ++e) {
-        const float x = sE[e][tl];
+        const float4 x = *reinterpret_cast<const float4*>(&sE[e][4 * tx]);
+        const float4 w = *reinterpret_cast<const float4*>(&sW[e][4 * ty]);
+        const float xs[4] = {x.x, x.y, x.z, x.w}, ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(sW[jg * 8 + i][e], x, acc[i]);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[i][k] = fmaf(ws[k], xs[i], acc[i][k]);
       }
       __syncthreads();
     }
-    if (t0 + tl < Tv) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int j = j0 + jg * 8 + i;
-        if (j < half) vis[((size_t)b * Tv + t0 + tl) * N + which * half + j] = acc[i] + bv[j];
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 + 4 * tx + i, j = j0 + 4 * ty;
+      if (t < Tv) {
+        float* dst = vis + ((size_t)b * Tv + t) * N + which * half + j;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (j + k < half) dst[k] = acc[i][k] + bv[j + k];
       }
     }
   }

@@ -331,7 +331,13 @@ k_tail_fused(const __half* __restrict__ px, const float* __restrict__ enc, const
 // arithmetic as k_tail_fused (lane = 4 channels, folded weights in registers, transposing butterfly), no index
 // arithmetic per frame.  Units j = -1 and j = S + 1 carry the frames of the centred pad (encoder term only).
 // ----------------------------------------------------------------------------------------
-constexpr int TS_WARPS = 8;                 // compute warps
+#ifndef TS_WARPS_N
+#define TS_WARPS_N 8
+#endif
+#ifndef TS_FR
+#define TS_FR 4
+#endif
+constexpr int TS_WARPS = TS_WARPS_N;        // compute warps
 constexpr int TS_THREADS = 32 * (TS_WARPS + 1);
 constexpr int TS_STAGES = 2;
 
@@ -342,7 +348,7 @@ k_tail_staged(const __half* __restrict__ px, const float* __restrict__ enc, cons
               int P, int L, int padl, float* __restrict__ proj) {
   using namespace ptx;
   constexpr int CH = N / 32;
-  constexpr int FR = 4;
+  constexpr int FR = TS_FR;
   static_assert(2 * K <= 16, "the transposing reduction carries 16 values");
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t enc_bytes = (uint32_t)P * N * 4, px_bytes = (uint32_t)P * N * 2;

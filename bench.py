@@ -215,7 +215,7 @@ def main():
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--total-utterances", type=int, default=0,
                     help="cfg-3: a fixed job of this many utterances, sharded over the ranks (strong scaling)")
-    ap.add_argument("--micro-batch", type=int, default=16)
+    ap.add_argument("--micro-batch", type=int, default=32)
     ap.add_argument("--loss", action="store_true", help="cfg-5: every step also computes the PIT SI-SNR loss")
     args = ap.parse_args()
 

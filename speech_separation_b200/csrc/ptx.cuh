@@ -112,6 +112,10 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > VATSS_MBAR_TIMEOUT_CYCLES) mbar_timeout(bar, parity);
   }
 }
+// warp-uniform probe (one vote): true when the phase has completed
+__device__ __forceinline__ bool mbar_try_wait_warp(uint32_t bar, uint32_t parity) {
+  return __all_sync(0xffffffffu, mbar_try_wait(bar, parity));
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait_cluster(bar, parity)) return;
   const long long t0 = clock64();

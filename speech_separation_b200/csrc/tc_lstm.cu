@@ -89,6 +89,40 @@ __device__ __forceinline__ float tanh_acc(float x) { return fmaf(2.0f, sigmoid_a
 template <bool PRECISE> __device__ __forceinline__ float act_sigmoid(float x) { return PRECISE ? sigmoid_acc(x) : sigmoid_fast(x); }
 template <bool PRECISE> __device__ __forceinline__ float act_tanh(float x) { return PRECISE ? tanh_acc(x) : tanh_fast(x); }
 
+// One LSTM cell from the four gate pre-activations (bias added); returns h, updates c.
+//   plain fp16 path: five tanh.approx (the i / f / o pre-activations arrive halved, see sigmoid_fast).
+//   PRECISE path: ex2 + rcp sigmoids would cost 10 MUFU operations per cell.  The four gate functions share ONE
+//   reciprocal instead (1 / (d_i d_f d_g d_o), each factor recovered with two multiplies), so a cell costs 4 ex2 + 1 rcp
+//   for the gates and ex2 + rcp for tanh(c): 7.  The exponents are clamped to 2^30 so that the product of four
+//   denominators stays finite (a gate below 2^-30 is returned as 2^-30).
+template <bool PRECISE>
+__device__ __forceinline__ float lstm_cell(float xi, float xf, float xg, float xo, float& c) {
+  if constexpr (!PRECISE) {
+    const float ig = sigmoid_fast(xi), fg = sigmoid_fast(xf), g_ = tanh_fast(xg), og = sigmoid_fast(xo);
+    const float cc = fmaf(fg, c, ig * g_);
+    c = cc;
+    return og * tanh_fast(cc);
+  } else {
+    constexpr float L2E = 1.4426950408889634f;
+    auto ex2c = [](float a) {
+      float e;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(a, 30.f)));
+      return e;
+    };
+    const float di = 1.f + ex2c(-L2E * xi), df = 1.f + ex2c(-L2E * xf);
+    const float dg = 1.f + ex2c(-2.f * L2E * xg), d_o = 1.f + ex2c(-L2E * xo);
+    const float p1 = di * df, p2 = dg * d_o;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p1 * p2));
+    const float r12 = r * p2, r34 = r * p1;                       // 1 / (d_i d_f), 1 / (d_g d_o)
+    const float ig = r12 * df, fg = r12 * di, og = r34 * dg;
+    const float g_ = fmaf(2.f, r34 * d_o, -1.f);                   // tanh(x_g) = 2 sigmoid(2 x_g) - 1
+    const float cc = fmaf(fg, c, ig * g_);
+    c = cc;
+    return og * tanh_acc(cc);
+  }
+}
+
 template <int NFEAT, bool PRECISE, bool TRACE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
 k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapXlo,
@@ -350,13 +384,8 @@ k_tc_lstm(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUt
           float hv[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float ig = act_sigmoid<PRECISE>(__uint_as_float(gi[j]) + bi[j]);
-            const float fg = act_sigmoid<PRECISE>(__uint_as_float(gf[j]) + bf[j]);
-            const float g_ = act_tanh<PRECISE>(__uint_as_float(gg[j]) + bg[j]);
-            const float og = act_sigmoid<PRECISE>(__uint_as_float(go[j]) + bo[j]);
-            const float cc = fmaf(fg, cst[c][sub * 8 + j], ig * g_);
-            cst[c][sub * 8 + j] = cc;
-            hv[j] = og * act_tanh<PRECISE>(cc);
+            hv[j] = lstm_cell<PRECISE>(__uint_as_float(gi[j]) + bi[j], __uint_as_float(gf[j]) + bf[j],
+                                       __uint_as_float(gg[j]) + bg[j], __uint_as_float(go[j]) + bo[j], cst[c][sub * 8 + j]);
           }
           uint32_t ho[4];
 #pragma unroll
@@ -745,13 +774,8 @@ k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
             float hv[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float ig = act_sigmoid<PRECISE>(__uint_as_float(gi[j]) + bi[j]);
-              const float fg = act_sigmoid<PRECISE>(__uint_as_float(gf[j]) + bf[j]);
-              const float g_ = act_tanh<PRECISE>(__uint_as_float(gg[j]) + bg[j]);
-              const float og = act_sigmoid<PRECISE>(__uint_as_float(go[j]) + bo[j]);
-              const float cc = fmaf(fg, cst[h][pr][sub * 8 + j], ig * g_);
-              cst[h][pr][sub * 8 + j] = cc;
-              hv[j] = og * act_tanh<PRECISE>(cc);
+              hv[j] = lstm_cell<PRECISE>(__uint_as_float(gi[j]) + bi[j], __uint_as_float(gf[j]) + bf[j],
+                                         __uint_as_float(gg[j]) + bg[j], __uint_as_float(go[j]) + bo[j], cst[h][pr][sub * 8 + j]);
             }
             uint32_t ho[4];
 #pragma unroll

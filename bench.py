@@ -338,10 +338,29 @@ def main():
             step_loss(out)
         return reduce_sisnr(sisnr_sums(rows, rows_loss)) if world > 1 else rows
 
+    # End-to-end step through the public nn.Module / metric API from PINNED HOST buffers.  Input copies are double
+    # buffered the way an evaluation loop over a DataLoader runs (speech_separation_b200.Inferencer): while step k
+    # computes, the inputs of step k + 1 travel host -> device on a second stream.  Every copy lies inside the timed
+    # region (step k's interval contains the copy for step k + 1; K steps contain K input copies and K output copies).
+    copy_stream = torch.cuda.Stream(dev)
+    pending = []
+
+    def issue_inputs():
+        with torch.cuda.stream(copy_stream):
+            ts = tuple(x.to(dev, non_blocking=True) for x in (mix_h, e1_h, e2_h))
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ts, ev
+
     def step_e2e():
-        m = mix_h.to(dev, non_blocking=True)
-        a = e1_h.to(dev, non_blocking=True)
-        b = e2_h.to(dev, non_blocking=True)
+        if not pending:
+            pending.append(issue_inputs())
+        (m, a, b), ev = pending.pop()
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for t in (m, a, b):
+            t.record_stream(cur)
+        pending.append(issue_inputs())
         out = fwd(m, a, b)
         out_h[0].copy_(out["s1_pred"], non_blocking=True)
         out_h[1].copy_(out["s2_pred"], non_blocking=True)
@@ -465,7 +484,8 @@ def main():
                     "h2d_bytes_per_step": int(mix_h.numel() + (e1_h.numel() + e2_h.numel() if av else 0)) * 4,
                     "d2h_bytes_per_step": int(2 * B * T) * 4 + 4,
                     "note": "bytes of rank 0; mixture + lip embeddings host->device and both separated waveforms + the "
-                            "metric device->host every step; the ground-truth sources s1, s2 (metric inputs only) stay resident"},
+                            "metric device->host every step; the ground-truth sources s1, s2 (metric inputs only) stay resident; "
+                            "the input copy of step k+1 runs on a second stream while step k computes (double-buffered, inside the timed region)"},
             "gpu_launches": int(launches), "roofline": roofline, "si_snri_db": snri, "wall_s_timed": wall}
     if world == 1 and not args.no_eager_baseline and not sharded_job:
         # the reference's own torch.nn modules on this GPU (cuDNN LSTM, fused MHA, cuBLAS; fp32 with

@@ -30,6 +30,9 @@ namespace vatss {
 
 using namespace ptx;
 
+#ifndef LSTM_PREFETCH
+#define LSTM_PREFETCH 1
+#endif
 constexpr int LSTM_H = 128;
 constexpr int LSTM_THREADS = 320;
 constexpr int LSTM_CHUNKS = 4;          // 4 x (32 units x 4 gates) = 512 accumulator columns
@@ -746,16 +749,41 @@ k_tc_lstm_pp(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
           const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + h * 256 + pr * 128 + hs * 16;
           __half* orow = p.out + (row_base[h] + (long long)t * row_tstride) * ldo + dir * LSTM_H +
                          chunk * LSTM_UNITS_PER_CHUNK + hs * 16;
+#if LSTM_PREFETCH
+          // The second 8-unit pass's accumulator loads are issued before the first pass's arithmetic: the two gate warps
+          // of a scheduler run in step (same barriers), so a tcgen05.ld round trip in front of every pass was exposed
+          // (~200 of the ~860 cycles of a pass).
+          uint32_t gq[2][4][8];
+          {
+            const int uo0 = dup ? (q & 1) * 8 : 0;
+            tmem_ld_32x32b_x8(taddr + uo0 + 0, gq[0][0]);
+            tmem_ld_32x32b_x8(taddr + uo0 + 32, gq[0][1]);
+            tmem_ld_32x32b_x8(taddr + uo0 + 64, gq[0][2]);
+            tmem_ld_32x32b_x8(taddr + uo0 + 96, gq[0][3]);
+            tmem_ld_wait();
+            if (!dup) {
+              tmem_ld_32x32b_x8(taddr + 8 + 0, gq[1][0]);
+              tmem_ld_32x32b_x8(taddr + 8 + 32, gq[1][1]);
+              tmem_ld_32x32b_x8(taddr + 8 + 64, gq[1][2]);
+              tmem_ld_32x32b_x8(taddr + 8 + 96, gq[1][3]);
+            }
+          }
+#endif
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
             if (dup && sub == 1) break;   // a duplicated group: this lane half owns 8 of the 16 units, one pass
             const int uo = dup ? (q & 1) * 8 : sub * 8;
+#if LSTM_PREFETCH
+            uint32_t (&gi)[8] = gq[sub][0], (&gf)[8] = gq[sub][1], (&gg)[8] = gq[sub][2], (&go)[8] = gq[sub][3];
+            if (sub == 1) tmem_ld_wait();
+#else
             uint32_t gi[8], gf[8], gg[8], go[8];
             tmem_ld_32x32b_x8(taddr + uo + 0, gi);
             tmem_ld_32x32b_x8(taddr + uo + 32, gf);
             tmem_ld_32x32b_x8(taddr + uo + 64, gg);
             tmem_ld_32x32b_x8(taddr + uo + 96, go);
             tmem_ld_wait();
+#endif
             if (sub == 1 || dup) {
               tc_fence_before();
               __syncwarp();

@@ -11,4 +11,4 @@ ncu --set full --clock-control none --import-source on --kernel-name regex:"k_tc
     --launch-skip 62 --launch-count 11 -f -o gpurun_out/r02_full_a python tools/profile_forward.py > gpurun_out/r02_ncu_full_a.log 2>&1
 ncu --set full --clock-control none --import-source on --kernel-name regex:"k_tail_staged|k_visual" \
     --launch-skip 2 --launch-count 2 -f -o gpurun_out/r02_full_b python tools/profile_forward.py > gpurun_out/r02_ncu_full_b.log 2>&1
-tail -2 gpurun_out/r02_ncu_full_a.log gpurun_out/r02_ncu_full_b.log
+tail -n 2 gpurun_out/r02_ncu_full_a.log; tail -n 2 gpurun_out/r02_ncu_full_b.log

@@ -290,7 +290,7 @@ def main():
 
     import speech_separation_b200 as V
     from speech_separation_b200 import _lib
-    from speech_separation_b200.sharding import reduce_sisnr, separate_in_micro_batches, shard_range, sisnr_sums
+    from speech_separation_b200.sharding import all_reduce_sisnr_sums, separate_in_micro_batches, shard_range, sisnr_sums
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -336,7 +336,9 @@ def main():
         rows, rows_loss, _ = V.pit_sisnr_all(out["s1_pred"], out["s2_pred"], s1, s2, mix)
         if args.loss:
             step_loss(out)
-        return reduce_sisnr(sisnr_sums(rows, rows_loss)) if world > 1 else rows
+        # N > 1: the NCCL all-reduce of the SI-SNR sums is issued every step, stream-ordered; the reduced vector stays on
+        # the device (an evaluation loop reads it once per partition, not once per batch)
+        return all_reduce_sisnr_sums(sisnr_sums(rows, rows_loss)) if world > 1 else rows
 
     # End-to-end step through the public nn.Module / metric API from PINNED HOST buffers.  Input copies are double
     # buffered the way an evaluation loop over a DataLoader runs (speech_separation_b200.Inferencer): while step k

@@ -51,16 +51,29 @@ def sisnr_sums(rows, rows_loss=None):
     return torch.cat(parts)
 
 
+def all_reduce_sisnr_sums(sums, group=None):
+    """The exchange step alone: all-reduce(sum) of the 12-element vector of `sisnr_sums`, result left ON THE DEVICE.
+
+    The collective is stream-ordered (the current stream waits for it, the host does not), so an evaluation loop can
+    issue it every step and read the metrics once per partition (`metrics_from_sums(t.tolist())`) instead of
+    synchronising the host with the GPU after every batch."""
+    sums = sums.clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    return sums
+
+
 def reduce_sisnr(sums, group=None):
-    """all-reduce(sum) the vector of `sisnr_sums` and derive the global metrics.
+    """all-reduce(sum) the vector of `sisnr_sums` and derive the global metrics (one host read).
 
     Returns dict with: si_snri_batch_pit (reference batch-level PIT over the GLOBAL batch),
     si_snri_utt_pit (mean of per-utterance PIT SI-SNRi), si_snr_batch_pit, loss_batch_pit, count.
     """
-    sums = sums.clone()
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    s = sums.tolist()
+    return metrics_from_sums(all_reduce_sisnr_sums(sums, group).tolist())
+
+
+def metrics_from_sums(s):
+    """Global metrics from the reduced 12-element vector (a Python list)."""
     n = s[7]
     m = [v / n for v in s[:6]]
     sep = max((m[0] + m[1]) / 2, (m[2] + m[3]) / 2)

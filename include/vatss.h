@@ -221,6 +221,9 @@ void vatss_debug_lstm_groups(int groups);
 /* fused tail of the post-conv heads: 1 = rows staged through shared memory by bulk copies (default where the chunk
  * overlap is 50 %), 0 = the gather kernel (bit-identical results; cross-check) */
 void vatss_debug_tail_staged(int on);
+/* 1 (default): the QKV and out-projection GEMMs walk their row tiles in reverse so that they start on the part of their
+ * input that the preceding kernel wrote last (L2 reuse); 0: every kernel walks forwards.  Same results. */
+void vatss_debug_gemm_l2_order(int on);
 /* select the tcgen05 attention kernel: 3 = P and O kept in TMEM (tc_attn3.cu, default), 1 = round-1 kernel (tc_attention.cu) */
 void vatss_debug_attention_version(int v);
 int vatss_profile_begin(void);

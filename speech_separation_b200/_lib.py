@@ -80,6 +80,7 @@ EXPORTS = {
     "vatss_debug_lstm_pingpong": (None, [ctypes.c_int]),
     "vatss_debug_lstm_groups": (None, [ctypes.c_int]),
     "vatss_debug_tail_staged": (None, [ctypes.c_int]),
+    "vatss_debug_gemm_l2_order": (None, [ctypes.c_int]),
     "vatss_debug_attention_version": (None, [ctypes.c_int]),
     "vatss_profile_begin": (ctypes.c_int, []),
     "vatss_profile_end": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int), ctypes.c_int]),

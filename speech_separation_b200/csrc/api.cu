@@ -431,6 +431,7 @@ void vatss_debug_cta_limit(int ctas) { vatss::g_cta_limit = ctas; }
 void vatss_debug_lstm_pingpong(int on) { vatss::g_lstm_pingpong = on; }
 void vatss_debug_lstm_groups(int groups) { vatss::g_lstm_groups = groups; }
 void vatss_debug_tail_staged(int on) { vatss::g_tail_staged = on; }
+void vatss_debug_gemm_l2_order(int on) { vatss::g_gemm_l2_order = on; }
 void vatss_debug_attention_version(int v) { vatss::g_attention_version = v == 1 ? 1 : 3; }
 
 unsigned long long vatss_launch_count(void) { return g_launches.load(); }

@@ -107,6 +107,7 @@ struct TcGemmArgs {
   __half* out16lo;   // optional: half(value - half(value)) (hi/lo split for the PRECISE LSTM), same pitch as out16
   int act16;  // activation applied to the fp16 copy only: 0 none, 1 relu, 2 prelu
   const float* prelu_a;
+  int reverse;   // walk the tiles from the last to the first (L2 reuse of the producer's most recent output)
 };
 
 // TMA warp, MMA warp and 8 epilogue warps: two warps per TMEM lane quadrant split the columns of the 128-row tile
@@ -273,7 +274,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
       for (int kb = 0; kb < L::KBW; ++kb)
         for (int n0 = 0; n0 < NOUT; n0 += 64) tma_load_2d(sW + kb * NOUT * 128 + n0 * 128, &tmapW, bar_w, kb * 64, n0);
       int i = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
+      for (int tile_i = blockIdx.x; tile_i < p.num_tiles; tile_i += gridDim.x, ++i) {
+        const int tile = p.reverse ? p.num_tiles - 1 - tile_i : tile_i;
         const int s = i % L::A_STAGES, ph = (i / L::A_STAGES) & 1;
         mbar_wait(bar_aempty + 8 * s, ph ^ 1);
         mbar_expect_tx(bar_afull + 8 * s, L::A_STAGE_BYTES);
@@ -329,7 +331,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
     float* stage = reinterpret_cast<float*>(gen + L::OFF_STAGE) + (warp - 2) * 32 * STG_LD;
     const float slope = (p.act16 == 2 && p.prelu_a) ? p.prelu_a[0] : 0.f;
     int i = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
+    for (int tile_i = blockIdx.x; tile_i < p.num_tiles; tile_i += gridDim.x, ++i) {
+      const int tile = p.reverse ? p.num_tiles - 1 - tile_i : tile_i;
       const long long row0 = (long long)tile * 128 + q * 32;          // first row of this warp
       const long long left = p.M - row0;
       const int rows_valid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
@@ -591,7 +594,7 @@ static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const
 int launch_tc_gemm(int epi, const __half* A, long long lda, const __half* W, const float* bias, const float* res,
                    long long ldr, const float* ln_w, const float* ln_b, float* out32, long long ldo32, __half* out16,
                    long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int KDIM,
-                   cudaStream_t st, __half* out16lo, int wsplit, const __half* res16, long long ldr16) {
+                   cudaStream_t st, __half* out16lo, int wsplit, const __half* res16, long long ldr16, int reverse) {
   if (M == 0) return 0;
   VATSS_CHECK_ARG(((uintptr_t)A & 15) == 0 && (lda * 2) % 16 == 0, "tc_gemm: A must be 16-byte aligned with 16-byte row pitch");
   TcGemmArgs a;
@@ -600,6 +603,7 @@ int launch_tc_gemm(int epi, const __half* A, long long lda, const __half* W, con
   a.bias = bias; a.res = res; a.ldr = ldr; a.res16 = res16; a.ldr16 = ldr16; a.ln_w = ln_w; a.ln_b = ln_b;
   a.out32 = out32; a.ldo32 = ldo32; a.out16 = out16; a.ldo16 = ldo16; a.act16 = act16; a.prelu_a = prelu_a;
   a.out16lo = out16lo;
+  a.reverse = reverse;
   if (epi == TC_EPI_F16) VATSS_CHECK_ARG(out16 != nullptr, "tc_gemm: fp16 output missing");
   if (epi == TC_EPI_F32) VATSS_CHECK_ARG(out32 != nullptr, "tc_gemm: fp32 output missing");
   if (epi == TC_EPI_LN || epi == TC_EPI_LN_POST)

@@ -15,6 +15,7 @@ extern int g_cta_limit;
 extern int g_lstm_pingpong;
 extern int g_lstm_groups;
 extern int g_tail_staged;
+extern int g_gemm_l2_order;
 extern long long* g_lstm_trace;   // debug trace buffer of k_tc_lstm (NULL in production)
 
 // out = A[M,K] (fp16, row pitch lda) x W[NOUT,K]^T (fp16) + bias, then
@@ -25,7 +26,11 @@ extern long long* g_lstm_trace;   // debug trace buffer of k_tc_lstm (NULL in pr
 int launch_tc_gemm(int epi, const __half* A, long long lda, const __half* W, const float* bias, const float* res,
                    long long ldr, const float* ln_w, const float* ln_b, float* out32, long long ldo32, __half* out16,
                    long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int KDIM, cudaStream_t st,
-                   __half* out16lo = nullptr, int wsplit = 0, const __half* res16 = nullptr, long long ldr16 = 0);
+                   __half* out16lo = nullptr, int wsplit = 0, const __half* res16 = nullptr, long long ldr16 = 0,
+                   int reverse = 0);
+// reverse = 1: the persistent CTAs walk the row tiles from the last to the first.  A consumer that starts where its
+// producer stopped finds the most recently written ~100 MB of its input still in the 126 MB L2 (FFN -> QKV reads x16,
+// attention -> out-projection reads att16).
 
 // Persistent LSTM recurrence on a CTA pair (tc_lstm.cu).  x16: token-major (B,S,C,NFEAT) fp16 activation,
 // Wpack / bias_pack from launch_pack_lstm, out16: (tokens, ndir*128) fp16 (relu(h) when act=1).

@@ -8,7 +8,14 @@
 
 #include "tc_kernels.cuh"
 
+#include <cstdlib>
+
 namespace vatss {
+
+// 1: the QKV and out-projection GEMMs walk their tiles in reverse, i.e. they start where their producers (FFN,
+// attention) stopped and read the tail of x16 / att16 from L2 (VATSS_GEMM_L2_ORDER=0 / vatss_debug_gemm_l2_order(0):
+// all kernels walk forwards).  Results do not depend on the order.
+int g_gemm_l2_order = -1;
 
 namespace {
 
@@ -169,6 +176,10 @@ int tensor_engine_pack(const vatss_model_desc* d, const float* const* params, vo
   const int N = d->N, H = d->H;
   const bool dprnn = d->kind == VATSS_KIND_DPRNN;
   int rc;
+  if (g_gemm_l2_order < 0) {
+    const char* e = getenv("VATSS_GEMM_L2_ORDER");
+    g_gemm_l2_order = e ? atoi(e) : 1;
+  }
   for (int blk = 0; blk < d->num_blocks; ++blk)
     for (int path = 0; path < 2; ++path) {
       const int ndir = (path == 0 || d->bidir) ? 2 : 1;
@@ -259,7 +270,7 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
         {
           StageScope sc(ST_QKV, st);
           if ((rc = launch_tc_gemm(TC_EPI_F16, w.xa16, N, s.win, s.bin, nullptr, 0, nullptr, nullptr, nullptr, 0,
-                                   w.qkv16, 3 * N, 0, nullptr, tok, 3 * N, N, st)))
+                                   w.qkv16, 3 * N, 0, nullptr, tok, 3 * N, N, st, nullptr, 0, nullptr, 0, g_gemm_l2_order)))
             return rc;
         }
         {
@@ -270,7 +281,7 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
           StageScope sc(ST_OUTPROJ_LN, st);
           if ((rc = launch_tc_gemm(TC_EPI_LN, w.att16, N, s.wout, sp(VATSS_S_OUTPROJ_B), f16res ? nullptr : w.xa32, N,
                                    sp(VATSS_S_LN1_W), sp(VATSS_S_LN1_B), y16res ? nullptr : w.xb32, N, w.xb16, N, 0, nullptr,
-                                   tok, N, N, st, nullptr, 0, f16res ? w.xa16 : nullptr, N)))
+                                   tok, N, N, st, nullptr, 0, f16res ? w.xa16 : nullptr, N, g_gemm_l2_order)))
             return rc;
         }
         {

@@ -80,19 +80,22 @@ def stage_flops(B, T, model="dptn_av"):
 
 
 def stage_bytes(B, T, model="dptn_av", f16res=False):
-    """Algorithmic HBM bytes per forward by stage (fp16 activations, fp32 block residual stream)."""
+    """Algorithmic HBM bytes per forward by stage (fp16 activations, block residual stream as an fp16 hi / lo pair)."""
     if model == "dprnn":
         return {}
     L, S = geometry(T)
     tok = B * S * 150
     N, H = (128, 128) if model == "dptn_av" else (64, 128)
-    x32 = 0 if f16res else 4 * N   # fp32 copy of the block residual (read by the out-projection, written by the FFN)
+    # block residual x: fp16 hi + fp16 lo pair (hi is the operand copy the projections read); the masking model keeps
+    # fp32 + fp16 copies, the fp16-stream engine only hi
+    lo = 0 if f16res else (4 * N if model == "dptn_mask" else 2 * N)   # bytes beyond the fp16 operand copy
+    res_read = 2 * N if f16res else (4 * N if model == "dptn_mask" else 4 * N)   # what the out-projection reads of x
     per_sub = {
         "qkv": 2 * N + 2 * 3 * N,                                  # x16 in, qkv16 out
         "attention": 2 * 3 * N + 2 * N,                            # qkv16 in, att16 out
-        "outproj_ln1": 2 * N + (x32 if x32 else 2 * N) + 2 * N,    # att16 + residual x in, y16 out
+        "outproj_ln1": 2 * N + res_read + 2 * N,                   # att16 + residual x (hi + lo) in, y16 out
         "lstm_recurrent": 2 * 2 * N + 2 * 2 * H,                   # y16 read by both directions, ReLU(h) fp16 out
-        "ffn_ln2": 2 * 2 * H + 2 * N + x32 + 2 * N,                # rnn16 + residual y16 in, x32 + x16 out
+        "ffn_ln2": 2 * 2 * H + 2 * N + lo + 2 * N,                 # rnn16 + residual y16 in, x lo + x16 (hi) out
     }
     return {k: 12 * tok * v for k, v in per_sub.items()}
 

@@ -97,6 +97,7 @@ struct TcGemmArgs {
   const float* res;
   long long ldr;
   const __half* res16;   // fp16 residual (RES16 instances): the same tensor the next operand is read from
+  const __half* res16lo; // RES16 = 2: second fp16 tensor, residual = res16 + res16lo (hi / lo split of an fp32 stream)
   long long ldr16;
   const float* ln_w;
   const float* ln_b;
@@ -119,7 +120,10 @@ constexpr int tcg_epilogue_warps(int fixed_bytes) { return fixed_bytes + 8 * 32 
 
 // WSPLIT: W is stored as [half(W) | half(W - half(W))] (hi/lo split, 2 x KDIM columns) and both halves are
 // contracted with the same A tile - used where an fp16-rounded weight misses the tolerance (DPRNN fc).
-template <int NOUT, int KDIM, bool RES_TMA = false, bool WSPLIT = false, bool RES16 = false>
+// RES16: 0 = fp32 residual, 1 = fp16 residual, 2 = fp16 hi + lo pair (the fp32 residual stream stored as
+// half(x) + half(x - half(x)): same bytes to read as fp32, but the producer writes 4 instead of 6 bytes per element
+// because the hi half IS the fp16 operand copy the next projection reads)
+template <int NOUT, int KDIM, bool RES_TMA = false, bool WSPLIT = false, int RES16 = 0>
 struct TcGemmSmem {
   static constexpr int KB = KDIM / 64;
   static constexpr int KBW = WSPLIT ? 2 * KB : KB;
@@ -127,7 +131,7 @@ struct TcGemmSmem {
   static constexpr int A_STAGE_BYTES = KB * 128 * 128;
   // residual tile [128 rows x NOUT fp32] as NOUT/32 column blocks of 128-byte rows (SWIZZLE_128B), TMA-prefetched
   // (RES16: NOUT/64 column blocks of 64 fp16 columns instead)
-  static constexpr int RES_BYTES = RES_TMA ? 128 * NOUT * (RES16 ? 2 : 4) : 0;
+  static constexpr int RES_BYTES = RES_TMA ? 128 * NOUT * (RES16 == 1 ? 2 : 4) : 0;
   static constexpr int A_STAGES = (W_BYTES + 2 * A_STAGE_BYTES + RES_BYTES + 24 * 1024 <= 227 * 1024) ? 2 : 1;
   static constexpr int OFF_W = 0;
   static constexpr int OFF_A = OFF_W + W_BYTES;
@@ -213,10 +217,10 @@ __device__ __forceinline__ void staged_store_f16(__half* __restrict__ g, long lo
   __syncwarp();
 }
 
-template <int NOUT, int KDIM, int EPI, bool WSPLIT, bool RES16>
+template <int NOUT, int KDIM, int EPI, bool WSPLIT, int RES16>
 __global__ void __launch_bounds__((TcGemmSmem<NOUT, KDIM, (EPI == TC_EPI_LN || EPI == TC_EPI_LN_POST), WSPLIT, RES16>::THREADS), 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapW,
-          const __grid_constant__ CUtensorMap tmapR, TcGemmArgs p) {
+          const __grid_constant__ CUtensorMap tmapR, const __grid_constant__ CUtensorMap tmapR2, TcGemmArgs p) {
   constexpr bool RES_TMA = (EPI == TC_EPI_LN || EPI == TC_EPI_LN_POST);   // residual tile prefetched by TMA
   using L = TcGemmSmem<NOUT, KDIM, RES_TMA, WSPLIT, RES16>;
   static_assert(NOUT % 16 == 0 && NOUT <= 512 && KDIM % 64 == 0, "shape");
@@ -287,6 +291,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
           constexpr int RCOLS = RES16 ? 64 : 32;   // columns per 128-byte-row block
           for (int cbk = 0; cbk < NOUT / RCOLS; ++cbk)
             tma_load_2d(sR + cbk * 16384, &tmapR, bar_rfull, cbk * RCOLS, tile * 128);
+          if constexpr (RES16 == 2)                // lo tile behind the hi tile
+            for (int cbk = 0; cbk < NOUT / 64; ++cbk)
+              tma_load_2d(sR + (NOUT / 64 + cbk) * 16384, &tmapR2, bar_rfull, cbk * 64, tile * 128);
         }
       }
     }
@@ -445,8 +452,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
           } else {
             const int col = cbase + c0;
 #pragma unroll
+            for (int part = 0; part < (RES16 == 2 ? 2 : 1); ++part)
+#pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const uint4 x = *reinterpret_cast<const uint4*>(gen + L::OFF_RES + (col / 64) * 16384 +
+              const uint4 x = *reinterpret_cast<const uint4*>(gen + L::OFF_RES + (part * (NOUT / 64) + col / 64) * 16384 +
                                                               sw128_offset((uint32_t)rr, (uint32_t)((col % 64) / 8 + c)));
               const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&x.x));
               const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&x.y));
@@ -549,18 +558,20 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
   if (warp == 1) tmem_dealloc<1>(tmem, L::TMEM_COLS);
 }
 
-template <int NOUT, int KDIM, int EPI, bool WSPLIT = false, bool RES16 = false>
+template <int NOUT, int KDIM, int EPI, bool WSPLIT = false, int RES16 = 0>
 static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const TcGemmArgs& args, cudaStream_t st) {
   constexpr bool RES_TMA = (EPI == TC_EPI_LN || EPI == TC_EPI_LN_POST);
   using L = TcGemmSmem<NOUT, KDIM, RES_TMA, WSPLIT, RES16>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
-  CUtensorMap tmA, tmW, tmR;
+  CUtensorMap tmA, tmW, tmR, tmR2;
   tmR = CUtensorMap();
+  tmR2 = CUtensorMap();
   if (RES_TMA && RES16) {
     const uint64_t dims[2] = {(uint64_t)NOUT, (uint64_t)args.M};
     const uint64_t str[1] = {(uint64_t)args.ldr16 * 2};
     const uint32_t box[2] = {64, 128};
     if (make_tmap_f16(&tmR, args.res16, 2, dims, str, box)) return -1;
+    if (RES16 == 2 && make_tmap_f16(&tmR2, args.res16lo, 2, dims, str, box)) return -1;
   } else if (RES_TMA) {
     const uint64_t dims[2] = {(uint64_t)NOUT, (uint64_t)args.M};
     const uint64_t str[1] = {(uint64_t)args.ldr * 4};
@@ -586,7 +597,7 @@ static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const
     VATSS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
   }
   const int grid = args.num_tiles < grid_cap() ? args.num_tiles : grid_cap();
-  kern<<<grid, L::THREADS, L::TOTAL, st>>>(tmA, tmW, tmR, args);
+  kern<<<grid, L::THREADS, L::TOTAL, st>>>(tmA, tmW, tmR, tmR2, args);
   VATSS_LAUNCH_OK();
   return 0;
 }
@@ -594,13 +605,14 @@ static int tc_gemm_launch(const __half* A, long long lda, const __half* W, const
 int launch_tc_gemm(int epi, const __half* A, long long lda, const __half* W, const float* bias, const float* res,
                    long long ldr, const float* ln_w, const float* ln_b, float* out32, long long ldo32, __half* out16,
                    long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int KDIM,
-                   cudaStream_t st, __half* out16lo, int wsplit, const __half* res16, long long ldr16, int reverse) {
+                   cudaStream_t st, __half* out16lo, int wsplit, const __half* res16, long long ldr16, int reverse,
+                   const __half* res16lo) {
   if (M == 0) return 0;
   VATSS_CHECK_ARG(((uintptr_t)A & 15) == 0 && (lda * 2) % 16 == 0, "tc_gemm: A must be 16-byte aligned with 16-byte row pitch");
   TcGemmArgs a;
   a.M = M;
   a.num_tiles = (int)((M + 127) / 128);
-  a.bias = bias; a.res = res; a.ldr = ldr; a.res16 = res16; a.ldr16 = ldr16; a.ln_w = ln_w; a.ln_b = ln_b;
+  a.bias = bias; a.res = res; a.ldr = ldr; a.res16 = res16; a.res16lo = res16lo; a.ldr16 = ldr16; a.ln_w = ln_w; a.ln_b = ln_b;
   a.out32 = out32; a.ldo32 = ldo32; a.out16 = out16; a.ldo16 = ldo16; a.act16 = act16; a.prelu_a = prelu_a;
   a.out16lo = out16lo;
   a.reverse = reverse;
@@ -612,8 +624,15 @@ int launch_tc_gemm(int epi, const __half* A, long long lda, const __half* W, con
   if (res16) {   // fp16 residual stream (DPTN sub-blocks)
     VATSS_CHECK_ARG(epi == TC_EPI_LN && !wsplit && ((uintptr_t)res16 & 15) == 0 && (ldr16 * 2) % 16 == 0,
                     "tc_gemm: fp16 residual needs the LayerNorm epilogue and 16-byte aligned rows");
+    if (res16lo) {   // residual = res16 + res16lo (out-projection of the DPTN sub-blocks)
+      VATSS_CHECK_ARG(((uintptr_t)res16lo & 15) == 0, "tc_gemm: lo residual must be 16-byte aligned");
+      if (NOUT == 128 && KDIM == 128) return tc_gemm_launch<128, 128, TC_EPI_LN, false, 2>(A, lda, W, a, st);
+      if (NOUT == 64 && KDIM == 64) return tc_gemm_launch<64, 64, TC_EPI_LN, false, 2>(A, lda, W, a, st);
+      set_error("tc_gemm: no hi/lo-residual instantiation for NOUT=%d K=%d", NOUT, KDIM);
+      return -1;
+    }
 #define TCG_CASE16(N_, K_) \
-  if (NOUT == N_ && KDIM == K_) return tc_gemm_launch<N_, K_, TC_EPI_LN, false, true>(A, lda, W, a, st);
+  if (NOUT == N_ && KDIM == K_) return tc_gemm_launch<N_, K_, TC_EPI_LN, false, 1>(A, lda, W, a, st);
     TCG_CASE16(128, 128)
     TCG_CASE16(128, 256)
     TCG_CASE16(64, 64)

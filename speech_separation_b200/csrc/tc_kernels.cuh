@@ -27,7 +27,7 @@ int launch_tc_gemm(int epi, const __half* A, long long lda, const __half* W, con
                    long long ldr, const float* ln_w, const float* ln_b, float* out32, long long ldo32, __half* out16,
                    long long ldo16, int act16, const float* prelu_a, long long M, int NOUT, int KDIM, cudaStream_t st,
                    __half* out16lo = nullptr, int wsplit = 0, const __half* res16 = nullptr, long long ldr16 = 0,
-                   int reverse = 0);
+                   int reverse = 0, const __half* res16lo = nullptr);
 // reverse = 1: the persistent CTAs walk the row tiles from the last to the first.  A consumer that starts where its
 // producer stopped finds the most recently written ~100 MB of its input still in the 126 MB L2 (FFN -> QKV reads x16,
 // attention -> out-projection reads att16).

@@ -16,6 +16,15 @@ namespace vatss {
 // attention) stopped and read the tail of x16 / att16 from L2 (VATSS_GEMM_L2_ORDER=0 / vatss_debug_gemm_l2_order(0):
 // all kernels walk forwards).  Results do not depend on the order.
 int g_gemm_l2_order = -1;
+// 1: DPTN residual stream x as an fp16 hi / lo pair (no fp32 copy); 0: fp32 + fp16 copies (VATSS_X16SPLIT, experiments)
+int g_x16split = -1;
+static bool x16split_enabled() {
+  if (g_x16split < 0) {
+    const char* e = getenv("VATSS_X16SPLIT");
+    g_x16split = e ? atoi(e) : 1;
+  }
+  return g_x16split != 0;
+}
 
 namespace {
 
@@ -125,11 +134,14 @@ size_t carve_work(const vatss_model_desc* d, int B, int Tv, int L, int S, void* 
   // fp32 residual stream: DPRNN keeps both ping-pong copies; the DPTN sub-blocks take the LayerNorm-1 output back as
   // fp16 (no xb32), and the fp16-stream variant drops the fp32 copy altogether
   const bool f16res = d->engine == VATSS_ENGINE_TENSOR_F16RES && !dprnn && !mask;
-  w.xa32 = b.take<float>(f16res ? 0 : tok * N);
+  // DPTN (not the masking model): the fp32 residual stream x is stored as the hi / lo fp16 pair (xa16, xa16lo) - xa16 is
+  // the operand copy the projections read anyway, so x costs 4 bytes per element to write instead of 6
+  const bool x16split = !dprnn && !mask && !f16res && x16split_enabled();
+  w.xa32 = b.take<float>((f16res || x16split) ? 0 : tok * N);
   w.xb32 = b.take<float>(dprnn || mask ? tok * N : 0);   // (the masking head keeps y in fp32, see forward)
   w.xa16 = b.take<__half>(tok * N);
   w.xb16 = b.take<__half>(tok * N);
-  w.xa16lo = b.take<__half>(dprnn ? tok * N : 0);   // lo halves of the hi/lo split LSTM input (DPRNN)
+  w.xa16lo = b.take<__half>((dprnn || x16split) ? tok * N : 0);   // lo halves: hi/lo split LSTM input (DPRNN), residual x (DPTN)
   w.xb16lo = b.take<__half>(dprnn ? tok * N : 0);
   w.qkv16 = b.take<__half>(dprnn ? 0 : tok * 3 * N);
   w.att16 = b.take<__half>(dprnn ? 0 : tok * N);
@@ -232,6 +244,7 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
   // the tanh x sigmoid masking head is the most sensitive consumer (7.2e-4 with the fp16 y, 9.1e-4 with the fp16
   // stream, 4.5e-4 without): it always keeps the fp32 residuals
   const bool y16res = d->kind != VATSS_KIND_DPTN_MASK;
+  const bool x16split = !dprnn && d->kind != VATSS_KIND_DPTN_MASK && !f16res && x16split_enabled();   // x = xa16 + xa16lo (carve_work)
   int rc;
   {
     StageScope sc(ST_FRONTEND, st);
@@ -243,7 +256,7 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
     }
     if ((rc = launch_encoder(mix, params[VATSS_P_ENCODER_W], av ? w.vis : nullptr, params[VATSS_P_GATE],
                              params[VATSS_P_VLN_W], params[VATSS_P_VLN_B], B, T, Tv, N, d->K, L, S, C, d->P, w.enc32,
-                             f16res ? nullptr : w.xa32, w.xa16, st, dprnn ? w.xa16lo : nullptr)))
+                             (f16res || x16split) ? nullptr : w.xa32, w.xa16, st, (dprnn || x16split) ? w.xa16lo : nullptr)))
       return rc;
   }
   for (int blk = 0; blk < d->num_blocks; ++blk)
@@ -279,9 +292,11 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
         }
         {
           StageScope sc(ST_OUTPROJ_LN, st);
-          if ((rc = launch_tc_gemm(TC_EPI_LN, w.att16, N, s.wout, sp(VATSS_S_OUTPROJ_B), f16res ? nullptr : w.xa32, N,
-                                   sp(VATSS_S_LN1_W), sp(VATSS_S_LN1_B), y16res ? nullptr : w.xb32, N, w.xb16, N, 0, nullptr,
-                                   tok, N, N, st, nullptr, 0, f16res ? w.xa16 : nullptr, N, g_gemm_l2_order)))
+          if ((rc = launch_tc_gemm(TC_EPI_LN, w.att16, N, s.wout, sp(VATSS_S_OUTPROJ_B),
+                                   (f16res || x16split) ? nullptr : w.xa32, N, sp(VATSS_S_LN1_W), sp(VATSS_S_LN1_B),
+                                   y16res ? nullptr : w.xb32, N, w.xb16, N, 0, nullptr, tok, N, N, st, nullptr, 0,
+                                   (f16res || x16split) ? w.xa16 : nullptr, N, g_gemm_l2_order,
+                                   x16split ? w.xa16lo : nullptr)))
             return rc;
         }
         {
@@ -290,9 +305,9 @@ int tensor_engine_forward(const vatss_model_desc* d, const float* const* params,
         }
         StageScope sc(ST_FFN_LN, st);
         if ((rc = launch_tc_gemm(TC_EPI_LN, w.rnn16, ndir * H, s.wffn, sp(VATSS_S_FFN_B), y16res ? nullptr : w.xb32, N,
-                                 sp(VATSS_S_LN2_W), sp(VATSS_S_LN2_B), (f16res || last) ? nullptr : w.xa32, N, w.xa16, N,
-                                 last ? 2 : 0, params[VATSS_P_PRELU], tok, N, ndir * H, st, nullptr, 0,
-                                 y16res ? w.xb16 : nullptr, N)))
+                                 sp(VATSS_S_LN2_W), sp(VATSS_S_LN2_B), (f16res || x16split || last) ? nullptr : w.xa32, N,
+                                 w.xa16, N, last ? 2 : 0, params[VATSS_P_PRELU], tok, N, ndir * H, st,
+                                 (x16split && !last) ? w.xa16lo : nullptr, 0, y16res ? w.xb16 : nullptr, N)))
           return rc;
       }
     }

@@ -217,6 +217,16 @@ __device__ __forceinline__ void staged_store_f16(__half* __restrict__ g, long lo
   __syncwarp();
 }
 
+// a += half(lo 16 bits of h2), b += half(hi 16 bits): sm_100a mixed-precision adds (SASS: FHADD R, R.H0 / R.H1, R)
+__device__ __forceinline__ void add_half2(float& a, float& b, uint32_t h2) {
+  asm("{\n\t.reg .b16 l, h;\n\t"
+      "mov.b32 {l, h}, %2;\n\t"
+      "add.rn.f32.f16 %0, l, %0;\n\t"
+      "add.rn.f32.f16 %1, h, %1;\n\t}"
+      : "+f"(a), "+f"(b)
+      : "r"(h2));
+}
+
 template <int NOUT, int KDIM, int EPI, bool WSPLIT, int RES16>
 __global__ void __launch_bounds__((TcGemmSmem<NOUT, KDIM, (EPI == TC_EPI_LN || EPI == TC_EPI_LN_POST), WSPLIT, RES16>::THREADS), 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapW,
@@ -457,12 +467,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUt
             for (int c = 0; c < 4; ++c) {
               const uint4 x = *reinterpret_cast<const uint4*>(gen + L::OFF_RES + (part * (NOUT / 64) + col / 64) * 16384 +
                                                               sw128_offset((uint32_t)rr, (uint32_t)((col % 64) / 8 + c)));
-              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&x.x));
-              const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&x.y));
-              const float2 cc = __half22float2(*reinterpret_cast<const __half2*>(&x.z));
-              const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&x.w));
-              v[c0 + 8 * c] += a.x; v[c0 + 8 * c + 1] += a.y; v[c0 + 8 * c + 2] += b.x; v[c0 + 8 * c + 3] += b.y;
-              v[c0 + 8 * c + 4] += cc.x; v[c0 + 8 * c + 5] += cc.y; v[c0 + 8 * c + 6] += d.x; v[c0 + 8 * c + 7] += d.y;
+              // mixed-precision add (add.rn.f32.f16 = one FHADD per value: no conversion instructions)
+              add_half2(v[c0 + 8 * c], v[c0 + 8 * c + 1], x.x);
+              add_half2(v[c0 + 8 * c + 2], v[c0 + 8 * c + 3], x.y);
+              add_half2(v[c0 + 8 * c + 4], v[c0 + 8 * c + 5], x.z);
+              add_half2(v[c0 + 8 * c + 6], v[c0 + 8 * c + 7], x.w);
             }
           }
         };

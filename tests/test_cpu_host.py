@@ -150,6 +150,14 @@ def _gloo_worker(rank, world, port, q):
     rows_loss = np.stack([O.sisnr_loss_rows(a, b) for a, b in pairs[:4]], axis=1)
     lo, hi = shard_range(n, rank, world)
     out = reduce_sisnr(sisnr_sums(torch.from_numpy(rows[lo:hi]), torch.from_numpy(rows_loss[lo:hi])))
+    # the stream-ordered form (vector left on the device, read once): two steps accumulate to twice the sums, and the
+    # metrics derived from them are those of the one-shot reduction
+    from speech_separation_b200.sharding import all_reduce_sisnr_sums, metrics_from_sums
+    red = all_reduce_sisnr_sums(sisnr_sums(torch.from_numpy(rows[lo:hi]), torch.from_numpy(rows_loss[lo:hi])))
+    acc = red + all_reduce_sisnr_sums(sisnr_sums(torch.from_numpy(rows[lo:hi]), torch.from_numpy(rows_loss[lo:hi])))
+    assert metrics_from_sums(red.tolist()) == out
+    twice = metrics_from_sums(acc.tolist())
+    assert twice["count"] == 2 * out["count"] and abs(twice["si_snri_batch_pit"] - out["si_snri_batch_pit"]) < 1e-12
     if rank == 0:
         q.put((out, O.pit_si_snri(s1p, s2p, s1, s2, mix), O.pit_sisnr_loss(s1p, s2p, s1, s2),
                float(np.mean(np.maximum((rows[:, 0] + rows[:, 1]) / 2, (rows[:, 2] + rows[:, 3]) / 2)

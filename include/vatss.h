@@ -229,6 +229,39 @@ void vatss_debug_attention_version(int v);
 int vatss_profile_begin(void);
 int vatss_profile_end(float* ms_per_stage, int* launches_per_stage, int n_stages);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Lipreader front end: the video feature extractor whose (512, Tv) embeddings the DPTN-AV model
+ * consumes.  Replaces, for modality="video", backbone_type="resnet", extract_feats=True:
+ *   Lipreading.forward(x, lengths)        src/lipreader/lipreading/model.py:252-273  (frontend3D :180-207, trunk = ResNet-18
+ *                                         src/lipreader/lipreading/models/resnet.py:31-145)
+ *   the "test" preprocessing pipeline     src/lipreader/lipreading/dataloaders.py:24-29 (Normalize(0,255), CenterCrop(88,88),
+ *                                         Normalize(0.421,0.165)) as an affine map + crop window folded into the first load
+ *   its callers                           make_embeddings.py:58-66, profiler.py:17-22, src/utils/init_utils.py:168-207
+ * Parameter table: host array of VATSS_LIP_NCONV * VATSS_LIP_PSLOTS device pointers (fp32), convolution-major:
+ *   conv 0            frontend3D.0 (Conv3d 64x1x5x7x7) with frontend3D.1 (BatchNorm3d) and frontend3D.2 (PReLU slopes, or NULL)
+ *   conv 1+3k, 2+3k   trunk.layer<l>.<b>.conv1 / conv2 with bn1 / bn2 and relu1 / relu2 slopes (PReLU only), k = 2(l-1)+b
+ *   conv 3+3k         trunk.layer<l>.<b>.downsample.0 / .1 (all six NULL where the block has no shortcut convolution)
+ *   slots per conv    weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, PReLU weight
+ * relu_type: 1 relu, 2 prelu, 3 swish (x * sigmoid(x), models/swish.py:10).  BatchNorm uses the running statistics
+ * (eval mode - the only mode the reference runs the lipreader in: make_embeddings.py:47).
+ * engine: VATSS_LIP_ENGINE_F32 = fp32 FMA-pipe implicit GEMM (exact to ~1e-6 against the fp32 reference);
+ *         VATSS_LIP_ENGINE_TENSOR = trunk convolutions on tcgen05 with fp16 activations, fp32 accumulation. */
+#define VATSS_LIP_NCONV 25
+#define VATSS_LIP_PSLOTS 6
+#define VATSS_LIP_ENGINE_F32 0
+#define VATSS_LIP_ENGINE_TENSOR 1
+size_t vatss_lipreader_packed_bytes(void);
+/* scratch for B x T frames cropped to Hc x Wc (frames are processed in chunks, so this is bounded) */
+size_t vatss_lipreader_workspace_bytes(int B, int T, int Hc, int Wc);
+/* fold BatchNorm into per-channel scale / shift and re-lay the convolution weights (tap-major fp32, K-major fp16) */
+int vatss_lipreader_pack_weights(const float* const* params, int n_params, int relu_type, void* packed,
+                                 size_t packed_bytes, void* stream);
+/* video (B, T, Hin, Win) f32 -> out (B, T, 512) f32.  The network sees
+ * video[:, :, y0:y0+Hc, x0:x0+Wc] * pre_scale + pre_shift (pass 0, 0, Hin, Win, 1, 0 for already preprocessed input). */
+int vatss_lipreader_forward(const void* packed, size_t packed_bytes, int relu_type, const float* video, int B, int T,
+                            int Hin, int Win, int y0, int x0, int Hc, int Wc, float pre_scale, float pre_shift,
+                            float* out, void* workspace, size_t workspace_bytes, int engine, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

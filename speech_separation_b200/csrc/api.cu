@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "tensor_engine.cuh"
 #include "tc_kernels.cuh"
+#include "lipreader.cuh"
 
 namespace vatss {
 
@@ -474,6 +475,19 @@ int vatss_pit_sisnr(const float* s1p, const float* s2p, const float* s1, const f
   StageScope sc(ST_SISNR, (cudaStream_t)stream);
   return launch_pit_sisnr(s1p, s2p, s1, s2, mix, B, T, rows_out, rows_loss_out, summary_out, scratch,
                           (cudaStream_t)stream);
+}
+
+size_t vatss_lipreader_packed_bytes(void) { return lip_packed_bytes(); }
+size_t vatss_lipreader_workspace_bytes(int B, int T, int Hc, int Wc) { return lip_workspace_bytes(B, T, Hc, Wc); }
+int vatss_lipreader_pack_weights(const float* const* params, int n_params, int relu_type, void* packed,
+                                 size_t packed_bytes, void* stream) {
+  return lip_pack(params, n_params, relu_type, packed, packed_bytes, (cudaStream_t)stream);
+}
+int vatss_lipreader_forward(const void* packed, size_t packed_bytes, int relu_type, const float* video, int B, int T,
+                            int Hin, int Win, int y0, int x0, int Hc, int Wc, float pre_scale, float pre_shift,
+                            float* out, void* workspace, size_t workspace_bytes, int engine, void* stream) {
+  return lip_forward(packed, packed_bytes, relu_type, video, B, T, Hin, Win, y0, x0, Hc, Wc, pre_scale, pre_shift, out,
+                     workspace, workspace_bytes, engine, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,466 @@
+// Lipreader front end: the video feature extractor that produces the (512, Tv) lip embeddings
+// the DPTN-AV model consumes - `Lipreading(modality="video", backbone_type="resnet", extract_feats=True)`,
+// reference src/lipreader/lipreading/model.py:252-273 (forward), :180-207 (frontend3D), models/resnet.py:31-145
+// (BasicBlock / ResNet-18 trunk), called from make_embeddings.py:58-66 and profiler.py:17-22.
+//
+//   video (B, T, Hin, Win) --crop + affine (dataloaders.py:24-27)--> (B, 1, T, 88, 88)
+//     Conv3d(1->64, 5x7x7, stride 1x2x2, pad 2x3x3) + BatchNorm3d (eval) + act        -> (F, 44, 44, 64)   F = B T
+//     MaxPool3d(1x3x3, stride 1x2x2, pad 0x1x1)                                        -> (F, 22, 22, 64)
+//     8 BasicBlocks: act(bn2(conv2(act(bn1(conv1 x)))) + shortcut(x)), widths 64/128/256/512, stride 2 from layer2 on,
+//       shortcut = 1x1 stride-2 conv + BN where the shape changes                      -> (F, 3, 3, 512)
+//     AdaptiveAvgPool2d(1)                                                             -> (B, T, 512)
+//
+// Layout: activations are PIXEL-MAJOR (frame, y, x, channel) - one row of channels per pixel, like the token-major
+// rows of the separation path - so a convolution is a GEMM over (pixels) x (taps x input channels) whose A rows are
+// plain channel vectors.  BatchNorm (running statistics) is folded into a per-channel scale / shift at pack time.
+// This file holds the fp32 engine (register-tiled implicit GEMM on the FMA pipe, exact to ~1e-6 against the fp32
+// reference) and the packing kernels; lipreader_tc.cu holds the tcgen05 engine for the 3x3 / 1x1 trunk convolutions.
+#include "common.cuh"
+#include "lipreader.cuh"
+
+namespace vatss {
+
+// ------------------------------------------------------------------------------------------
+// geometry / packed layout (host)
+// ------------------------------------------------------------------------------------------
+int lip_conv_table(LipConv* t) {
+  // conv 0: the 3-D front end (taps = 5*7*7, Cin = 1); then per BasicBlock conv1, conv2, shortcut (Cout = 0: none)
+  int n = 0;
+  size_t off = 0;
+  auto add = [&](int taps, int cin, int cout, int ks, int stride, int pad) {
+    LipConv c;
+    c.taps = taps; c.cin = cin; c.cout = cout; c.ks = ks; c.stride = stride; c.pad = pad;
+    c.off_w = off;   off += (size_t)taps * cin * cout * sizeof(float);
+    c.off_scale = off; off += (size_t)cout * sizeof(float);
+    c.off_shift = off; off += (size_t)cout * sizeof(float);
+    c.off_slope = off; off += (size_t)cout * sizeof(float);
+    c.off_w16 = off; off += (cin >= 64) ? (size_t)taps * cin * cout * sizeof(__half) : 0;
+    off = (off + 255) & ~(size_t)255;
+    if (t) t[n] = c;
+    ++n;
+  };
+  add(5 * 7 * 7, 1, 64, 7, 2, 3);
+  int inpl = 64;
+  const int widths[4] = {64, 128, 256, 512};
+  for (int l = 0; l < 4; ++l)
+    for (int b = 0; b < 2; ++b) {
+      const int pl = widths[l], stride = (l > 0 && b == 0) ? 2 : 1;
+      add(9, inpl, pl, 3, stride, 1);
+      add(9, pl, pl, 3, 1, 1);
+      if (stride != 1 || inpl != pl) add(1, inpl, pl, 1, stride, 0);
+      else {
+        LipConv c = {};
+        c.off_w = c.off_scale = c.off_shift = c.off_slope = c.off_w16 = off;
+        if (t) t[n] = c;
+        ++n;
+      }
+      inpl = pl;
+    }
+  if (t) t[n].off_w = off;   // sentinel: total bytes
+  return n;
+}
+
+size_t lip_packed_bytes() {
+  LipConv t[LIP_NCONV + 1];
+  lip_conv_table(t);
+  return t[LIP_NCONV].off_w;
+}
+
+// ------------------------------------------------------------------------------------------
+// packing kernels
+// ------------------------------------------------------------------------------------------
+// W (cout, cin, taps) fp32 -> Wp[(tap * cin + ci) * cout + co] fp32 and, for the tensor engine,
+// W16[(co * taps + tap) * cin + ci] fp16 (K-major rows of one output channel: tap-major, channel-minor)
+__global__ void k_lip_pack_w(const float* __restrict__ W, int cout, int cin, int taps, float* __restrict__ Wp,
+                             __half* __restrict__ W16) {
+  const long long n = (long long)cout * cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % taps);
+    const int ci = (int)((i / taps) % cin);
+    const int co = (int)(i / ((long long)taps * cin));
+    const float w = W[i];
+    Wp[((long long)tap * cin + ci) * cout + co] = w;
+    if (W16) W16[((long long)co * taps + tap) * cin + ci] = __float2half_rn(w);
+  }
+}
+// eval-mode BatchNorm as y = x * scale + shift (torch: (x - mean) / sqrt(var + eps) * weight + bias, eps = 1e-5)
+__global__ void k_lip_fold_bn(const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ rm,
+                              const float* __restrict__ rv, const float* __restrict__ slope_in, int cout,
+                              float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ slope) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cout) return;
+  const float s = g[c] / sqrtf(rv[c] + 1e-5f);
+  scale[c] = s;
+  shift[c] = b[c] - rm[c] * s;
+  slope[c] = slope_in ? slope_in[c] : 0.f;
+}
+
+int lip_pack(const float* const* params, int n_params, int relu_type, void* packed, size_t packed_bytes,
+             cudaStream_t st) {
+  VATSS_CHECK_ARG(params && n_params == LIP_NCONV * LIP_PSLOTS, "lipreader: parameter table must have %d entries",
+                  LIP_NCONV * LIP_PSLOTS);
+  VATSS_CHECK_ARG(relu_type >= LIP_ACT_RELU && relu_type <= LIP_ACT_SWISH, "lipreader: relu_type %d", relu_type);
+  VATSS_CHECK_ARG(packed && packed_bytes >= lip_packed_bytes(), "lipreader: packed buffer too small");
+  LipConv t[LIP_NCONV + 1];
+  lip_conv_table(t);
+  char* base = (char*)packed;
+  for (int i = 0; i < LIP_NCONV; ++i) {
+    const LipConv& c = t[i];
+    const float* const* p = params + i * LIP_PSLOTS;
+    if (c.cout == 0) {
+      VATSS_CHECK_ARG(p[0] == nullptr, "lipreader: conv slot %d has no shortcut convolution but a weight was given", i);
+      continue;
+    }
+    VATSS_CHECK_ARG(p[0] && p[1] && p[2] && p[3] && p[4], "lipreader: conv slot %d: missing weight / BatchNorm tensor", i);
+    const bool is_shortcut = (i > 0 && (i - 1) % 3 == 2);
+    VATSS_CHECK_ARG(relu_type != LIP_ACT_PRELU || is_shortcut || p[5], "lipreader: conv slot %d: PReLU slopes missing", i);
+    const long long n = (long long)c.taps * c.cin * c.cout;
+    k_lip_pack_w<<<ceil_div(n, 256) > 1184 ? 1184 : ceil_div(n, 256), 256, 0, st>>>(
+        p[0], c.cout, c.cin, c.taps, (float*)(base + c.off_w), c.cin >= 64 ? (__half*)(base + c.off_w16) : nullptr);
+    VATSS_LAUNCH_OK();
+    k_lip_fold_bn<<<ceil_div(c.cout, 128), 128, 0, st>>>(p[1], p[2], p[3], p[4],
+                                                         (relu_type == LIP_ACT_PRELU && !is_shortcut) ? p[5] : nullptr,
+                                                         c.cout, (float*)(base + c.off_scale),
+                                                         (float*)(base + c.off_shift), (float*)(base + c.off_slope));
+    VATSS_LAUNCH_OK();
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// activation (model.py:171-177, resnet.py:41-52)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lip_act(float v, int act, float slope) {
+  if (act == LIP_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == LIP_ACT_PRELU) return v >= 0.f ? v : v * slope;
+  if (act == LIP_ACT_SWISH) return v * (1.0f / (1.0f + expf(-v)));   // x * sigmoid(x), models/swish.py:10
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// front end: Conv3d(1 -> 64, 5x7x7, stride 1x2x2, pad 2x3x3) + BN + act, crop / normalisation folded into the load
+// ------------------------------------------------------------------------------------------
+// CTA = (frame, 4 output rows x W1 columns); the 5 x 13 x (Wc + 6) input patch and all 245 x 64 weights sit in shared
+// memory; thread = (output pixel, 32-channel half): 245 taps x 32 FMAs against broadcast weight reads.
+constexpr int LF_ROWS = 4;
+constexpr int LF_CO = 64, LF_KT = 5, LF_KS = 7, LF_TAPS = LF_KT * LF_KS * LF_KS;
+
+struct LipFrontArgs {
+  const float* vid;   // (B, T, Hin, Win)
+  int B, T, Hin, Win, y0, x0, Hc, Wc, H1, W1;
+  float pre_scale, pre_shift;
+  const float* Wp;    // [245][64]
+  const float* scale; const float* shift; const float* slope;
+  int act;
+  float* out;         // (frames, H1, W1, 64) of the chunk
+  __half* out16;      // optional fp16 copy (tensor engine)
+  int f0, nf;         // frame chunk
+};
+
+__global__ void __launch_bounds__(352) k_lip_front3d(const LipFrontArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int PW = a.Wc + 6, PH = 2 * LF_ROWS + 5;
+  float* Ws = smem;                       // 245 * 64
+  float* patch = smem + LF_TAPS * LF_CO;  // 5 * PH * PW
+  const int row_tiles = (a.H1 + LF_ROWS - 1) / LF_ROWS;
+  const int f = a.f0 + blockIdx.x / row_tiles, oy0 = (blockIdx.x % row_tiles) * LF_ROWS;
+  const int b = f / a.T, t = f % a.T;
+  for (int i = threadIdx.x; i < LF_TAPS * LF_CO / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(a.Wp)[i];
+  for (int i = threadIdx.x; i < LF_KT * PH * PW; i += blockDim.x) {
+    const int px = i % PW, py = (i / PW) % PH, kt = i / (PW * PH);
+    const int tt = t + kt - 2, iy = 2 * oy0 - 3 + py, ix = px - 3;
+    float v = 0.f;   // zero padding lives in the normalised domain
+    if (tt >= 0 && tt < a.T && iy >= 0 && iy < a.Hc && ix >= 0 && ix < a.Wc)
+      v = a.vid[(((long long)b * a.T + tt) * a.Hin + a.y0 + iy) * a.Win + a.x0 + ix] * a.pre_scale + a.pre_shift;
+    patch[i] = v;
+  }
+  __syncthreads();
+  const int npix = LF_ROWS * a.W1;
+  const int p = threadIdx.x % npix, h = threadIdx.x / npix;
+  if (h >= 2) return;
+  const int r = p / a.W1, ox = p % a.W1, oy = oy0 + r;
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  for (int kt = 0; kt < LF_KT; ++kt)
+    for (int ky = 0; ky < LF_KS; ++ky) {
+      const float* prow = patch + (kt * PH + 2 * r + ky) * PW + 2 * ox;
+      const float* wrow = Ws + ((kt * LF_KS + ky) * LF_KS) * LF_CO + h * 32;
+#pragma unroll
+      for (int kx = 0; kx < LF_KS; ++kx) {
+        const float v = prow[kx];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 w = *reinterpret_cast<const float4*>(wrow + kx * LF_CO + 4 * j);
+          acc[4 * j] = fmaf(v, w.x, acc[4 * j]);
+          acc[4 * j + 1] = fmaf(v, w.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(v, w.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(v, w.w, acc[4 * j + 3]);
+        }
+      }
+    }
+  if (oy >= a.H1) return;
+  const long long o = ((((long long)(f - a.f0)) * a.H1 + oy) * a.W1 + ox) * LF_CO + h * 32;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int c = h * 32 + j;
+    acc[j] = lip_act(fmaf(acc[j], a.scale[c], a.shift[c]), a.act, a.slope[c]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(a.out + o + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+}
+
+// MaxPool 3x3, stride 2, pad 1 over (F, H, W, 64) -> (F, Ho, Wo, 64); one thread per 4 channels of an output pixel
+__global__ void k_lip_maxpool(const float* __restrict__ in, int F, int H, int W, int C, int Ho, int Wo,
+                              float* __restrict__ out, __half* __restrict__ out16) {
+  const int c4 = C / 4;
+  const long long n = (long long)F * Ho * Wo * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4);
+    const int ox = (int)((i / c4) % Wo), oy = (int)((i / ((long long)c4 * Wo)) % Ho);
+    const long long f = i / ((long long)c4 * Wo * Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = 2 * oy - 1 + ky;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = 2 * ox - 1 + kx;
+        if (ix < 0 || ix >= W) continue;
+        const float4 v = *reinterpret_cast<const float4*>(in + (((f * H + iy) * W + ix) * (long long)C) + 4 * c);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    const long long o = ((f * Ho + oy) * Wo + ox) * (long long)C + 4 * c;
+    *reinterpret_cast<float4*>(out + o) = m;
+    if (out16) {
+      *reinterpret_cast<__half2*>(out16 + o) = __floats2half2_rn(m.x, m.y);
+      *reinterpret_cast<__half2*>(out16 + o + 2) = __floats2half2_rn(m.z, m.w);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 engine: 3x3 / 1x1 convolution as a register-tiled implicit GEMM
+//   out[m, co] = act( (sum_{tap, ci} in[pix(m, tap), ci] * Wp[tap][ci][co]) * scale[co] + shift[co] + res[m, co] )
+// ------------------------------------------------------------------------------------------
+constexpr int LC_BM = 64, LC_BN = 64, LC_BK = 16;
+
+struct LipConvArgs {
+  const float* in;    // (F, H, W, Cin)
+  int F, H, W, Cin, Ho, Wo, Cout, ks, stride, pad;
+  const float* Wp; const float* scale; const float* shift; const float* slope;
+  const float* res;   // (F, Ho, Wo, Cout) or NULL
+  int act;
+  float* out;
+};
+
+__global__ void __launch_bounds__(256) k_lip_conv_f32(const LipConvArgs a) {
+  __shared__ __align__(16) float As[LC_BK][LC_BM + 4];
+  __shared__ __align__(16) float Bs[LC_BK][LC_BN];
+  const long long M = (long long)a.F * a.Ho * a.Wo;
+  const long long m0 = (long long)blockIdx.x * LC_BM;
+  const int n0 = blockIdx.y * LC_BN;
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  // loader roles: A - thread (row = tid / 4, 4 channels at (tid % 4) * 4); B - thread (k = tid / 16, 4 couts at tx * 4)
+  const int arow = tid / 4, aq = tid % 4;
+  const long long am = m0 + arow;
+  int af = 0, aoy = 0, aox = 0;
+  const bool arow_ok = am < M;
+  if (arow_ok) {
+    aox = (int)(am % a.Wo);
+    aoy = (int)((am / a.Wo) % a.Ho);
+    af = (int)(am / ((long long)a.Wo * a.Ho));
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int taps = a.ks * a.ks;
+  for (int tap = 0; tap < taps; ++tap) {
+    const int ky = tap / a.ks, kx = tap % a.ks;
+    const int iy = aoy * a.stride + ky - a.pad, ix = aox * a.stride + kx - a.pad;
+    const bool ok = arow_ok && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+    const float* src = a.in + (((long long)af * a.H + iy) * a.W + ix) * a.Cin + aq * 4;
+    const float* wsrc = a.Wp + ((long long)tap * a.Cin + ty) * a.Cout + n0 + tx * 4;
+    for (int c0 = 0; c0 < a.Cin; c0 += LC_BK) {
+      float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) av = *reinterpret_cast<const float4*>(src + c0);
+      const float4 bv = *reinterpret_cast<const float4*>(wsrc + (long long)c0 * a.Cout);
+      __syncthreads();
+      As[aq * 4 + 0][arow] = av.x; As[aq * 4 + 1][arow] = av.y; As[aq * 4 + 2][arow] = av.z; As[aq * 4 + 3][arow] = av.w;
+      *reinterpret_cast<float4*>(&Bs[ty][tx * 4]) = bv;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < LC_BK; ++k) {
+        const float4 x = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 w = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float xa[4] = {x.x, x.y, x.z, x.w}, wa[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], wa[j], acc[i][j]);
+      }
+    }
+  }
+  const int c = n0 + tx * 4;
+  const float4 sc = *reinterpret_cast<const float4*>(a.scale + c), sh = *reinterpret_cast<const float4*>(a.shift + c);
+  const float4 sl = *reinterpret_cast<const float4*>(a.slope + c);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    float4 v = make_float4(fmaf(acc[i][0], sc.x, sh.x), fmaf(acc[i][1], sc.y, sh.y), fmaf(acc[i][2], sc.z, sh.z),
+                           fmaf(acc[i][3], sc.w, sh.w));
+    if (a.res) {
+      const float4 r = *reinterpret_cast<const float4*>(a.res + m * a.Cout + c);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    v.x = lip_act(v.x, a.act, sl.x); v.y = lip_act(v.y, a.act, sl.y);
+    v.z = lip_act(v.z, a.act, sl.z); v.w = lip_act(v.w, a.act, sl.w);
+    *reinterpret_cast<float4*>(a.out + m * a.Cout + c) = v;
+  }
+}
+
+// AdaptiveAvgPool2d(1): (F, HW, C) -> (F, C); fp32 or fp16 input
+template <typename TIN>
+__global__ void k_lip_avgpool(const TIN* __restrict__ in, int F, int HW, int C, float* __restrict__ out) {
+  const long long n = (long long)F * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long f = i / C;
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += (float)in[(f * HW + p) * C + c];
+    out[i] = s / (float)HW;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host: the launch sequence
+// ------------------------------------------------------------------------------------------
+static int out_dim(int n, int ks, int stride, int pad) { return (n + 2 * pad - ks) / stride + 1; }
+
+int lip_geometry(int Hc, int Wc, LipGeom* g) {
+  VATSS_CHECK_ARG(Hc >= 8 && Wc >= 8 && Wc <= 88 && Hc <= 1024, "lipreader: crop %d x %d unsupported (width <= 88)", Hc, Wc);
+  g->H1 = out_dim(Hc, 7, 2, 3); g->W1 = out_dim(Wc, 7, 2, 3);
+  g->H[0] = out_dim(g->H1, 3, 2, 1); g->W[0] = out_dim(g->W1, 3, 2, 1);
+  for (int l = 1; l < 4; ++l) { g->H[l] = out_dim(g->H[l - 1], 3, 2, 1); g->W[l] = out_dim(g->W[l - 1], 3, 2, 1); }
+  return 0;
+}
+
+static long long lip_frame_floats(const LipGeom& g) {
+  // conv3d output + four trunk buffers of the largest trunk activation (layer1: H0 x W0 x 64)
+  return (long long)g.H1 * g.W1 * 64 + 4ll * g.H[0] * g.W[0] * 64;
+}
+
+int lip_chunk_frames(long long F) { return (int)(F < LIP_CHUNK ? F : LIP_CHUNK); }
+
+size_t lip_workspace_bytes(int B, int T, int Hc, int Wc) {
+  LipGeom g;
+  if (B <= 0 || T <= 0 || lip_geometry(Hc, Wc, &g)) return 0;
+  const long long fc = lip_chunk_frames((long long)B * T);
+  // fp32 buffers + fp16 shadows of the trunk buffers (tensor engine) + slack
+  return (size_t)(fc * lip_frame_floats(g) * 4 + fc * 4ll * g.H[0] * g.W[0] * 64 * 2 + 4096);
+}
+
+int lip_forward(const void* packed, size_t packed_bytes, int relu_type, const float* video, int B, int T, int Hin,
+                int Win, int y0, int x0, int Hc, int Wc, float pre_scale, float pre_shift, float* out, void* workspace,
+                size_t workspace_bytes, int engine, cudaStream_t st) {
+  VATSS_CHECK_ARG(packed && video && out && workspace, "lipreader: NULL pointer");
+  VATSS_CHECK_ARG(packed_bytes >= lip_packed_bytes(), "lipreader: packed buffer too small");
+  VATSS_CHECK_ARG(relu_type >= LIP_ACT_RELU && relu_type <= LIP_ACT_SWISH, "lipreader: relu_type %d", relu_type);
+  VATSS_CHECK_ARG(B > 0 && T > 0 && y0 >= 0 && x0 >= 0 && y0 + Hc <= Hin && x0 + Wc <= Win,
+                  "lipreader: crop (%d,%d)+(%d,%d) outside the %d x %d frame", y0, x0, Hc, Wc, Hin, Win);
+  VATSS_CHECK_ARG(engine == VATSS_LIP_ENGINE_F32 || engine == VATSS_LIP_ENGINE_TENSOR, "lipreader: engine %d", engine);
+  LipGeom g;
+  if (int rc = lip_geometry(Hc, Wc, &g)) return rc;
+  VATSS_CHECK_ARG(workspace_bytes >= lip_workspace_bytes(B, T, Hc, Wc), "lipreader: workspace too small");
+  VATSS_CHECK_ARG(LF_ROWS * g.W1 * 2 <= 352, "lipreader: front-end tile does not fit (W1 = %d)", g.W1);
+  LipConv t[LIP_NCONV + 1];
+  lip_conv_table(t);
+  const char* pk = (const char*)packed;
+  const long long F = (long long)B * T;
+  const int FC = lip_chunk_frames(F);
+  float* buf0 = (float*)workspace;
+  const long long trunk_floats = (long long)FC * g.H[0] * g.W[0] * 64;
+  float* tb[4];
+  for (int i = 0; i < 4; ++i) tb[i] = buf0 + (long long)FC * g.H1 * g.W1 * 64 + i * trunk_floats;
+  __half* tb16[4];
+  for (int i = 0; i < 4; ++i) tb16[i] = (__half*)(tb[3] + trunk_floats) + i * trunk_floats;
+
+  static PerDeviceOnce configured;
+  const int front_smem = (LF_TAPS * LF_CO + LF_KT * (2 * LF_ROWS + 5) * (Wc + 6)) * 4;
+  if (configured.first())
+    VATSS_CUDA_OK(cudaFuncSetAttribute(k_lip_front3d, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  VATSS_CHECK_ARG(front_smem <= 100 * 1024, "lipreader: front-end patch too large");
+
+  for (long long f0 = 0; f0 < F; f0 += FC) {
+    const int nf = (int)((F - f0) < FC ? (F - f0) : FC);
+    {
+      LipFrontArgs a;
+      a.vid = video; a.B = B; a.T = T; a.Hin = Hin; a.Win = Win; a.y0 = y0; a.x0 = x0; a.Hc = Hc; a.Wc = Wc;
+      a.H1 = g.H1; a.W1 = g.W1; a.pre_scale = pre_scale; a.pre_shift = pre_shift;
+      a.Wp = (const float*)(pk + t[0].off_w); a.scale = (const float*)(pk + t[0].off_scale);
+      a.shift = (const float*)(pk + t[0].off_shift); a.slope = (const float*)(pk + t[0].off_slope);
+      a.act = relu_type; a.out = buf0; a.out16 = nullptr; a.f0 = (int)f0; a.nf = nf;
+      k_lip_front3d<<<nf * ((g.H1 + LF_ROWS - 1) / LF_ROWS), 352, front_smem, st>>>(a);
+      VATSS_LAUNCH_OK();
+    }
+    const bool tc = engine == VATSS_LIP_ENGINE_TENSOR;
+    {
+      const long long n = (long long)nf * g.H[0] * g.W[0] * 16;
+      k_lip_maxpool<<<(int)(ceil_div(n, 256) > 4736 ? 4736 : ceil_div(n, 256)), 256, 0, st>>>(
+          buf0, nf, g.H1, g.W1, 64, g.H[0], g.W[0], tb[0], tc ? tb16[0] : nullptr);
+      VATSS_LAUNCH_OK();
+    }
+    int cur = 0, H = g.H[0], W = g.W[0], ci = 1, final_c = 64;
+    for (int l = 0; l < 4; ++l)
+      for (int b = 0; b < 2; ++b, ci += 3) {
+        const LipConv &c1 = t[ci], &c2 = t[ci + 1], &cs = t[ci + 2];
+        const int Ho = out_dim(H, 3, c1.stride, 1), Wo = out_dim(W, 3, c1.stride, 1);
+        const int xb = cur, tbuf = (cur + 1) & 3, rb = (cur + 2) & 3, yb = (cur + 3) & 3;
+        if (tc) {
+          int rc = lip_conv_tc(pk, c1, tb16[xb], nf, H, W, Ho, Wo, nullptr, relu_type, tb16[tbuf], st);
+          if (rc) return rc;
+          const __half* res = tb16[xb];
+          if (cs.cout) {
+            rc = lip_conv_tc(pk, cs, tb16[xb], nf, H, W, Ho, Wo, nullptr, LIP_ACT_NONE, tb16[rb], st);
+            if (rc) return rc;
+            res = tb16[rb];
+          }
+          rc = lip_conv_tc(pk, c2, tb16[tbuf], nf, Ho, Wo, Ho, Wo, res, relu_type, tb16[yb], st);
+          if (rc) return rc;
+        } else {
+          auto run = [&](const LipConv& c, const float* in, int Hi, int Wi, const float* res, int act, float* o) -> int {
+            LipConvArgs a;
+            a.in = in; a.F = nf; a.H = Hi; a.W = Wi; a.Cin = c.cin; a.Ho = Ho; a.Wo = Wo; a.Cout = c.cout;
+            a.ks = c.ks; a.stride = c.stride; a.pad = c.pad;
+            a.Wp = (const float*)(pk + c.off_w); a.scale = (const float*)(pk + c.off_scale);
+            a.shift = (const float*)(pk + c.off_shift); a.slope = (const float*)(pk + c.off_slope);
+            a.res = res; a.act = act; a.out = o;
+            dim3 grid(ceil_div((long long)nf * Ho * Wo, LC_BM), c.cout / LC_BN);
+            k_lip_conv_f32<<<grid, 256, 0, st>>>(a);
+            VATSS_LAUNCH_OK();
+            return 0;
+          };
+          if (int rc = run(c1, tb[xb], H, W, nullptr, relu_type, tb[tbuf])) return rc;
+          const float* res = tb[xb];
+          if (cs.cout) {
+            if (int rc = run(cs, tb[xb], H, W, nullptr, LIP_ACT_NONE, tb[rb])) return rc;
+            res = tb[rb];
+          }
+          if (int rc = run(c2, tb[tbuf], Ho, Wo, res, relu_type, tb[yb])) return rc;
+        }
+        cur = yb; H = Ho; W = Wo; final_c = c2.cout;
+      }
+    const long long n = (long long)nf * final_c;
+    if (tc) k_lip_avgpool<__half><<<ceil_div(n, 256), 256, 0, st>>>(tb16[cur], nf, H * W, final_c, out + f0 * final_c);
+    else k_lip_avgpool<float><<<ceil_div(n, 256), 256, 0, st>>>(tb[cur], nf, H * W, final_c, out + f0 * final_c);
+    VATSS_LAUNCH_OK();
+  }
+  return 0;
+}
+
+}  // namespace vatss

@@ -1,0 +1,219 @@
+// Lipreader trunk convolutions on the tcgen05 tensor cores (reference: models/resnet.py:8-17,31-84 - the 3x3 / 1x1
+// Conv2d + BatchNorm2d + activation (+ shortcut) of the ResNet-18 BasicBlocks).
+//
+// Implicit GEMM over pixel-major fp16 activations:
+//   D[128 pixels, NT channels] += A_slab[128 pixels, 64 input channels of one tap] x W_slab[NT, 64]^T
+// for the taps x (Cin / 64) K slabs of the convolution.  K = 9 Cin is 576 ... 4608, so - unlike the per-token
+// projections of the separation path (tc_gemm.cu: K <= 256, W resident) - this is a K-pipelined kernel:
+//   warps 0..3  A producers, one thread per output pixel of the tile: the 128-byte channel vector of the pixel's tap
+//               neighbour (zeros outside the image) goes into the SWIZZLE_128B K-major operand layout with eight
+//               16-byte shared-memory stores; any stride / padding / image size, every tile has 128 useful rows.
+//               Thread 0 also fetches the weight slab with one TMA box.  After the last slab the same warps are the
+//               epilogue: tcgen05.ld of their TMEM lane quadrant, folded BatchNorm, shortcut add, activation, fp16 store.
+//   warp 4      MMA issuer: 4 x tcgen05.mma (M = 128, N = NT, K = 16) per slab, accumulator in TMEM, tcgen05.commit
+//               hands the stage back to the producers.
+// One tile per CTA, two CTAs per SM (3 stages x 32 KB): one CTA's epilogue runs under the other's main loop.
+#include "lipreader.cuh"
+#include "ptx.cuh"
+
+namespace vatss {
+
+using namespace ptx;
+
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
+
+constexpr int LT_STAGES = 3;
+constexpr int LT_A_BYTES = 128 * 128;
+
+struct LipTcArgs {
+  const __half* in;
+  int F, H, W, Cin, Ho, Wo, Cout, ks, stride, pad;
+  const float* scale; const float* shift; const float* slope;
+  const __half* res;
+  int act;
+  __half* out;
+};
+
+__device__ __forceinline__ float lip_act_tc(float v, int act, float slope) {
+  if (act == LIP_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == LIP_ACT_PRELU) return v >= 0.f ? v : v * slope;
+  if (act == LIP_ACT_SWISH) return v * (1.0f / (1.0f + __expf(-v)));
+  return v;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(160) k_lip_conv_tc(const __grid_constant__ CUtensorMap tmapW, const LipTcArgs a) {
+  constexpr int B_BYTES = NT * 128;
+  constexpr int STAGE_BYTES = LT_A_BYTES + B_BYTES;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + LT_STAGES * STAGE_BYTES;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * LT_STAGES, bar_acc = bars + 16 * LT_STAGES;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + LT_STAGES * STAGE_BYTES + 16 * LT_STAGES + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LT_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 129);   // 128 row writers + the expect_tx arrival of the weight TMA
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    fence_mbar_init();
+    prefetch_tmap(&tmapW);
+  }
+  if (warp == 4) {
+    tmem_alloc<1>(smem_u32(const_cast<uint32_t*>(tmem_slot)), NT);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const long long M = (long long)a.F * a.Ho * a.Wo;
+  const long long m0 = (long long)blockIdx.x * 128;
+  const int n0 = blockIdx.y * NT;
+  const int cblocks = a.Cin / 64;
+  const int nslabs = a.ks * a.ks * cblocks;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ A producers (thread = pixel row)
+    const int r = threadIdx.x;
+    const long long m = m0 + r;
+    const bool row_ok = m < M;
+    int f = 0, oy = 0, ox = 0;
+    if (row_ok) {
+      ox = (int)(m % a.Wo);
+      oy = (int)((m / a.Wo) % a.Ho);
+      f = (int)(m / ((long long)a.Wo * a.Ho));
+    }
+    for (int i = 0; i < nslabs; ++i) {
+      const int s = i % LT_STAGES, ph = (i / LT_STAGES) & 1;
+      const int tap = i / cblocks, cb = i - tap * cblocks;
+      const int ky = tap / a.ks, kx = tap - ky * a.ks;
+      const int iy = oy * a.stride + ky - a.pad, ix = ox * a.stride + kx - a.pad;
+      const bool ok = row_ok && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+      uint4 v[8];
+      if (ok) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.in + (((long long)f * a.H + iy) * a.W + ix) * a.Cin + cb * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = __ldg(src + c);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      const uint32_t sA = base + s * STAGE_BYTES;
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(bar_full + 8 * s, B_BYTES);
+        tma_load_2d(sA + LT_A_BYTES, &tmapW, bar_full + 8 * s, i * 64, n0);
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t dst = sA + sw128_offset((uint32_t)r, (uint32_t)c);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[c].x), "r"(v[c].y), "r"(v[c].z), "r"(v[c].w)
+                     : "memory");
+      }
+      fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy operand reads
+      mbar_arrive(bar_full + 8 * s);
+    }
+    // ------------------------------------------------------------------ epilogue (thread = pixel row, warp = lane quadrant)
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < NT; c0 += 32) {
+      uint32_t acc[32];
+      tmem_ld_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16) + c0, acc);
+      tmem_ld_wait();
+      if (row_ok) {
+        const int cg = n0 + c0;
+        uint32_t rr[16];
+        if (a.res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.res + m * a.Cout + cg);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 x = __ldg(rp + q);
+            rr[4 * q] = x.x; rr[4 * q + 1] = x.y; rr[4 * q + 2] = x.z; rr[4 * q + 3] = x.w;
+          }
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float v0 = fmaf(__uint_as_float(acc[2 * j]), __ldg(a.scale + cg + 2 * j), __ldg(a.shift + cg + 2 * j));
+          float v1 = fmaf(__uint_as_float(acc[2 * j + 1]), __ldg(a.scale + cg + 2 * j + 1), __ldg(a.shift + cg + 2 * j + 1));
+          if (a.res) {
+            const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rr[j]));
+            v0 += rf.x; v1 += rf.y;
+          }
+          const float s0 = a.act == LIP_ACT_PRELU ? __ldg(a.slope + cg + 2 * j) : 0.f;
+          const float s1 = a.act == LIP_ACT_PRELU ? __ldg(a.slope + cg + 2 * j + 1) : 0.f;
+          const __half2 h = __floats2half2_rn(lip_act_tc(v0, a.act, s0), lip_act_tc(v1, a.act, s1));
+          pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        uint4* op = reinterpret_cast<uint4*>(a.out + m * a.Cout + cg);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) op[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = idesc_f16(128, NT, 0);
+      for (int i = 0; i < nslabs; ++i) {
+        const int s = i % LT_STAGES, ph = (i / LT_STAGES) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sA = base + s * STAGE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t a_desc = smem_desc_sw128_kmajor(sA) + (uint64_t)(kk * 2);
+          const uint64_t b_desc = smem_desc_sw128_kmajor(sA + LT_A_BYTES) + (uint64_t)(kk * 2);
+          umma_f16<1>(tmem, a_desc, b_desc, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_empty + 8 * s);
+      }
+      umma_commit(bar_acc);
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<1>(tmem, NT);
+}
+
+template <int NT>
+static int lip_conv_tc_launch(const char* packed, const LipConv& c, const LipTcArgs& a, cudaStream_t st) {
+  constexpr int SMEM = LT_STAGES * (LT_A_BYTES + NT * 128) + 16 * LT_STAGES + 16 + 1024;
+  static PerDeviceOnce configured;
+  if (configured.first())
+    VATSS_CUDA_OK(cudaFuncSetAttribute(k_lip_conv_tc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  CUtensorMap tmapW;
+  const uint64_t K = (uint64_t)c.taps * c.cin;
+  const uint64_t dims[2] = {K, (uint64_t)c.cout};
+  const uint64_t strides[1] = {K * sizeof(__half)};
+  const uint32_t box[2] = {64, (uint32_t)NT};
+  if (int rc = make_tmap_f16(&tmapW, packed + c.off_w16, 2, dims, strides, box)) return rc;
+  const long long M = (long long)a.F * a.Ho * a.Wo;
+  dim3 grid(ceil_div(M, 128), c.cout / NT);
+  k_lip_conv_tc<NT><<<grid, 160, SMEM, st>>>(tmapW, a);
+  VATSS_LAUNCH_OK();
+  return 0;
+}
+
+int lip_conv_tc(const char* packed, const LipConv& c, const __half* in16, int F, int H, int W, int Ho, int Wo,
+                const __half* res16, int act, __half* out16, cudaStream_t st) {
+  VATSS_CHECK_ARG(c.cin % 64 == 0 && c.cout % 64 == 0, "lipreader tensor engine: channels %d -> %d must be multiples of 64",
+                  c.cin, c.cout);
+  LipTcArgs a;
+  a.in = in16; a.F = F; a.H = H; a.W = W; a.Cin = c.cin; a.Ho = Ho; a.Wo = Wo; a.Cout = c.cout;
+  a.ks = c.ks; a.stride = c.stride; a.pad = c.pad;
+  a.scale = (const float*)(packed + c.off_scale); a.shift = (const float*)(packed + c.off_shift);
+  a.slope = (const float*)(packed + c.off_slope);
+  a.res = res16; a.act = act; a.out = out16;
+  if (c.cout % 128 == 0) return lip_conv_tc_launch<128>(packed, c, a, st);
+  return lip_conv_tc_launch<64>(packed, c, a, st);
+}
+
+}  // namespace vatss

@@ -1,0 +1,166 @@
+"""Lipreader front end: oracle pinned to the reference's `Lipreading`, host-side mirror on CPU,
+and the CUDA path (through the C ABI) against the reference-generated goldens.
+
+Goldens: tests/golden/lipreader_*.npz - outputs of the reference class itself (oracle/gen_lipreader_golden.py) on the
+synthetic weights of oracle.lipreader_oracle.make_state_dict.  Tolerances: the fp32 engine is held to 2e-5 relative L2
+(fp32 summation order only); the tcgen05 engine (fp16 activations through 17 convolutions, fp32 accumulation) to 2e-3 (measured 3e-4 - 5e-4) -
+the reference states no tolerance for this path; the separation model layer-normalises what it receives.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lipreader_oracle as LO
+
+CASES = [("swish", 2, 7), ("prelu", 1, 5), ("relu", 1, 5)]
+F32_TOL = 2e-5
+TENSOR_TOL = 2e-3
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def load_case(golden_dir, relu_type, B, T):
+    z = np.load(os.path.join(golden_dir, f"lipreader_{relu_type}_B{B}_T{T}.npz"))
+    return z["frames"].astype(np.float32), z["features"], int(z["weight_seed"])
+
+
+# ------------------------------------------------------------------------------------------- CPU
+@pytest.mark.parametrize("relu_type,B,T", CASES)
+def test_oracle_matches_reference_lipreading(golden_dir, relu_type, B, T):
+    frames, feats, seed = load_case(golden_dir, relu_type, B, T)
+    sd = LO.make_state_dict(relu_type, seed)
+    x = torch.from_numpy(LO.preprocess(frames).astype(np.float32))[:, None]
+    with torch.no_grad():
+        y32 = LO.forward(sd, x, relu_type).numpy()
+        y64 = LO.forward(sd, x, relu_type, dtype=torch.float64).numpy()
+    assert y32.shape == feats.shape == (B, T, 512)
+    assert rel_l2(y32, feats) < 1e-6      # same torch ops in the same order as the reference modules
+    assert rel_l2(y64, feats) < 2e-6      # the reference ran in fp32
+
+
+def test_frames_generator_is_deterministic(golden_dir):
+    frames, _, _ = load_case(golden_dir, "swish", 2, 7)
+    assert np.array_equal(LO.make_frames(2, 7), frames)
+
+
+def test_mirror_state_dict_and_constructor_contract():
+    from speech_separation_b200 import Lipreading
+    from speech_separation_b200.lipreader import _conv_param_names, center_crop_window
+
+    for relu_type in ("swish", "prelu", "relu"):
+        m = Lipreading(relu_type=relu_type, extract_feats=True)
+        own = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith("num_batches_tracked")}
+        ref = dict(LO.state_dict_names(relu_type))
+        assert own == ref
+        assert list(own) == [k for k, _ in LO.state_dict_names(relu_type)]   # the reference's key order
+        sd = LO.make_state_dict(relu_type)
+        sd["tcn.tcn_output.weight"] = torch.zeros(500, 768)                  # a full checkpoint also has the head
+        m.load_state_dict(sd, strict=False)
+        names = _conv_param_names(relu_type)
+        assert len(names) == 25 * 6
+        assert {n for n in names if n} == set(ref)
+        assert not m.training
+        with pytest.raises(NotImplementedError):
+            m.train()
+    for kw in ({"extract_feats": False}, {"modality": "audio", "extract_feats": True},
+               {"backbone_type": "shufflenet", "extract_feats": True}, {"use_boundary": True, "extract_feats": True}):
+        with pytest.raises(NotImplementedError):
+            Lipreading(**kw)
+    assert center_crop_window(96, 96) == (4, 4, 88, 88)
+    # conv init scale of the reference (model.py:281-293): std = sqrt(2 / (prod(kernel) * out_channels))
+    torch.manual_seed(0)
+    m = Lipreading(relu_type="swish", extract_feats=True)
+    w = m.trunk.layer3[1].conv2.weight
+    assert abs(float(w.detach().std()) - (2.0 / (9 * 256)) ** 0.5) < 2e-4
+    assert float(m.frontend3D[1].weight.min()) == 1.0 and float(m.frontend3D[1].bias.abs().max()) == 0.0
+
+
+def test_no_cpu_path():
+    from speech_separation_b200 import Lipreading
+
+    m = Lipreading(relu_type="swish", extract_feats=True)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 3, 88, 88), lengths=[3])
+
+
+# ------------------------------------------------------------------------------------------- GPU
+def _net(relu_type, seed, engine):
+    from speech_separation_b200 import Lipreading
+
+    m = Lipreading(relu_type=relu_type, extract_feats=True)
+    m.load_state_dict(LO.make_state_dict(relu_type, seed), strict=True)
+    return m.to("cuda:0").set_engine(engine)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("engine,tol", [("f32", F32_TOL), ("tensor", TENSOR_TOL)])
+@pytest.mark.parametrize("relu_type,B,T", CASES)
+def test_cuda_forward_matches_reference_golden(golden_dir, relu_type, B, T, engine, tol):
+    frames, feats, seed = load_case(golden_dir, relu_type, B, T)
+    net = _net(relu_type, seed, engine)
+    x = torch.from_numpy(LO.preprocess(frames).astype(np.float32))[:, None].to("cuda:0")
+    y = net(x, lengths=[T] * B).cpu().numpy()
+    assert y.shape == feats.shape
+    err = rel_l2(y, feats)
+    print(f"lipreader {relu_type} {engine}: rel-L2 {err:.3e}")
+    assert err < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("engine,tol", [("f32", F32_TOL), ("tensor", TENSOR_TOL)])
+def test_cuda_embeddings_from_raw_frames(golden_dir, engine, tol):
+    """make_embeddings.py:58-66: raw 96 x 96 crops -> (512, T); crop + normalisation folded into the first kernel."""
+    from speech_separation_b200 import extract_embeddings
+
+    frames, feats, seed = load_case(golden_dir, "swish", 2, 7)
+    net = _net("swish", seed, engine)
+    emb = extract_embeddings(net, torch.from_numpy(frames).to("cuda:0"))
+    assert tuple(emb.shape) == (2, 512, 7)
+    assert rel_l2(emb.transpose(1, 2).cpu().numpy(), feats) < tol
+    one = extract_embeddings(net, torch.from_numpy(frames[1]).to("cuda:0"))     # a single (T, H, W) clip
+    assert rel_l2(one[0].T.cpu().numpy(), feats[1]) < tol
+
+
+@pytest.mark.gpu
+def test_cuda_frame_chunks_and_utterance_boundaries():
+    """More frames than one trunk pass holds (256): chunk seams and the temporal zero padding at utterance boundaries
+    against the CPU oracle; the tensor engine against the fp32 engine at the same size."""
+    relu_type, B, T = "swish", 3, 90
+    sd = LO.make_state_dict(relu_type, 11)
+    frames = LO.make_frames(B, T, seed=3)
+    x = torch.from_numpy(LO.preprocess(frames).astype(np.float32))[:, None]
+    with torch.no_grad():
+        ref = LO.forward(sd, x, relu_type).numpy()
+    net = _net(relu_type, 11, "f32")
+    y = net(x.to("cuda:0"), lengths=[T] * B).cpu().numpy()
+    assert rel_l2(y, ref) < F32_TOL
+    yt = net.set_engine("tensor")(x.to("cuda:0"), lengths=[T] * B).cpu().numpy()
+    assert rel_l2(yt, ref) < TENSOR_TOL
+    # utterances are independent: clip 1 alone gives the same rows bit for bit (fp32 engine)
+    net.set_engine("f32")
+    y1 = net(x[1:2].to("cuda:0"), lengths=[T]).cpu().numpy()
+    assert np.array_equal(y1[0], y[1])
+
+
+@pytest.mark.gpu
+def test_lipreader_feeds_the_separator(golden_dir):
+    """profiler.py:17-22: video -> lipreader -> permute -> DPTN-AV; shapes and finiteness end to end on the device."""
+    from speech_separation_b200 import DPTNAVWavEncDec, extract_embeddings
+
+    net = _net("swish", 2024, "tensor")
+    frames = torch.from_numpy(LO.make_frames(2, 25, seed=5)).to("cuda:0")
+    emb = extract_embeddings(net, frames)                       # (2, 512, 25): one second of video per speaker
+    torch.manual_seed(42)
+    sep = DPTNAVWavEncDec(num_features=128, video_emb_size=512, hidden_video=128, kernel_size_enc=7, hidden_dim=128,
+                          num_blocks=2, chunk_size=150, step_size=75).eval().to("cuda:0")
+    mix = 0.1 * torch.randn(1, 16000, device="cuda:0")
+    out = sep(mix=mix, s1_embedding=emb[0:1].contiguous(), s2_embedding=emb[1:2].contiguous())
+    assert tuple(out["s1_pred"].shape) == (1, 16000)
+    assert bool(torch.isfinite(out["s1_pred"]).all()) and bool(torch.isfinite(out["s2_pred"]).all())

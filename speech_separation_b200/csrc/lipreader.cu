@@ -140,8 +140,8 @@ __device__ __forceinline__ float lip_act(float v, int act, float slope) {
 // ------------------------------------------------------------------------------------------
 // front end: Conv3d(1 -> 64, 5x7x7, stride 1x2x2, pad 2x3x3) + BN + act, crop / normalisation folded into the load
 // ------------------------------------------------------------------------------------------
-// CTA = (frame, 4 output rows x W1 columns); the 5 x 13 x (Wc + 6) input patch and all 245 x 64 weights sit in shared
-// memory; thread = (output pixel, 32-channel half): 245 taps x 32 FMAs against broadcast weight reads.
+// CTA = (frame, 4 output rows x W1 columns); the 5 x 13 x (Wc + 8) input patch and all 245 x 64 weights sit in shared
+// memory; thread = (two adjacent output pixels, 32-channel half): 245 taps x 64 FMAs against broadcast weight reads.
 constexpr int LF_ROWS = 4;
 constexpr int LF_CO = 64, LF_KT = 5, LF_KS = 7, LF_TAPS = LF_KT * LF_KS * LF_KS;
 
@@ -157,9 +157,10 @@ struct LipFrontArgs {
   int f0, nf;         // frame chunk
 };
 
-__global__ void __launch_bounds__(352) k_lip_front3d(const LipFrontArgs a) {
+__global__ void __launch_bounds__(192) k_lip_front3d(const LipFrontArgs a) {
   extern __shared__ __align__(16) float smem[];
-  const int PW = a.Wc + 6, PH = 2 * LF_ROWS + 5;
+  const int npairs = (a.W1 + 1) / 2;
+  const int PW = 4 * npairs + 8, PH = 2 * LF_ROWS + 5;   // PW >= Wc + 6, rows are 16-byte aligned
   float* Ws = smem;                       // 245 * 64
   float* patch = smem + LF_TAPS * LF_CO;  // 5 * PH * PW
   const int row_tiles = (a.H1 + LF_ROWS - 1) / LF_ROWS;
@@ -176,40 +177,52 @@ __global__ void __launch_bounds__(352) k_lip_front3d(const LipFrontArgs a) {
     patch[i] = v;
   }
   __syncthreads();
-  const int npix = LF_ROWS * a.W1;
-  const int p = threadIdx.x % npix, h = threadIdx.x / npix;
+  // thread = (output row r, pixel pair j, 32-channel half h): 2 x 32 accumulators, so a broadcast weight read feeds
+  // two FMAs and the three 16-byte patch reads of a (kt, ky) row feed all 7 x 2 taps (FMA-bound instead of LSU-bound)
+  const int nthr = LF_ROWS * npairs;
+  const int h = threadIdx.x / nthr, p = threadIdx.x % nthr;
   if (h >= 2) return;
-  const int r = p / a.W1, ox = p % a.W1, oy = oy0 + r;
-  float acc[32];
+  const int r = p / npairs, j = p % npairs, oy = oy0 + r;
+  float acc0[32], acc1[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  for (int q = 0; q < 32; ++q) acc0[q] = acc1[q] = 0.f;
   for (int kt = 0; kt < LF_KT; ++kt)
     for (int ky = 0; ky < LF_KS; ++ky) {
-      const float* prow = patch + (kt * PH + 2 * r + ky) * PW + 2 * ox;
+      const float4* pr = reinterpret_cast<const float4*>(patch + (kt * PH + 2 * r + ky) * PW + 4 * j);
+      const float4 q0 = pr[0], q1 = pr[1], q2 = pr[2];
+      const float pv[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
       const float* wrow = Ws + ((kt * LF_KS + ky) * LF_KS) * LF_CO + h * 32;
 #pragma unroll
       for (int kx = 0; kx < LF_KS; ++kx) {
-        const float v = prow[kx];
+        const float va = pv[kx], vb = pv[kx + 2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 w = *reinterpret_cast<const float4*>(wrow + kx * LF_CO + 4 * j);
-          acc[4 * j] = fmaf(v, w.x, acc[4 * j]);
-          acc[4 * j + 1] = fmaf(v, w.y, acc[4 * j + 1]);
-          acc[4 * j + 2] = fmaf(v, w.z, acc[4 * j + 2]);
-          acc[4 * j + 3] = fmaf(v, w.w, acc[4 * j + 3]);
+        for (int q = 0; q < 8; ++q) {
+          const float4 w = *reinterpret_cast<const float4*>(wrow + kx * LF_CO + 4 * q);
+          acc0[4 * q] = fmaf(va, w.x, acc0[4 * q]);         acc1[4 * q] = fmaf(vb, w.x, acc1[4 * q]);
+          acc0[4 * q + 1] = fmaf(va, w.y, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(vb, w.y, acc1[4 * q + 1]);
+          acc0[4 * q + 2] = fmaf(va, w.z, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(vb, w.z, acc1[4 * q + 2]);
+          acc0[4 * q + 3] = fmaf(va, w.w, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(vb, w.w, acc1[4 * q + 3]);
         }
       }
     }
   if (oy >= a.H1) return;
-  const long long o = ((((long long)(f - a.f0)) * a.H1 + oy) * a.W1 + ox) * LF_CO + h * 32;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int c = h * 32 + j;
-    acc[j] = lip_act(fmaf(acc[j], a.scale[c], a.shift[c]), a.act, a.slope[c]);
+  for (int q = 0; q < 32; ++q) {
+    const int c = h * 32 + q;
+    const float sc = a.scale[c], sh = a.shift[c], sl = a.slope[c];
+    acc0[q] = lip_act(fmaf(acc0[q], sc, sh), a.act, sl);
+    acc1[q] = lip_act(fmaf(acc1[q], sc, sh), a.act, sl);
   }
+  const long long o = ((((long long)(f - a.f0)) * a.H1 + oy) * a.W1 + 2 * j) * LF_CO + h * 32;
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    *reinterpret_cast<float4*>(a.out + o + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(a.out + o + 4 * q) = make_float4(acc0[4 * q], acc0[4 * q + 1], acc0[4 * q + 2], acc0[4 * q + 3]);
+  if (2 * j + 1 < a.W1) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<float4*>(a.out + o + LF_CO + 4 * q) =
+          make_float4(acc1[4 * q], acc1[4 * q + 1], acc1[4 * q + 2], acc1[4 * q + 3]);
+  }
 }
 
 // MaxPool 3x3, stride 2, pad 1 over (F, H, W, 64) -> (F, Ho, Wo, 64); one thread per 4 channels of an output pixel
@@ -377,7 +390,8 @@ int lip_forward(const void* packed, size_t packed_bytes, int relu_type, const fl
   LipGeom g;
   if (int rc = lip_geometry(Hc, Wc, &g)) return rc;
   VATSS_CHECK_ARG(workspace_bytes >= lip_workspace_bytes(B, T, Hc, Wc), "lipreader: workspace too small");
-  VATSS_CHECK_ARG(LF_ROWS * g.W1 * 2 <= 352, "lipreader: front-end tile does not fit (W1 = %d)", g.W1);
+  const int front_pairs = (g.W1 + 1) / 2;
+  VATSS_CHECK_ARG(LF_ROWS * front_pairs * 2 <= 192, "lipreader: front-end tile does not fit (W1 = %d)", g.W1);
   LipConv t[LIP_NCONV + 1];
   lip_conv_table(t);
   const char* pk = (const char*)packed;
@@ -391,7 +405,7 @@ int lip_forward(const void* packed, size_t packed_bytes, int relu_type, const fl
   for (int i = 0; i < 4; ++i) tb16[i] = (__half*)(tb[3] + trunk_floats) + i * trunk_floats;
 
   static PerDeviceOnce configured;
-  const int front_smem = (LF_TAPS * LF_CO + LF_KT * (2 * LF_ROWS + 5) * (Wc + 6)) * 4;
+  const int front_smem = (LF_TAPS * LF_CO + LF_KT * (2 * LF_ROWS + 5) * (4 * front_pairs + 8)) * 4;
   if (configured.first())
     VATSS_CUDA_OK(cudaFuncSetAttribute(k_lip_front3d, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   VATSS_CHECK_ARG(front_smem <= 100 * 1024, "lipreader: front-end patch too large");
@@ -405,7 +419,7 @@ int lip_forward(const void* packed, size_t packed_bytes, int relu_type, const fl
       a.Wp = (const float*)(pk + t[0].off_w); a.scale = (const float*)(pk + t[0].off_scale);
       a.shift = (const float*)(pk + t[0].off_shift); a.slope = (const float*)(pk + t[0].off_slope);
       a.act = relu_type; a.out = buf0; a.out16 = nullptr; a.f0 = (int)f0; a.nf = nf;
-      k_lip_front3d<<<nf * ((g.H1 + LF_ROWS - 1) / LF_ROWS), 352, front_smem, st>>>(a);
+      k_lip_front3d<<<nf * ((g.H1 + LF_ROWS - 1) / LF_ROWS), 192, front_smem, st>>>(a);
       VATSS_LAUNCH_OK();
     }
     const bool tc = engine == VATSS_LIP_ENGINE_TENSOR;

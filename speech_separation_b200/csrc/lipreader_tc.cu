@@ -5,12 +5,13 @@
 //   D[128 pixels, NT channels] += A_slab[128 pixels, 64 input channels of one tap] x W_slab[NT, 64]^T
 // for the taps x (Cin / 64) K slabs of the convolution.  K = 9 Cin is 576 ... 4608, so - unlike the per-token
 // projections of the separation path (tc_gemm.cu: K <= 256, W resident) - this is a K-pipelined kernel:
-//   warps 0..3  A producers, one thread per output pixel of the tile: the 128-byte channel vector of the pixel's tap
-//               neighbour (zeros outside the image) goes into the SWIZZLE_128B K-major operand layout with eight
-//               16-byte shared-memory stores; any stride / padding / image size, every tile has 128 useful rows.
-//               Thread 0 also fetches the weight slab with one TMA box.  After the last slab the same warps are the
-//               epilogue: tcgen05.ld of their TMEM lane quadrant, folded BatchNorm, shortcut add, activation, fp16 store.
-//   warp 4      MMA issuer: 4 x tcgen05.mma (M = 128, N = NT, K = 16) per slab, accumulator in TMEM, tcgen05.commit
+//   warps 0..7  A producers, two threads per output pixel of the tile: the 128-byte channel vector of the pixel's tap
+//               neighbour (zeros outside the image) goes into the SWIZZLE_128B K-major operand layout with 16-byte
+//               shared-memory stores; any stride / padding / image size, every tile has 128 useful rows.  The loads
+//               of three slabs are in flight per thread.  Thread 0 also fetches the weight slab with one TMA box.
+//               After the last slab the same warps are the epilogue: tcgen05.ld of their TMEM lane quadrant, folded
+//               BatchNorm, shortcut add, activation, fp16 store.
+//   warp 8      MMA issuer: 4 x tcgen05.mma (M = 128, N = NT, K = 16) per slab, accumulator in TMEM, tcgen05.commit
 //               hands the stage back to the producers.
 // One tile per CTA, two CTAs per SM (3 stages x 32 KB): one CTA's epilogue runs under the other's main loop.
 #include "lipreader.cuh"
@@ -43,7 +44,7 @@ __device__ __forceinline__ float lip_act_tc(float v, int act, float slope) {
 }
 
 template <int NT>
-__global__ void __launch_bounds__(160) k_lip_conv_tc(const __grid_constant__ CUtensorMap tmapW, const LipTcArgs a) {
+__global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ CUtensorMap tmapW, const LipTcArgs a) {
   constexpr int B_BYTES = NT * 128;
   constexpr int STAGE_BYTES = LT_A_BYTES + B_BYTES;
   extern __shared__ unsigned char smem_raw[];
@@ -51,20 +52,21 @@ __global__ void __launch_bounds__(160) k_lip_conv_tc(const __grid_constant__ CUt
   unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bars = base + LT_STAGES * STAGE_BYTES;
   const uint32_t bar_full = bars, bar_empty = bars + 8 * LT_STAGES, bar_acc = bars + 16 * LT_STAGES;
+  const uint32_t tmem_slot_addr = bars + 16 * LT_STAGES + 8;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + LT_STAGES * STAGE_BYTES + 16 * LT_STAGES + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < LT_STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 129);   // 128 row writers + the expect_tx arrival of the weight TMA
+      mbar_init(bar_full + 8 * s, 257);   // 256 half-row writers + the expect_tx arrival of the weight TMA
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_acc, 1);
     fence_mbar_init();
     prefetch_tmap(&tmapW);
   }
-  if (warp == 4) {
-    tmem_alloc<1>(smem_u32(const_cast<uint32_t*>(tmem_slot)), NT);
+  if (warp == 8) {
+    tmem_alloc<1>(tmem_slot_addr, NT);
     tmem_relinquish<1>();
   }
   tc_fence_before();
@@ -78,9 +80,9 @@ __global__ void __launch_bounds__(160) k_lip_conv_tc(const __grid_constant__ CUt
   const int cblocks = a.Cin / 64;
   const int nslabs = a.ks * a.ks * cblocks;
 
-  if (warp < 4) {
-    // ------------------------------------------------------------------ A producers (thread = pixel row)
-    const int r = threadIdx.x;
+  if (warp < 8) {
+    // ------------------------------------------------------------------ A producers (thread = half a pixel row)
+    const int r = threadIdx.x & 127, hsel = threadIdx.x >> 7;
     const long long m = m0 + r;
     const bool row_ok = m < M;
     int f = 0, oy = 0, ox = 0;
@@ -89,21 +91,25 @@ __global__ void __launch_bounds__(160) k_lip_conv_tc(const __grid_constant__ CUt
       oy = (int)((m / a.Wo) % a.Ho);
       f = (int)(m / ((long long)a.Wo * a.Ho));
     }
-    for (int i = 0; i < nslabs; ++i) {
-      const int s = i % LT_STAGES, ph = (i / LT_STAGES) & 1;
+    // Three slabs of loads are in flight per thread (registers) while earlier slabs are written to the ring: the
+    // global / L2 latency of a gather (~1 us) is several times the tensor-core time of a slab.
+    auto issue = [&](int i, uint4* v) {
+      if (i >= nslabs) return;
       const int tap = i / cblocks, cb = i - tap * cblocks;
       const int ky = tap / a.ks, kx = tap - ky * a.ks;
       const int iy = oy * a.stride + ky - a.pad, ix = ox * a.stride + kx - a.pad;
-      const bool ok = row_ok && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
-      uint4 v[8];
-      if (ok) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.in + (((long long)f * a.H + iy) * a.W + ix) * a.Cin + cb * 64);
+      if (row_ok && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.in + (((long long)f * a.H + iy) * a.W + ix) * a.Cin + cb * 64) + 4 * hsel;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = __ldg(src + c);
+        for (int c = 0; c < 4; ++c) v[c] = __ldg(src + c);
       } else {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = make_uint4(0u, 0u, 0u, 0u);
+        for (int c = 0; c < 4; ++c) v[c] = make_uint4(0u, 0u, 0u, 0u);
       }
+    };
+    auto commit = [&](int i, const uint4* v) {
+      if (i >= nslabs) return;
+      const int s = i % LT_STAGES, ph = (i / LT_STAGES) & 1;
       mbar_wait(bar_empty + 8 * s, ph ^ 1);
       const uint32_t sA = base + s * STAGE_BYTES;
       if (threadIdx.x == 0) {
@@ -111,21 +117,30 @@ __global__ void __launch_bounds__(160) k_lip_conv_tc(const __grid_constant__ CUt
         tma_load_2d(sA + LT_A_BYTES, &tmapW, bar_full + 8 * s, i * 64, n0);
       }
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t dst = sA + sw128_offset((uint32_t)r, (uint32_t)c);
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t dst = sA + sw128_offset((uint32_t)r, (uint32_t)(4 * hsel + c));
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[c].x), "r"(v[c].y), "r"(v[c].z), "r"(v[c].w)
                      : "memory");
       }
       fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy operand reads
       mbar_arrive(bar_full + 8 * s);
+    };
+    uint4 v0[4], v1[4], v2[4];
+    issue(0, v0);
+    issue(1, v1);
+    for (int i = 0; i < nslabs; i += 3) {
+      issue(i + 2, v2); commit(i, v0);
+      issue(i + 3, v0); commit(i + 1, v1);
+      issue(i + 4, v1); commit(i + 2, v2);
     }
-    // ------------------------------------------------------------------ epilogue (thread = pixel row, warp = lane quadrant)
+    // ------------------------------------------------------------------ epilogue (thread = pixel row; the two warps of a
+    // TMEM lane quadrant take alternate 32-column pieces)
     mbar_wait(bar_acc, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < NT; c0 += 32) {
+    for (int c0 = 32 * hsel; c0 < NT; c0 += 64) {
       uint32_t acc[32];
-      tmem_ld_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16) + c0, acc);
+      tmem_ld_32x32b_x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, acc);
       tmem_ld_wait();
       if (row_ok) {
         const int cg = n0 + c0;
@@ -141,15 +156,15 @@ __global__ void __launch_bounds__(160) k_lip_conv_tc(const __grid_constant__ CUt
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float v0 = fmaf(__uint_as_float(acc[2 * j]), __ldg(a.scale + cg + 2 * j), __ldg(a.shift + cg + 2 * j));
-          float v1 = fmaf(__uint_as_float(acc[2 * j + 1]), __ldg(a.scale + cg + 2 * j + 1), __ldg(a.shift + cg + 2 * j + 1));
+          float v0f = fmaf(__uint_as_float(acc[2 * j]), __ldg(a.scale + cg + 2 * j), __ldg(a.shift + cg + 2 * j));
+          float v1f = fmaf(__uint_as_float(acc[2 * j + 1]), __ldg(a.scale + cg + 2 * j + 1), __ldg(a.shift + cg + 2 * j + 1));
           if (a.res) {
             const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rr[j]));
-            v0 += rf.x; v1 += rf.y;
+            v0f += rf.x; v1f += rf.y;
           }
           const float s0 = a.act == LIP_ACT_PRELU ? __ldg(a.slope + cg + 2 * j) : 0.f;
           const float s1 = a.act == LIP_ACT_PRELU ? __ldg(a.slope + cg + 2 * j + 1) : 0.f;
-          const __half2 h = __floats2half2_rn(lip_act_tc(v0, a.act, s0), lip_act_tc(v1, a.act, s1));
+          const __half2 h = __floats2half2_rn(lip_act_tc(v0f, a.act, s0), lip_act_tc(v1f, a.act, s1));
           pk[j] = *reinterpret_cast<const uint32_t*>(&h);
         }
         uint4* op = reinterpret_cast<uint4*>(a.out + m * a.Cout + cg);
@@ -180,7 +195,7 @@ __global__ void __launch_bounds__(160) k_lip_conv_tc(const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<1>(tmem, NT);
+  if (warp == 8) tmem_dealloc<1>(tmem, NT);
 }
 
 template <int NT>
@@ -197,7 +212,7 @@ static int lip_conv_tc_launch(const char* packed, const LipConv& c, const LipTcA
   if (int rc = make_tmap_f16(&tmapW, packed + c.off_w16, 2, dims, strides, box)) return rc;
   const long long M = (long long)a.F * a.Ho * a.Wo;
   dim3 grid(ceil_div(M, 128), c.cout / NT);
-  k_lip_conv_tc<NT><<<grid, 160, SMEM, st>>>(tmapW, a);
+  k_lip_conv_tc<NT><<<grid, 288, SMEM, st>>>(tmapW, a);
   VATSS_LAUNCH_OK();
   return 0;
 }

@@ -129,10 +129,11 @@ def test_cuda_embeddings_from_raw_frames(golden_dir, engine, tol):
 
 
 @pytest.mark.gpu
-def test_cuda_frame_chunks_and_utterance_boundaries():
-    """More frames than one trunk pass holds (256): chunk seams and the temporal zero padding at utterance boundaries
-    against the CPU oracle; the tensor engine against the fp32 engine at the same size."""
-    relu_type, B, T = "swish", 3, 90
+def test_cuda_utterance_boundaries_and_frame_chunks():
+    """Temporal zero padding at utterance boundaries against the CPU oracle, and more frames than one trunk pass holds
+    (1024): the chunk seam falls inside an utterance, whose rows must not change (utterances are independent and a
+    pixel's result does not depend on the tile it lands in - bit for bit on both engines)."""
+    relu_type, B, T = "swish", 3, 40
     sd = LO.make_state_dict(relu_type, 11)
     frames = LO.make_frames(B, T, seed=3)
     x = torch.from_numpy(LO.preprocess(frames).astype(np.float32))[:, None]
@@ -143,10 +144,12 @@ def test_cuda_frame_chunks_and_utterance_boundaries():
     assert rel_l2(y, ref) < F32_TOL
     yt = net.set_engine("tensor")(x.to("cuda:0"), lengths=[T] * B).cpu().numpy()
     assert rel_l2(yt, ref) < TENSOR_TOL
-    # utterances are independent: clip 1 alone gives the same rows bit for bit (fp32 engine)
-    net.set_engine("f32")
-    y1 = net(x[1:2].to("cuda:0"), lengths=[T]).cpu().numpy()
-    assert np.array_equal(y1[0], y[1])
+    big = x.to("cuda:0").repeat(9, 1, 1, 1, 1)[:26]            # 26 x 40 = 1040 frames: seam at utterance 25, t = 24
+    for engine, small in (("f32", y), ("tensor", yt)):
+        net.set_engine(engine)
+        yb = net(big, lengths=[T] * 26).cpu().numpy()
+        for b in range(26):
+            assert np.array_equal(yb[b], small[b % 3]), (engine, b)
 
 
 @pytest.mark.gpu

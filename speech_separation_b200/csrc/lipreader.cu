@@ -17,6 +17,7 @@
 // reference) and the packing kernels; lipreader_tc.cu holds the tcgen05 engine for the 3x3 / 1x1 trunk convolutions.
 #include "common.cuh"
 #include "lipreader.cuh"
+#include "tc_kernels.cuh"
 
 namespace vatss {
 
@@ -34,7 +35,8 @@ int lip_conv_table(LipConv* t) {
     c.off_scale = off; off += (size_t)cout * sizeof(float);
     c.off_shift = off; off += (size_t)cout * sizeof(float);
     c.off_slope = off; off += (size_t)cout * sizeof(float);
-    c.off_w16 = off; off += (cin >= 64) ? (size_t)taps * cin * cout * sizeof(__half) : 0;
+    c.off_w16 = off;   // tensor engine: K-major fp16 (the front end as a 64 x 256 matrix, taps zero-padded to 256)
+    off += (cin >= 64) ? (size_t)taps * cin * cout * sizeof(__half) : (size_t)LIP_FRONT_K * cout * sizeof(__half);
     off = (off + 255) & ~(size_t)255;
     if (t) t[n] = c;
     ++n;
@@ -83,6 +85,13 @@ __global__ void k_lip_pack_w(const float* __restrict__ W, int cout, int cin, int
     if (W16) W16[((long long)co * taps + tap) * cin + ci] = __float2half_rn(w);
   }
 }
+// front end for the tensor engine: W (64, 1, 5, 7, 7) -> W16[co * 256 + tap], taps 245..255 zero
+__global__ void k_lip_pack_front16(const float* __restrict__ W, __half* __restrict__ W16) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * LIP_FRONT_K) return;
+  const int tap = i % LIP_FRONT_K, co = i / LIP_FRONT_K;
+  W16[i] = __float2half_rn(tap < 245 ? W[co * 245 + tap] : 0.f);
+}
 // eval-mode BatchNorm as y = x * scale + shift (torch: (x - mean) / sqrt(var + eps) * weight + bias, eps = 1e-5)
 __global__ void k_lip_fold_bn(const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ rm,
                               const float* __restrict__ rv, const float* __restrict__ slope_in, int cout,
@@ -118,6 +127,10 @@ int lip_pack(const float* const* params, int n_params, int relu_type, void* pack
     k_lip_pack_w<<<ceil_div(n, 256) > 1184 ? 1184 : ceil_div(n, 256), 256, 0, st>>>(
         p[0], c.cout, c.cin, c.taps, (float*)(base + c.off_w), c.cin >= 64 ? (__half*)(base + c.off_w16) : nullptr);
     VATSS_LAUNCH_OK();
+    if (i == 0) {
+      k_lip_pack_front16<<<ceil_div(64 * LIP_FRONT_K, 256), 256, 0, st>>>(p[0], (__half*)(base + c.off_w16));
+      VATSS_LAUNCH_OK();
+    }
     k_lip_fold_bn<<<ceil_div(c.cout, 128), 128, 0, st>>>(p[1], p[2], p[3], p[4],
                                                          (relu_type == LIP_ACT_PRELU && !is_shortcut) ? p[5] : nullptr,
                                                          c.cout, (float*)(base + c.off_scale),
@@ -164,69 +177,145 @@ __global__ void __launch_bounds__(192) k_lip_front3d(const LipFrontArgs a) {
   float* Ws = smem;                       // 245 * 64
   float* patch = smem + LF_TAPS * LF_CO;  // 5 * PH * PW
   const int row_tiles = (a.H1 + LF_ROWS - 1) / LF_ROWS;
-  const int f = a.f0 + blockIdx.x / row_tiles, oy0 = (blockIdx.x % row_tiles) * LF_ROWS;
-  const int b = f / a.T, t = f % a.T;
+  // persistent: the 63 KB of weights are read once per CTA; a CTA walks a contiguous run of (frame, row tile) items
   for (int i = threadIdx.x; i < LF_TAPS * LF_CO / 4; i += blockDim.x)
-    reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(a.Wp)[i];
-  for (int i = threadIdx.x; i < LF_KT * PH * PW; i += blockDim.x) {
-    const int px = i % PW, py = (i / PW) % PH, kt = i / (PW * PH);
-    const int tt = t + kt - 2, iy = 2 * oy0 - 3 + py, ix = px - 3;
-    float v = 0.f;   // zero padding lives in the normalised domain
-    if (tt >= 0 && tt < a.T && iy >= 0 && iy < a.Hc && ix >= 0 && ix < a.Wc)
-      v = a.vid[(((long long)b * a.T + tt) * a.Hin + a.y0 + iy) * a.Win + a.x0 + ix] * a.pre_scale + a.pre_shift;
-    patch[i] = v;
-  }
-  __syncthreads();
+    reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(a.Wp) + i);
+  const int total = a.nf * row_tiles;
+  const int per = (total + gridDim.x - 1) / gridDim.x;
+  const int it0 = blockIdx.x * per, it1 = (it0 + per < total) ? it0 + per : total;
   // thread = (output row r, pixel pair j, 32-channel half h): 2 x 32 accumulators, so a broadcast weight read feeds
-  // two FMAs and the three 16-byte patch reads of a (kt, ky) row feed all 7 x 2 taps (FMA-bound instead of LSU-bound)
+  // two FMAs and the three 16-byte patch reads of a (kt, ky) row feed all 7 x 2 taps
   const int nthr = LF_ROWS * npairs;
   const int h = threadIdx.x / nthr, p = threadIdx.x % nthr;
-  if (h >= 2) return;
-  const int r = p / npairs, j = p % npairs, oy = oy0 + r;
-  float acc0[32], acc1[32];
+  const int r = p / npairs, j = p % npairs;
+  const int npatch = LF_KT * PH * PW;
+  for (int item = it0; item < it1; ++item) {
+    const int f = a.f0 + item / row_tiles, oy0 = (item % row_tiles) * LF_ROWS;
+    const int b = f / a.T, t = f % a.T;
+    __syncthreads();   // the previous item's patch is no longer read
+    for (int i0 = threadIdx.x; i0 < npatch; i0 += 8 * 192) {
+      float v[8];
 #pragma unroll
-  for (int q = 0; q < 32; ++q) acc0[q] = acc1[q] = 0.f;
-  for (int kt = 0; kt < LF_KT; ++kt)
-    for (int ky = 0; ky < LF_KS; ++ky) {
-      const float4* pr = reinterpret_cast<const float4*>(patch + (kt * PH + 2 * r + ky) * PW + 4 * j);
-      const float4 q0 = pr[0], q1 = pr[1], q2 = pr[2];
-      const float pv[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-      const float* wrow = Ws + ((kt * LF_KS + ky) * LF_KS) * LF_CO + h * 32;
+      for (int u = 0; u < 8; ++u) {   // eight independent global loads in flight per thread
+        const int i = i0 + u * 192;
+        const int px = i % PW, py = (i / PW) % PH, kt = i / (PW * PH);
+        const int tt = t + kt - 2, iy = 2 * oy0 - 3 + py, ix = px - 3;
+        v[u] = 0.f;   // zero padding lives in the normalised domain
+        if (i < npatch && tt >= 0 && tt < a.T && iy >= 0 && iy < a.Hc && ix >= 0 && ix < a.Wc)
+          v[u] = __ldg(a.vid + (((long long)b * a.T + tt) * a.Hin + a.y0 + iy) * a.Win + a.x0 + ix) * a.pre_scale + a.pre_shift;
+      }
 #pragma unroll
-      for (int kx = 0; kx < LF_KS; ++kx) {
-        const float va = pv[kx], vb = pv[kx + 2];
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u * 192 < npatch) patch[i0 + u * 192] = v[u];
+    }
+    __syncthreads();
+    const int oy = oy0 + r;
+    if (h >= 2 || oy >= a.H1) continue;
+    float acc0[32], acc1[32];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 w = *reinterpret_cast<const float4*>(wrow + kx * LF_CO + 4 * q);
-          acc0[4 * q] = fmaf(va, w.x, acc0[4 * q]);         acc1[4 * q] = fmaf(vb, w.x, acc1[4 * q]);
-          acc0[4 * q + 1] = fmaf(va, w.y, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(vb, w.y, acc1[4 * q + 1]);
-          acc0[4 * q + 2] = fmaf(va, w.z, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(vb, w.z, acc1[4 * q + 2]);
-          acc0[4 * q + 3] = fmaf(va, w.w, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(vb, w.w, acc1[4 * q + 3]);
+    for (int q = 0; q < 32; ++q) acc0[q] = acc1[q] = 0.f;
+    for (int kt = 0; kt < LF_KT; ++kt)
+      for (int ky = 0; ky < LF_KS; ++ky) {
+        const float4* pr = reinterpret_cast<const float4*>(patch + (kt * PH + 2 * r + ky) * PW + 4 * j);
+        const float4 q0 = pr[0], q1 = pr[1], q2 = pr[2];
+        const float pv[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+        const float* wrow = Ws + ((kt * LF_KS + ky) * LF_KS) * LF_CO + h * 32;
+#pragma unroll
+        for (int kx = 0; kx < LF_KS; ++kx) {
+          const float va = pv[kx], vb = pv[kx + 2];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 w = *reinterpret_cast<const float4*>(wrow + kx * LF_CO + 4 * q);
+            acc0[4 * q] = fmaf(va, w.x, acc0[4 * q]);         acc1[4 * q] = fmaf(vb, w.x, acc1[4 * q]);
+            acc0[4 * q + 1] = fmaf(va, w.y, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(vb, w.y, acc1[4 * q + 1]);
+            acc0[4 * q + 2] = fmaf(va, w.z, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(vb, w.z, acc1[4 * q + 2]);
+            acc0[4 * q + 3] = fmaf(va, w.w, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(vb, w.w, acc1[4 * q + 3]);
+          }
         }
       }
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      const int c = h * 32 + q;
+      const float sc = a.scale[c], sh = a.shift[c], sl = a.slope[c];
+      acc0[q] = lip_act(fmaf(acc0[q], sc, sh), a.act, sl);
+      acc1[q] = lip_act(fmaf(acc1[q], sc, sh), a.act, sl);
     }
-  if (oy >= a.H1) return;
-#pragma unroll
-  for (int q = 0; q < 32; ++q) {
-    const int c = h * 32 + q;
-    const float sc = a.scale[c], sh = a.shift[c], sl = a.slope[c];
-    acc0[q] = lip_act(fmaf(acc0[q], sc, sh), a.act, sl);
-    acc1[q] = lip_act(fmaf(acc1[q], sc, sh), a.act, sl);
-  }
-  const long long o = ((((long long)(f - a.f0)) * a.H1 + oy) * a.W1 + 2 * j) * LF_CO + h * 32;
-#pragma unroll
-  for (int q = 0; q < 8; ++q)
-    *reinterpret_cast<float4*>(a.out + o + 4 * q) = make_float4(acc0[4 * q], acc0[4 * q + 1], acc0[4 * q + 2], acc0[4 * q + 3]);
-  if (2 * j + 1 < a.W1) {
+    const long long o = ((((long long)(f - a.f0)) * a.H1 + oy) * a.W1 + 2 * j) * LF_CO + h * 32;
 #pragma unroll
     for (int q = 0; q < 8; ++q)
-      *reinterpret_cast<float4*>(a.out + o + LF_CO + 4 * q) =
-          make_float4(acc1[4 * q], acc1[4 * q + 1], acc1[4 * q + 2], acc1[4 * q + 3]);
+      *reinterpret_cast<float4*>(a.out + o + 4 * q) = make_float4(acc0[4 * q], acc0[4 * q + 1], acc0[4 * q + 2], acc0[4 * q + 3]);
+    if (2 * j + 1 < a.W1) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(a.out + o + LF_CO + 4 * q) =
+            make_float4(acc1[4 * q], acc1[4 * q + 1], acc1[4 * q + 2], acc1[4 * q + 3]);
+    }
   }
 }
 
-// MaxPool 3x3, stride 2, pad 1 over (F, H, W, 64) -> (F, Ho, Wo, 64); one thread per 4 channels of an output pixel
-__global__ void k_lip_maxpool(const float* __restrict__ in, int F, int H, int W, int C, int Ho, int Wo,
+// Tensor engine: the front-end convolution as a GEMM.  This kernel writes the fp16 im2col matrix
+//   A[(frame, oy, ox), tap] = video'[t + kt - 2, 2 oy + ky - 3, 2 ox + kx - 3],  tap = (kt 7 + ky) 7 + kx  (< 245, rest 0)
+// (256 columns = 512 bytes per output pixel) and the 1 x 1 "convolution" kernel of lipreader_tc.cu contracts it with the
+// 64 x 256 weight matrix (4 K slabs) - BatchNorm, activation and the fp16 store are that kernel's epilogue.
+// CTA = (frame, 4 output rows): patch in shared memory as above, then thread = (pixel, 16-byte chunk of 8 taps):
+// the 32 lanes of a warp write the 512 contiguous bytes of one pixel.
+__global__ void __launch_bounds__(256) k_lip_im2col_front(const LipFrontArgs a, __half* __restrict__ A16) {
+  extern __shared__ __align__(16) float smem[];
+  const int PW = a.Wc + 6, PH = 2 * LF_ROWS + 5;
+  float* patch = smem;                                                  // 5 * PH * PW
+  int* tapoff = reinterpret_cast<int*>(smem + LF_KT * PH * PW);         // 256 offsets (-1: zero column)
+  const int row_tiles = (a.H1 + LF_ROWS - 1) / LF_ROWS;
+  const int f = a.f0 + blockIdx.x / row_tiles, oy0 = (blockIdx.x % row_tiles) * LF_ROWS;
+  const int b = f / a.T, t = f % a.T;
+  {
+    const int tap = threadIdx.x;   // 256 threads
+    const int kx = tap % LF_KS, ky = (tap / LF_KS) % LF_KS, kt = tap / (LF_KS * LF_KS);
+    tapoff[tap] = tap < LF_TAPS ? (kt * PH + ky) * PW + kx : -1;
+  }
+  const int npatch = LF_KT * PH * PW;
+  for (int i0 = threadIdx.x; i0 < npatch; i0 += 8 * 256) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * 256;
+      const int px = i % PW, py = (i / PW) % PH, kt = i / (PW * PH);
+      const int tt = t + kt - 2, iy = 2 * oy0 - 3 + py, ix = px - 3;
+      v[u] = 0.f;
+      if (i < npatch && tt >= 0 && tt < a.T && iy >= 0 && iy < a.Hc && ix >= 0 && ix < a.Wc)
+        v[u] = __ldg(a.vid + (((long long)b * a.T + tt) * a.Hin + a.y0 + iy) * a.Win + a.x0 + ix) * a.pre_scale + a.pre_shift;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (i0 + u * 256 < npatch) patch[i0 + u * 256] = v[u];
+  }
+  __syncthreads();
+  const int rows = (a.H1 - oy0 < LF_ROWS) ? a.H1 - oy0 : LF_ROWS;
+  const int ntask = rows * a.W1 * (LIP_FRONT_K / 8);
+  for (int idx = threadIdx.x; idx < ntask; idx += 256) {
+    const int c = idx & 31, p = idx >> 5;
+    const int r = p / a.W1, ox = p - r * a.W1;
+    const float* pb = patch + (2 * r) * PW + 2 * ox;
+    uint32_t pk[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int o0 = tapoff[8 * c + 2 * q], o1 = tapoff[8 * c + 2 * q + 1];
+      const __half2 h = __floats2half2_rn(o0 >= 0 ? pb[o0] : 0.f, o1 >= 0 ? pb[o1] : 0.f);
+      pk[q] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    const long long row = (((long long)(f - a.f0)) * a.H1 + oy0 + r) * a.W1 + ox;
+    *reinterpret_cast<uint4*>(A16 + row * LIP_FRONT_K + 8 * c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// MaxPool 3x3, stride 2, pad 1 over (F, H, W, C) -> (F, Ho, Wo, C); one thread per 4 channels of an output pixel
+__device__ __forceinline__ float4 lip_load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 lip_load4(const __half* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename TIN>
+__global__ void k_lip_maxpool(const TIN* __restrict__ in, int F, int H, int W, int C, int Ho, int Wo,
                               float* __restrict__ out, __half* __restrict__ out16) {
   const int c4 = C / 4;
   const long long n = (long long)F * Ho * Wo * c4;
@@ -241,12 +330,12 @@ __global__ void k_lip_maxpool(const float* __restrict__ in, int F, int H, int W,
       for (int kx = 0; kx < 3; ++kx) {
         const int ix = 2 * ox - 1 + kx;
         if (ix < 0 || ix >= W) continue;
-        const float4 v = *reinterpret_cast<const float4*>(in + (((f * H + iy) * W + ix) * (long long)C) + 4 * c);
+        const float4 v = lip_load4(in + (((f * H + iy) * W + ix) * (long long)C) + 4 * c);
         m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
       }
     }
     const long long o = ((f * Ho + oy) * Wo + ox) * (long long)C + 4 * c;
-    *reinterpret_cast<float4*>(out + o) = m;
+    if (out) *reinterpret_cast<float4*>(out + o) = m;
     if (out16) {
       *reinterpret_cast<__half2*>(out16 + o) = __floats2half2_rn(m.x, m.y);
       *reinterpret_cast<__half2*>(out16 + o + 2) = __floats2half2_rn(m.z, m.w);
@@ -374,8 +463,9 @@ size_t lip_workspace_bytes(int B, int T, int Hc, int Wc) {
   LipGeom g;
   if (B <= 0 || T <= 0 || lip_geometry(Hc, Wc, &g)) return 0;
   const long long fc = lip_chunk_frames((long long)B * T);
-  // fp32 buffers + fp16 shadows of the trunk buffers (tensor engine) + slack
-  return (size_t)(fc * lip_frame_floats(g) * 4 + fc * 4ll * g.H[0] * g.W[0] * 64 * 2 + 4096);
+  // fp32 buffers + fp16 shadows of the trunk buffers and the front end's im2col matrix (tensor engine) + slack
+  return (size_t)(fc * lip_frame_floats(g) * 4 + fc * 4ll * g.H[0] * g.W[0] * 64 * 2 +
+                  fc * (long long)g.H1 * g.W1 * LIP_FRONT_K * 2 + 4096);
 }
 
 int lip_forward(const void* packed, size_t packed_bytes, int relu_type, const float* video, int B, int T, int Hin,
@@ -403,6 +493,7 @@ int lip_forward(const void* packed, size_t packed_bytes, int relu_type, const fl
   for (int i = 0; i < 4; ++i) tb[i] = buf0 + (long long)FC * g.H1 * g.W1 * 64 + i * trunk_floats;
   __half* tb16[4];
   for (int i = 0; i < 4; ++i) tb16[i] = (__half*)(tb[3] + trunk_floats) + i * trunk_floats;
+  __half* im2col16 = tb16[3] + trunk_floats;   // (FC, H1, W1, 256) fp16
 
   static PerDeviceOnce configured;
   const int front_smem = (LF_TAPS * LF_CO + LF_KT * (2 * LF_ROWS + 5) * (4 * front_pairs + 8)) * 4;
@@ -410,23 +501,39 @@ int lip_forward(const void* packed, size_t packed_bytes, int relu_type, const fl
     VATSS_CUDA_OK(cudaFuncSetAttribute(k_lip_front3d, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   VATSS_CHECK_ARG(front_smem <= 100 * 1024, "lipreader: front-end patch too large");
 
+  static PerDeviceOnce configured_im2col;
+  const int im2col_smem = (LF_KT * (2 * LF_ROWS + 5) * (Wc + 6)) * 4 + 256 * 4;
+  if (configured_im2col.first())
+    VATSS_CUDA_OK(cudaFuncSetAttribute(k_lip_im2col_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  VATSS_CHECK_ARG(im2col_smem <= 64 * 1024, "lipreader: front-end patch too large");
+
   for (long long f0 = 0; f0 < F; f0 += FC) {
     const int nf = (int)((F - f0) < FC ? (F - f0) : FC);
-    {
-      LipFrontArgs a;
-      a.vid = video; a.B = B; a.T = T; a.Hin = Hin; a.Win = Win; a.y0 = y0; a.x0 = x0; a.Hc = Hc; a.Wc = Wc;
-      a.H1 = g.H1; a.W1 = g.W1; a.pre_scale = pre_scale; a.pre_shift = pre_shift;
-      a.Wp = (const float*)(pk + t[0].off_w); a.scale = (const float*)(pk + t[0].off_scale);
-      a.shift = (const float*)(pk + t[0].off_shift); a.slope = (const float*)(pk + t[0].off_slope);
-      a.act = relu_type; a.out = buf0; a.out16 = nullptr; a.f0 = (int)f0; a.nf = nf;
-      k_lip_front3d<<<nf * ((g.H1 + LF_ROWS - 1) / LF_ROWS), 192, front_smem, st>>>(a);
-      VATSS_LAUNCH_OK();
-    }
     const bool tc = engine == VATSS_LIP_ENGINE_TENSOR;
-    {
-      const long long n = (long long)nf * g.H[0] * g.W[0] * 16;
-      k_lip_maxpool<<<(int)(ceil_div(n, 256) > 4736 ? 4736 : ceil_div(n, 256)), 256, 0, st>>>(
-          buf0, nf, g.H1, g.W1, 64, g.H[0], g.W[0], tb[0], tc ? tb16[0] : nullptr);
+    LipFrontArgs a;
+    a.vid = video; a.B = B; a.T = T; a.Hin = Hin; a.Win = Win; a.y0 = y0; a.x0 = x0; a.Hc = Hc; a.Wc = Wc;
+    a.H1 = g.H1; a.W1 = g.W1; a.pre_scale = pre_scale; a.pre_shift = pre_shift;
+    a.Wp = (const float*)(pk + t[0].off_w); a.scale = (const float*)(pk + t[0].off_scale);
+    a.shift = (const float*)(pk + t[0].off_shift); a.slope = (const float*)(pk + t[0].off_slope);
+    a.act = relu_type; a.out = buf0; a.out16 = nullptr; a.f0 = (int)f0; a.nf = nf;
+    const int items = nf * ((g.H1 + LF_ROWS - 1) / LF_ROWS);
+    const long long npool = (long long)nf * g.H[0] * g.W[0] * 16;
+    const int pool_grid = (int)(ceil_div(npool, 256) > 4736 ? 4736 : ceil_div(npool, 256));
+    if (tc) {
+      // im2col (fp16) -> GEMM with the 64 x 256 weight matrix on the tensor cores (+ BN + act) -> max pool
+      k_lip_im2col_front<<<items, 256, im2col_smem, st>>>(a, im2col16);
+      VATSS_LAUNCH_OK();
+      LipConv cf = t[0];
+      cf.taps = 1; cf.cin = LIP_FRONT_K; cf.ks = 1; cf.stride = 1; cf.pad = 0;
+      __half* front16 = (__half*)buf0;   // (nf, H1, W1, 64) fp16 in the (unused) fp32 front-end buffer
+      if (int rc = lip_conv_tc(pk, cf, im2col16, nf, g.H1, g.W1, g.H1, g.W1, nullptr, relu_type, front16, st)) return rc;
+      k_lip_maxpool<__half><<<pool_grid, 256, 0, st>>>(front16, nf, g.H1, g.W1, 64, g.H[0], g.W[0], nullptr, tb16[0]);
+      VATSS_LAUNCH_OK();
+    } else {
+      const int slots = 2 * num_sms();
+      k_lip_front3d<<<items < slots ? items : slots, 192, front_smem, st>>>(a);
+      VATSS_LAUNCH_OK();
+      k_lip_maxpool<float><<<pool_grid, 256, 0, st>>>(buf0, nf, g.H1, g.W1, 64, g.H[0], g.W[0], tb[0], nullptr);
       VATSS_LAUNCH_OK();
     }
     int cur = 0, H = g.H[0], W = g.W[0], ci = 1, final_c = 64;

@@ -8,6 +8,7 @@ namespace vatss {
 enum { LIP_ACT_NONE = 0, LIP_ACT_RELU = 1, LIP_ACT_PRELU = 2, LIP_ACT_SWISH = 3 };
 constexpr int LIP_NCONV = 25;    // front end + 8 blocks x (conv1, conv2, shortcut slot)
 constexpr int LIP_PSLOTS = 6;    // per conv: weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, prelu slopes
+constexpr int LIP_FRONT_K = 256;  // front end on the tensor engine: 5 x 7 x 7 = 245 taps zero-padded to 4 K slabs
 constexpr int LIP_CHUNK = 1024;  // frames per pass through the trunk (bounds the workspace)
 
 struct LipConv {

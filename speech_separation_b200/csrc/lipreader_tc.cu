@@ -5,10 +5,10 @@
 //   D[128 pixels, NT channels] += A_slab[128 pixels, 64 input channels of one tap] x W_slab[NT, 64]^T
 // for the taps x (Cin / 64) K slabs of the convolution.  K = 9 Cin is 576 ... 4608, so - unlike the per-token
 // projections of the separation path (tc_gemm.cu: K <= 256, W resident) - this is a K-pipelined kernel:
-//   warps 0..7  A producers, two threads per output pixel of the tile: the 128-byte channel vector of the pixel's tap
-//               neighbour (zeros outside the image) goes into the SWIZZLE_128B K-major operand layout with 16-byte
-//               shared-memory stores; any stride / padding / image size, every tile has 128 useful rows.  The loads
-//               of three slabs are in flight per thread.  Thread 0 also fetches the weight slab with one TMA box.
+//   warps 0..7  A producers: the 128-byte channel vector of every output pixel's tap neighbour (zeros outside the
+//               image) goes into the SWIZZLE_128B K-major operand layout with 16-byte shared-memory stores (eight lanes
+//               per pixel: whole lines per warp instruction); any stride / padding / image size, every tile has 128
+//               useful rows.  The loads of three slabs are in flight per thread.  Thread 0 also fetches the weight slab with one TMA box.
 //               After the last slab the same warps are the epilogue: tcgen05.ld of their TMEM lane quadrant, folded
 //               BatchNorm, shortcut add, activation, fp16 store.
 //   warp 8      MMA issuer: 4 x tcgen05.mma (M = 128, N = NT, K = 16) per slab, accumulator in TMEM, tcgen05.commit
@@ -81,15 +81,27 @@ __global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ 
   const int nslabs = a.ks * a.ks * cblocks;
 
   if (warp < 8) {
-    // ------------------------------------------------------------------ A producers (thread = half a pixel row)
+    // ------------------------------------------------------------------ A producers
+    // Gather mapping: thread = (16-byte chunk ch of the 128-byte channel vector, rows g, g + 32, g + 64, g + 96), so the
+    // eight lanes of a row read one whole line and a warp instruction touches 4 lines (a thread-per-row mapping
+    // touches 32 lines with 16 bytes each and is bound by the L1 tag rate).  The epilogue below is thread = row.
     const int r = threadIdx.x & 127, hsel = threadIdx.x >> 7;
     const long long m = m0 + r;
     const bool row_ok = m < M;
-    int f = 0, oy = 0, ox = 0;
-    if (row_ok) {
-      ox = (int)(m % a.Wo);
-      oy = (int)((m / a.Wo) % a.Ho);
-      f = (int)(m / ((long long)a.Wo * a.Ho));
+    const int ch = threadIdx.x & 7, g = threadIdx.x >> 3;
+    int gy[4], gx[4];          // stride * oy - pad, stride * ox - pad of the thread's four rows (gy = -2^20: row beyond M)
+    long long gbase[4];        // frame offset (elements)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long mk = m0 + g + 32 * k;
+      if (mk < M) {
+        const int ox = (int)(mk % a.Wo), oy = (int)((mk / a.Wo) % a.Ho);
+        gy[k] = oy * a.stride - a.pad;
+        gx[k] = ox * a.stride - a.pad;
+        gbase[k] = (mk / ((long long)a.Wo * a.Ho)) * a.H * a.W * a.Cin + ch * 8;
+      } else {
+        gy[k] = -(1 << 20); gx[k] = 0; gbase[k] = 0;
+      }
     }
     // Three slabs of loads are in flight per thread (registers) while earlier slabs are written to the ring: the
     // global / L2 latency of a gather (~1 us) is several times the tensor-core time of a slab.
@@ -97,14 +109,13 @@ __global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ 
       if (i >= nslabs) return;
       const int tap = i / cblocks, cb = i - tap * cblocks;
       const int ky = tap / a.ks, kx = tap - ky * a.ks;
-      const int iy = oy * a.stride + ky - a.pad, ix = ox * a.stride + kx - a.pad;
-      if (row_ok && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.in + (((long long)f * a.H + iy) * a.W + ix) * a.Cin + cb * 64) + 4 * hsel;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = __ldg(src + c);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = make_uint4(0u, 0u, 0u, 0u);
+      for (int k = 0; k < 4; ++k) {
+        const int iy = gy[k] + ky, ix = gx[k] + kx;
+        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+          v[k] = __ldg(reinterpret_cast<const uint4*>(a.in + gbase[k] + ((long long)iy * a.W + ix) * a.Cin + cb * 64));
+        else
+          v[k] = make_uint4(0u, 0u, 0u, 0u);
       }
     };
     auto commit = [&](int i, const uint4* v) {
@@ -117,9 +128,9 @@ __global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ 
         tma_load_2d(sA + LT_A_BYTES, &tmapW, bar_full + 8 * s, i * 64, n0);
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t dst = sA + sw128_offset((uint32_t)r, (uint32_t)(4 * hsel + c));
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[c].x), "r"(v[c].y), "r"(v[c].z), "r"(v[c].w)
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t dst = sA + sw128_offset((uint32_t)(g + 32 * k), (uint32_t)ch);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[k].x), "r"(v[k].y), "r"(v[k].z), "r"(v[k].w)
                      : "memory");
       }
       fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy operand reads

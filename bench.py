@@ -216,6 +216,7 @@ def main():
                     help="dptn_av = the headline config; the others are the remaining BASELINE.json models")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--no-lipreader", action="store_true", help="skip the lipreader front-end side measurement")
     ap.add_argument("--total-utterances", type=int, default=0,
                     help="cfg-3: a fixed job of this many utterances, sharded over the ranks (strong scaling)")
     ap.add_argument("--micro-batch", type=int, default=32)
@@ -513,6 +514,37 @@ def main():
                                                   "forward only, fp32 / TF32 defaults, 3 steps after 2 warm-ups"}
         except Exception as e:   # a baseline must never take the bench line down
             line["eager_gpu_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
+    if world == 1 and av and not args.no_lipreader and not sharded_job:
+        # the lipreader front end that produces this batch's lip embeddings from raw mouth crops
+        # (2 speakers x B clips x Tv frames of 96 x 96), timed beside the separation step; not part of `value`
+        try:
+            from speech_separation_b200 import Lipreading, extract_embeddings
+            torch.manual_seed(7)
+            lip = Lipreading(relu_type="swish", extract_feats=True).to(dev)
+            Tv = 25 * T // SR
+            video = (torch.rand(2 * B, Tv, 96, 96, device=dev) * 255).round()
+            for _ in range(2):
+                extract_embeddings(lip, video)
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = lib.vatss_launch_count()
+            t0.record()
+            for _ in range(3):
+                emb = extract_embeddings(lip, video)
+            t1.record()
+            torch.cuda.synchronize()
+            lms = t0.elapsed_time(t1) / 3
+            frames = 2 * B * Tv
+            line["lipreader_frontend"] = {
+                "frames_per_s": frames / (lms * 1e-3), "ms_per_batch_video": lms, "frames": frames,
+                "tflops": frames * 632317952 / (lms * 1e-3) / 1e12, "gpu_launches": int(lib.vatss_launch_count() - n0),
+                "output": list(emb.shape), "engine": "tensor (tcgen05 trunk, fp16 activations)",
+                "what": "Lipreading(video, resnet, swish, extract_feats=True) on raw 96 x 96 mouth crops of this batch "
+                        "(crop + normalisation folded into the first kernel), 3 runs after 2 warm-ups; 632.3 MFLOP per frame"}
+            del lip, video, emb
+        except Exception as e:   # a side measurement must never take the bench line down
+            line["lipreader_frontend"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
         _, _, info = cpu_reference_arm(2, 1, CPU_SAMPLE_BATCH, T, args.model)

@@ -250,6 +250,12 @@ int vatss_profile_end(float* ms_per_stage, int* launches_per_stage, int n_stages
 #define VATSS_LIP_PSLOTS 6
 #define VATSS_LIP_ENGINE_F32 0
 #define VATSS_LIP_ENGINE_TENSOR 1
+/* experiments only (tools/lipreader_ablate.py): switch parts of the tcgen05 convolution kernel off to time the rest:
+ * bit 0 no gather loads, bit 1 no epilogue math / stores, bit 2 no weight TMA.  0 = production. */
+void vatss_debug_lipreader(int flags);
+/* debug: device buffer (>= 8192 int64) receiving globaltimer / clock64 stamps of the first 1024 CTAs of every
+ * following tcgen05 convolution launch (the last launch wins); NULL disables */
+void vatss_debug_lipreader_trace(void* dev_buffer);
 size_t vatss_lipreader_packed_bytes(void);
 /* scratch for B x T frames cropped to Hc x Wc (frames are processed in chunks, so this is bounded) */
 size_t vatss_lipreader_workspace_bytes(int B, int T, int Hc, int Wc);

@@ -26,6 +26,9 @@ int lip_forward(const void* packed, size_t packed_bytes, int relu_type, const fl
                 int Win, int y0, int x0, int Hc, int Wc, float pre_scale, float pre_shift, float* out, void* workspace,
                 size_t workspace_bytes, int engine, cudaStream_t st);
 
+extern long long* g_lip_trace;
+extern int g_lip_dbg;   // experiment switches of k_lip_conv_tc (0 in production)
+
 // tcgen05 engine: out16 (F, Ho, Wo, Cout) = act(conv(in16 (F, H, W, Cin)) * scale + shift + res16), fp16 activations,
 // fp32 accumulation in TMEM
 int lip_conv_tc(const char* packed, const LipConv& c, const __half* in16, int F, int H, int W, int Ho, int Wo,

@@ -24,6 +24,8 @@ using namespace ptx;
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
 
+int g_lip_dbg = 0;
+long long* g_lip_trace = nullptr;   // debug: per-CTA clock64 / globaltimer stamps of the next launches (NULL in production)
 constexpr int LT_STAGES = 3;
 constexpr int LT_A_BYTES = 128 * 128;
 
@@ -34,6 +36,8 @@ struct LipTcArgs {
   const __half* res;
   int act;
   __half* out;
+  long long* trace;   // debug: 8 stamps per CTA for the first 1024 CTAs
+  int dbg;   // experiments (vatss_debug_lipreader): bit 0 no gather loads, bit 1 no epilogue stores, bit 2 no weight TMA
 };
 
 __device__ __forceinline__ float lip_act_tc(float v, int act, float slope) {
@@ -54,11 +58,23 @@ __global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ 
   const uint32_t bar_full = bars, bar_empty = bars + 8 * LT_STAGES, bar_acc = bars + 16 * LT_STAGES;
   const uint32_t tmem_slot_addr = bars + 16 * LT_STAGES + 8;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + LT_STAGES * STAGE_BYTES + 16 * LT_STAGES + 8);
+  float* sPar = reinterpret_cast<float*>(gen + LT_STAGES * STAGE_BYTES + 16 * LT_STAGES + 16);   // scale, shift, slope [NT]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool tr = a.trace != nullptr && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 1024;
+  long long* trow = a.trace + (tr ? blockIdx.x * 8 : 0);
+  if (tr) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    trow[0] = (long long)gt;
+    trow[1] = clock64();
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    trow[7] = smid;
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < LT_STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 257);   // 256 half-row writers + the expect_tx arrival of the weight TMA
+      mbar_init(bar_full + 8 * s, 9);     // one arrival per producer warp + the expect_tx arrival of the weight TMA
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_acc, 1);
@@ -69,14 +85,21 @@ __global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ 
     tmem_alloc<1>(tmem_slot_addr, NT);
     tmem_relinquish<1>();
   }
+  const int n0 = blockIdx.y * NT;
+  // folded BatchNorm / PReLU parameters of this CTA's channels: read once (the streaming gathers evict them from L1)
+  for (int i = threadIdx.x; i < NT; i += blockDim.x) {
+    sPar[i] = a.scale[n0 + i];
+    sPar[NT + i] = a.shift[n0 + i];
+    sPar[2 * NT + i] = a.slope[n0 + i];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (tr) trow[2] = clock64();   // prologue done
 
-  const long long M = (long long)a.F * a.Ho * a.Wo;
-  const long long m0 = (long long)blockIdx.x * 128;
-  const int n0 = blockIdx.y * NT;
+  const int M = a.F * a.Ho * a.Wo;            // < 2^31: at most LIP_CHUNK frames per launch (32-bit index maths)
+  const int m0 = blockIdx.x * 128;
   const int cblocks = a.Cin / 64;
   const int nslabs = a.ks * a.ks * cblocks;
 
@@ -86,19 +109,20 @@ __global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ 
     // eight lanes of a row read one whole line and a warp instruction touches 4 lines (a thread-per-row mapping
     // touches 32 lines with 16 bytes each and is bound by the L1 tag rate).  The epilogue below is thread = row.
     const int r = threadIdx.x & 127, hsel = threadIdx.x >> 7;
-    const long long m = m0 + r;
+    const int m = m0 + r;
     const bool row_ok = m < M;
     const int ch = threadIdx.x & 7, g = threadIdx.x >> 3;
     int gy[4], gx[4];          // stride * oy - pad, stride * ox - pad of the thread's four rows (gy = -2^20: row beyond M)
     long long gbase[4];        // frame offset (elements)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const long long mk = m0 + g + 32 * k;
+      const int mk = m0 + g + 32 * k;
       if (mk < M) {
-        const int ox = (int)(mk % a.Wo), oy = (int)((mk / a.Wo) % a.Ho);
+        const int fr = mk / (a.Wo * a.Ho), rem = mk - fr * (a.Wo * a.Ho);
+        const int oy = rem / a.Wo, ox = rem - oy * a.Wo;
         gy[k] = oy * a.stride - a.pad;
         gx[k] = ox * a.stride - a.pad;
-        gbase[k] = (mk / ((long long)a.Wo * a.Ho)) * a.H * a.W * a.Cin + ch * 8;
+        gbase[k] = (long long)fr * a.H * a.W * a.Cin + ch * 8;
       } else {
         gy[k] = -(1 << 20); gx[k] = 0; gbase[k] = 0;
       }
@@ -112,7 +136,7 @@ __global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ 
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int iy = gy[k] + ky, ix = gx[k] + kx;
-        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W && !(a.dbg & 1))
           v[k] = __ldg(reinterpret_cast<const uint4*>(a.in + gbase[k] + ((long long)iy * a.W + ix) * a.Cin + cb * 64));
         else
           v[k] = make_uint4(0u, 0u, 0u, 0u);
@@ -121,11 +145,15 @@ __global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ 
     auto commit = [&](int i, const uint4* v) {
       if (i >= nslabs) return;
       const int s = i % LT_STAGES, ph = (i / LT_STAGES) & 1;
-      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      if (lane == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1);   // one poller per warp
+      __syncwarp();
       const uint32_t sA = base + s * STAGE_BYTES;
       if (threadIdx.x == 0) {
-        mbar_expect_tx(bar_full + 8 * s, B_BYTES);
-        tma_load_2d(sA + LT_A_BYTES, &tmapW, bar_full + 8 * s, i * 64, n0);
+        if (a.dbg & 4) mbar_arrive(bar_full + 8 * s);
+        else {
+          mbar_expect_tx(bar_full + 8 * s, B_BYTES);
+          tma_load_2d(sA + LT_A_BYTES, &tmapW, bar_full + 8 * s, i * 64, n0);
+        }
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -134,7 +162,8 @@ __global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ 
                      : "memory");
       }
       fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy operand reads
-      mbar_arrive(bar_full + 8 * s);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);   // one arrival per warp (256 arrivals on one mbarrier serialise)
     };
     uint4 v0[4], v1[4], v2[4];
     issue(0, v0);
@@ -146,18 +175,24 @@ __global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ 
     }
     // ------------------------------------------------------------------ epilogue (thread = pixel row; the two warps of a
     // TMEM lane quadrant take alternate 32-column pieces)
-    mbar_wait(bar_acc, 0);
+    if (tr) trow[3] = clock64();   // all slabs written
+    if (lane == 0) mbar_wait(bar_acc, 0);
+    __syncwarp();
     tc_fence_after();
+    if (tr) trow[4] = clock64();   // accumulator complete
 #pragma unroll 1
     for (int c0 = 32 * hsel; c0 < NT; c0 += 64) {
       uint32_t acc[32];
       tmem_ld_32x32b_x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, acc);
       tmem_ld_wait();
-      if (row_ok) {
+      if (row_ok && !(a.dbg & 2)) {
         const int cg = n0 + c0;
+        const float* sSc = sPar + c0;
+        const float* sSh = sPar + NT + c0;
+        const float* sSl = sPar + 2 * NT + c0;
         uint32_t rr[16];
         if (a.res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(a.res + m * a.Cout + cg);
+          const uint4* rp = reinterpret_cast<const uint4*>(a.res + (long long)m * a.Cout + cg);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint4 x = __ldg(rp + q);
@@ -167,18 +202,17 @@ __global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ 
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float v0f = fmaf(__uint_as_float(acc[2 * j]), __ldg(a.scale + cg + 2 * j), __ldg(a.shift + cg + 2 * j));
-          float v1f = fmaf(__uint_as_float(acc[2 * j + 1]), __ldg(a.scale + cg + 2 * j + 1), __ldg(a.shift + cg + 2 * j + 1));
+          float v0f = fmaf(__uint_as_float(acc[2 * j]), sSc[2 * j], sSh[2 * j]);
+          float v1f = fmaf(__uint_as_float(acc[2 * j + 1]), sSc[2 * j + 1], sSh[2 * j + 1]);
           if (a.res) {
             const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rr[j]));
             v0f += rf.x; v1f += rf.y;
           }
-          const float s0 = a.act == LIP_ACT_PRELU ? __ldg(a.slope + cg + 2 * j) : 0.f;
-          const float s1 = a.act == LIP_ACT_PRELU ? __ldg(a.slope + cg + 2 * j + 1) : 0.f;
+          const float s0 = sSl[2 * j], s1 = sSl[2 * j + 1];
           const __half2 h = __floats2half2_rn(lip_act_tc(v0f, a.act, s0), lip_act_tc(v1f, a.act, s1));
           pk[j] = *reinterpret_cast<const uint32_t*>(&h);
         }
-        uint4* op = reinterpret_cast<uint4*>(a.out + m * a.Cout + cg);
+        uint4* op = reinterpret_cast<uint4*>(a.out + (long long)m * a.Cout + cg);
 #pragma unroll
         for (int q = 0; q < 4; ++q) op[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
@@ -204,14 +238,16 @@ __global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ 
     }
     __syncwarp();
   }
+  if (tr) trow[5] = clock64();     // epilogue of warp 0 done
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc<1>(tmem, NT);
+  if (tr) trow[6] = clock64();
 }
 
 template <int NT>
 static int lip_conv_tc_launch(const char* packed, const LipConv& c, const LipTcArgs& a, cudaStream_t st) {
-  constexpr int SMEM = LT_STAGES * (LT_A_BYTES + NT * 128) + 16 * LT_STAGES + 16 + 1024;
+  constexpr int SMEM = LT_STAGES * (LT_A_BYTES + NT * 128) + 16 * LT_STAGES + 16 + 3 * NT * 4 + 1024;
   static PerDeviceOnce configured;
   if (configured.first())
     VATSS_CUDA_OK(cudaFuncSetAttribute(k_lip_conv_tc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -222,6 +258,7 @@ static int lip_conv_tc_launch(const char* packed, const LipConv& c, const LipTcA
   const uint32_t box[2] = {64, (uint32_t)NT};
   if (int rc = make_tmap_f16(&tmapW, packed + c.off_w16, 2, dims, strides, box)) return rc;
   const long long M = (long long)a.F * a.Ho * a.Wo;
+  VATSS_CHECK_ARG(M < (1ll << 31) - 256, "lipreader tensor engine: %lld output pixels in one launch", M);
   dim3 grid(ceil_div(M, 128), c.cout / NT);
   k_lip_conv_tc<NT><<<grid, 288, SMEM, st>>>(tmapW, a);
   VATSS_LAUNCH_OK();
@@ -237,7 +274,7 @@ int lip_conv_tc(const char* packed, const LipConv& c, const __half* in16, int F,
   a.ks = c.ks; a.stride = c.stride; a.pad = c.pad;
   a.scale = (const float*)(packed + c.off_scale); a.shift = (const float*)(packed + c.off_shift);
   a.slope = (const float*)(packed + c.off_slope);
-  a.res = res16; a.act = act; a.out = out16;
+  a.res = res16; a.act = act; a.out = out16; a.dbg = g_lip_dbg; a.trace = g_lip_trace;
   if (c.cout % 128 == 0) return lip_conv_tc_launch<128>(packed, c, a, st);
   return lip_conv_tc_launch<64>(packed, c, a, st);
 }

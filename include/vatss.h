@@ -253,6 +253,10 @@ int vatss_profile_end(float* ms_per_stage, int* launches_per_stage, int n_stages
 /* experiments only (tools/lipreader_ablate.py): switch parts of the tcgen05 convolution kernel off to time the rest:
  * bit 0 no gather loads, bit 1 no epilogue math / stores, bit 2 no weight TMA.  0 = production. */
 void vatss_debug_lipreader(int flags);
+/* select the tcgen05 convolution kernel: 1 = one tile per CTA, two CTAs per SM (default; the ablation switches and the
+ * trace exist in this kernel only), 2 = persistent kernel with a separate epilogue warpgroup (bit-identical results,
+ * measured slower: DESIGN.md 3.7) */
+void vatss_debug_lipreader_kernel(int version);
 /* debug: device buffer (>= 8192 int64) receiving globaltimer / clock64 stamps of the first 1024 CTAs of every
  * following tcgen05 convolution launch (the last launch wins); NULL disables */
 void vatss_debug_lipreader_trace(void* dev_buffer);

@@ -87,6 +87,7 @@ EXPORTS = {
     "vatss_sisnr_chunks": (ctypes.c_int, [ctypes.c_int]),
     "vatss_pit_sisnr": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5),
     "vatss_debug_lipreader": (None, [ctypes.c_int]),
+    "vatss_debug_lipreader_kernel": (None, [ctypes.c_int]),
     "vatss_debug_lipreader_trace": (None, [ctypes.c_void_p]),
     "vatss_lipreader_packed_bytes": (ctypes.c_size_t, []),
     "vatss_lipreader_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 4),

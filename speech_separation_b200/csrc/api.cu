@@ -478,6 +478,7 @@ int vatss_pit_sisnr(const float* s1p, const float* s2p, const float* s1, const f
 }
 
 void vatss_debug_lipreader(int flags) { vatss::g_lip_dbg = flags; }
+void vatss_debug_lipreader_kernel(int version) { vatss::g_lip_tc_version = version == 2 ? 2 : 1; }
 void vatss_debug_lipreader_trace(void* dev_buffer) { vatss::g_lip_trace = (long long*)dev_buffer; }
 size_t vatss_lipreader_packed_bytes(void) { return lip_packed_bytes(); }
 size_t vatss_lipreader_workspace_bytes(int B, int T, int Hc, int Wc) { return lip_workspace_bytes(B, T, Hc, Wc); }

@@ -27,6 +27,7 @@ int lip_forward(const void* packed, size_t packed_bytes, int relu_type, const fl
                 size_t workspace_bytes, int engine, cudaStream_t st);
 
 extern long long* g_lip_trace;
+extern int g_lip_tc_version;
 extern int g_lip_dbg;   // experiment switches of k_lip_conv_tc (0 in production)
 
 // tcgen05 engine: out16 (F, Ho, Wo, Cout) = act(conv(in16 (F, H, W, Cin)) * scale + shift + res16), fp16 activations,

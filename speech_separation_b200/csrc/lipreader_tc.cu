@@ -16,6 +16,7 @@
 // One tile per CTA, two CTAs per SM (3 stages x 32 KB): one CTA's epilogue runs under the other's main loop.
 #include "lipreader.cuh"
 #include "ptx.cuh"
+#include "tc_kernels.cuh"
 
 namespace vatss {
 
@@ -43,7 +44,9 @@ struct LipTcArgs {
 __device__ __forceinline__ float lip_act_tc(float v, int act, float slope) {
   if (act == LIP_ACT_RELU) return fmaxf(v, 0.f);
   if (act == LIP_ACT_PRELU) return v >= 0.f ? v : v * slope;
-  if (act == LIP_ACT_SWISH) return v * (1.0f / (1.0f + __expf(-v)));
+  // x sigmoid(x) with the approximate exponential and division (MUFU.EX2 + MUFU.RCP, no IEEE slow path): the result is
+  // rounded to fp16 anyway; the IEEE division cost 1.0 of 9.7 ms per 3200 frames (tools/lipreader_ablate.py)
+  if (act == LIP_ACT_SWISH) return __fdividef(v, 1.0f + __expf(-v));
   return v;
 }
 
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ 
         const float* sSh = sPar + NT + c0;
         const float* sSl = sPar + 2 * NT + c0;
         uint32_t rr[16];
-        if (a.res) {
+        if (a.res && !(a.dbg & 32)) {
           const uint4* rp = reinterpret_cast<const uint4*>(a.res + (long long)m * a.Cout + cg);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -204,17 +207,19 @@ __global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ 
         for (int j = 0; j < 16; ++j) {
           float v0f = fmaf(__uint_as_float(acc[2 * j]), sSc[2 * j], sSh[2 * j]);
           float v1f = fmaf(__uint_as_float(acc[2 * j + 1]), sSc[2 * j + 1], sSh[2 * j + 1]);
-          if (a.res) {
+          if (a.res && !(a.dbg & 32)) {
             const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rr[j]));
             v0f += rf.x; v1f += rf.y;
           }
           const float s0 = sSl[2 * j], s1 = sSl[2 * j + 1];
-          const __half2 h = __floats2half2_rn(lip_act_tc(v0f, a.act, s0), lip_act_tc(v1f, a.act, s1));
+          const int actx = (a.dbg & 16) ? LIP_ACT_NONE : a.act;
+          const __half2 h = __floats2half2_rn(lip_act_tc(v0f, actx, s0), lip_act_tc(v1f, actx, s1));
           pk[j] = *reinterpret_cast<const uint32_t*>(&h);
         }
         uint4* op = reinterpret_cast<uint4*>(a.out + (long long)m * a.Cout + cg);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) op[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        for (int q = 0; q < 4; ++q)
+          if (!(a.dbg & 8) || pk[4 * q] == 0x12345678u) op[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
     }
   } else {
@@ -243,6 +248,245 @@ __global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ 
   __syncthreads();
   if (warp == 8) tmem_dealloc<1>(tmem, NT);
   if (tr) trow[6] = clock64();
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent version: one CTA per SM walks tiles (m tile, n tile); every role runs ahead across tile boundaries.
+//   warps 0..7   A producers in four groups of two warps; group g owns ring stage g and the K slabs j = g (mod 4) of the
+//                CTA's slab sequence (thread = 16-byte chunk ch of rows r, r + 8, ...): the stage turn-round of one
+//                group (loads -> st.shared -> fence.proxy.async -> arrival -> MMA -> commit) overlaps the other three
+//   warp 8       MMA issuer, accumulators double-buffered in TMEM (2 x NT columns)
+//   warp 9       weight slabs by TMA into their own 8-stage ring (a slab ahead of the A ring by up to 8)
+//   warps 10..13 epilogue (TMEM lane quadrant = warp & 3): runs under the next tile's main loop
+// The one-tile-per-CTA kernel above paid prologue, pipeline fill, epilogue and teardown per tile (clock64 trace of a
+// 9-slab tile: 13.4k cycles of slabs, 9k of epilogue, 3k of prologue / teardown; profiles/r02_lipreader_*).
+// ------------------------------------------------------------------------------------------
+constexpr int LP_SA = 4, LP_SB = 8;
+
+template <int NT>
+__global__ void __launch_bounds__(448, 1) k_lip_conv_tc2(const __grid_constant__ CUtensorMap tmapW, const LipTcArgs a) {
+  constexpr int B_BYTES = NT * 128;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA0 = base, sB0 = base + LP_SA * LT_A_BYTES;
+  constexpr int OFF_BAR = LP_SA * LT_A_BYTES + LP_SB * B_BYTES;
+  const uint32_t bars = base + OFF_BAR;
+  const uint32_t bar_fullA = bars, bar_emptyA = bars + 32, bar_fullB = bars + 64, bar_emptyB = bars + 128,
+                 bar_accfull = bars + 192, bar_accempty = bars + 208, tmem_slot_addr = bars + 224;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + OFF_BAR + 224);
+  float* sPar = reinterpret_cast<float*>(gen + OFF_BAR + 256);   // scale, shift, slope [Cout]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LP_SA; ++s) { mbar_init(bar_fullA + 8 * s, 2); mbar_init(bar_emptyA + 8 * s, 1); }
+    for (int s = 0; s < LP_SB; ++s) { mbar_init(bar_fullB + 8 * s, 1); mbar_init(bar_emptyB + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accempty + 8 * s, 4); }
+    fence_mbar_init();
+    prefetch_tmap(&tmapW);
+  }
+  if (warp == 8) {
+    tmem_alloc<1>(tmem_slot_addr, 2 * NT);
+    tmem_relinquish<1>();
+  }
+  for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) {
+    sPar[i] = a.scale[i];
+    sPar[a.Cout + i] = a.shift[i];
+    sPar[2 * a.Cout + i] = a.slope[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int M = a.F * a.Ho * a.Wo;
+  const int mtiles = (M + 127) / 128, ntiles = a.Cout / NT, total = mtiles * ntiles;
+  const int cblocks = a.Cin / 64;
+  const int nslabs = a.ks * a.ks * cblocks;
+  const int my_tiles = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // grid <= total
+  const long long nj = (long long)my_tiles * nslabs;   // K slabs this CTA streams, numbered across its tiles
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ A producers
+    const int gi = warp >> 1, t64 = threadIdx.x & 63, ch = t64 & 7, g8 = t64 >> 3;
+    const uint4* in4 = reinterpret_cast<const uint4*>(a.in);
+    const int cin8 = a.Cin / 8;
+    int gyx[16], gb[16];   // (stride oy - pad) << 16 | (stride ox - pad) & 0xffff; frame offset in 16-byte units + ch
+    int cur_tk = -1;
+    uint4 v[16];
+    auto issue = [&](long long j) {
+      const int tk = (int)(j / nslabs), i = (int)(j - (long long)tk * nslabs);
+      if (tk != cur_tk) {
+        cur_tk = tk;
+        const int mt = ((int)blockIdx.x + tk * (int)gridDim.x) / ntiles;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int mk = mt * 128 + g8 + 8 * k;
+          if (mk < M) {
+            const int fr = mk / (a.Wo * a.Ho), rem = mk - fr * (a.Wo * a.Ho);
+            const int oy = rem / a.Wo, ox = rem - oy * a.Wo;
+            gyx[k] = ((oy * a.stride - a.pad) << 16) | ((ox * a.stride - a.pad) & 0xffff);
+            gb[k] = fr * a.H * a.W * cin8 + ch;
+          } else {
+            gyx[k] = (int)0x80000000;   // gy = -32768: never inside the image
+            gb[k] = 0;
+          }
+        }
+      }
+      const int tap = i / cblocks, cb = i - tap * cblocks;
+      const int ky = tap / a.ks, kx = tap - ky * a.ks;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int iy = (gyx[k] >> 16) + ky, ix = (int)(short)(gyx[k] & 0xffff) + kx;
+        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+          v[k] = __ldg(in4 + gb[k] + (iy * a.W + ix) * cin8 + cb * 8);
+        else
+          v[k] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    long long j = gi;
+    if (j < nj) issue(j);
+    const uint32_t sA = sA0 + gi * LT_A_BYTES;
+    for (; j < nj; j += LP_SA) {
+      const int ph = (int)((j >> 2) & 1);
+      if (lane == 0) mbar_wait(bar_emptyA + 8 * gi, ph ^ 1);
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const uint32_t dst = sA + sw128_offset((uint32_t)(g8 + 8 * k), (uint32_t)ch);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[k].x), "r"(v[k].y), "r"(v[k].z), "r"(v[k].w)
+                     : "memory");
+      }
+      fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy operand reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_fullA + 8 * gi);
+      if (j + LP_SA < nj) issue(j + LP_SA);   // in flight during the stage's turn-round
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = idesc_f16(128, NT, 0);
+      long long j = 0;
+      for (int tk = 0; tk < my_tiles; ++tk) {
+        const int slot = tk & 1;
+        mbar_wait(bar_accempty + 8 * slot, ((tk >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int i = 0; i < nslabs; ++i, ++j) {
+          const int sa = (int)(j & 3), sb = (int)(j & 7);
+          mbar_wait(bar_fullA + 8 * sa, (int)((j >> 2) & 1));
+          mbar_wait(bar_fullB + 8 * sb, (int)((j >> 3) & 1));
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t a_desc = smem_desc_sw128_kmajor(sA0 + sa * LT_A_BYTES) + (uint64_t)(kk * 2);
+            const uint64_t b_desc = smem_desc_sw128_kmajor(sB0 + sb * B_BYTES) + (uint64_t)(kk * 2);
+            umma_f16<1>(tmem + slot * NT, a_desc, b_desc, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_emptyA + 8 * sa);
+          umma_commit(bar_emptyB + 8 * sb);
+        }
+        umma_commit(bar_accfull + 8 * slot);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ weight slabs (TMA)
+    if (lane == 0) {
+      long long j = 0;
+      for (int tk = 0; tk < my_tiles; ++tk) {
+        const int nt = ((int)blockIdx.x + tk * (int)gridDim.x) % ntiles;
+        for (int i = 0; i < nslabs; ++i, ++j) {
+          const int sb = (int)(j & 7);
+          mbar_wait(bar_emptyB + 8 * sb, (int)((j >> 3) & 1) ^ 1);
+          mbar_expect_tx(bar_fullB + 8 * sb, B_BYTES);
+          tma_load_2d(sB0 + sb * B_BYTES, &tmapW, bar_fullB + 8 * sb, i * 64, nt * NT);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (thread = pixel row)
+    const int q = warp & 3;
+    for (int tk = 0; tk < my_tiles; ++tk) {
+      const int tile = (int)blockIdx.x + tk * (int)gridDim.x;
+      const int mt = tile / ntiles, n0 = (tile - mt * ntiles) * NT, slot = tk & 1;
+      const int m = mt * 128 + q * 32 + lane;
+      const bool row_ok = m < M;
+      if (lane == 0) mbar_wait(bar_accfull + 8 * slot, (tk >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + slot * NT + c0, acc);
+        tmem_ld_wait();
+        if (c0 + 32 >= NT) {   // the accumulator slot is free for the tile after the next
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_accempty + 8 * slot);
+        }
+        if (row_ok) {
+          const int cg = n0 + c0;
+          const float* sSc = sPar + cg;
+          const float* sSh = sPar + a.Cout + cg;
+          const float* sSl = sPar + 2 * a.Cout + cg;
+          uint32_t rr[16];
+          if (a.res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(a.res + (long long)m * a.Cout + cg);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint4 x = __ldg(rp + u);
+              rr[4 * u] = x.x; rr[4 * u + 1] = x.y; rr[4 * u + 2] = x.z; rr[4 * u + 3] = x.w;
+            }
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            float v0f = fmaf(__uint_as_float(acc[2 * u]), sSc[2 * u], sSh[2 * u]);
+            float v1f = fmaf(__uint_as_float(acc[2 * u + 1]), sSc[2 * u + 1], sSh[2 * u + 1]);
+            if (a.res) {
+              const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rr[u]));
+              v0f += rf.x; v1f += rf.y;
+            }
+            const __half2 h = __floats2half2_rn(lip_act_tc(v0f, a.act, sSl[2 * u]), lip_act_tc(v1f, a.act, sSl[2 * u + 1]));
+            pk[u] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          uint4* op = reinterpret_cast<uint4*>(a.out + (long long)m * a.Cout + cg);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) op[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<1>(tmem, 2 * NT);
+}
+
+int g_lip_tc_version = 1;   // 1 = one tile per CTA, two CTAs per SM (default: faster), 2 = persistent kernel
+
+template <int NT>
+static int lip_conv_tc2_launch(const char* packed, const LipConv& c, const LipTcArgs& a, cudaStream_t st) {
+  constexpr int SMEM = LP_SA * LT_A_BYTES + LP_SB * NT * 128 + 256 + 3 * 512 * 4 + 1024;
+  static_assert(SMEM <= 227 * 1024, "shared memory");
+  static PerDeviceOnce configured;
+  if (configured.first())
+    VATSS_CUDA_OK(cudaFuncSetAttribute(k_lip_conv_tc2<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  VATSS_CHECK_ARG(c.cout <= 512 && a.H < 16384 && a.W < 16384, "lipreader tensor engine: shape");
+  CUtensorMap tmapW;
+  const uint64_t K = (uint64_t)c.taps * c.cin;
+  const uint64_t dims[2] = {K, (uint64_t)c.cout};
+  const uint64_t strides[1] = {K * sizeof(__half)};
+  const uint32_t box[2] = {64, (uint32_t)NT};
+  if (int rc = make_tmap_f16(&tmapW, packed + c.off_w16, 2, dims, strides, box)) return rc;
+  const long long M = (long long)a.F * a.Ho * a.Wo;
+  VATSS_CHECK_ARG(M < (1ll << 31) - 256 && (long long)a.F * a.H * a.W * (a.Cin / 8) < (1ll << 31),
+                  "lipreader tensor engine: %lld output pixels in one launch", M);
+  const long long total = (long long)ceil_div(M, 128) * (c.cout / NT);
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  k_lip_conv_tc2<NT><<<grid, 448, SMEM, st>>>(tmapW, a);
+  VATSS_LAUNCH_OK();
+  return 0;
 }
 
 template <int NT>
@@ -275,6 +519,10 @@ int lip_conv_tc(const char* packed, const LipConv& c, const __half* in16, int F,
   a.scale = (const float*)(packed + c.off_scale); a.shift = (const float*)(packed + c.off_shift);
   a.slope = (const float*)(packed + c.off_slope);
   a.res = res16; a.act = act; a.out = out16; a.dbg = g_lip_dbg; a.trace = g_lip_trace;
+  if (g_lip_tc_version == 2 && !g_lip_dbg && !g_lip_trace) {
+    if (c.cout % 128 == 0) return lip_conv_tc2_launch<128>(packed, c, a, st);
+    return lip_conv_tc2_launch<64>(packed, c, a, st);
+  }
   if (c.cout % 128 == 0) return lip_conv_tc_launch<128>(packed, c, a, st);
   return lip_conv_tc_launch<64>(packed, c, a, st);
 }

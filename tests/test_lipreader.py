@@ -153,6 +153,25 @@ def test_cuda_utterance_boundaries_and_frame_chunks():
 
 
 @pytest.mark.gpu
+def test_persistent_convolution_kernel_equals_one_tile_per_cta_kernel():
+    """The persistent tcgen05 convolution (experiment, vatss_debug_lipreader_kernel(2)) against the default one-tile-per-CTA
+    kernel: same K-slab order, same MMA shapes, same epilogue arithmetic - bit-identical features (270 frames: tiles in
+    every role's second lap)."""
+    from speech_separation_b200 import _lib
+
+    net = _net("swish", 5, "tensor")
+    x = torch.from_numpy(LO.preprocess(LO.make_frames(3, 90, seed=9)).astype(np.float32))[:, None].to("cuda:0")
+    lib = _lib.load()
+    try:
+        lib.vatss_debug_lipreader_kernel(2)
+        y2 = net(x, lengths=[90] * 3).cpu().numpy()
+    finally:
+        lib.vatss_debug_lipreader_kernel(1)
+    y1 = net(x, lengths=[90] * 3).cpu().numpy()
+    assert np.isfinite(y2).all() and np.array_equal(y1, y2)
+
+
+@pytest.mark.gpu
 def test_lipreader_feeds_the_separator(golden_dir):
     """profiler.py:17-22: video -> lipreader -> permute -> DPTN-AV; shapes and finiteness end to end on the device."""
     from speech_separation_b200 import DPTNAVWavEncDec, extract_embeddings

@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(448, 1) k_lip_conv_tc2(const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_accempty + 8 * slot);
         }
-        if (row_ok) {
+        if (row_ok && !(a.dbg & 2)) {
           const int cg = n0 + c0;
           const float* sSc = sPar + cg;
           const float* sSh = sPar + a.Cout + cg;
@@ -519,7 +519,7 @@ int lip_conv_tc(const char* packed, const LipConv& c, const __half* in16, int F,
   a.scale = (const float*)(packed + c.off_scale); a.shift = (const float*)(packed + c.off_shift);
   a.slope = (const float*)(packed + c.off_slope);
   a.res = res16; a.act = act; a.out = out16; a.dbg = g_lip_dbg; a.trace = g_lip_trace;
-  if (g_lip_tc_version == 2 && !g_lip_dbg && !g_lip_trace) {
+  if (g_lip_tc_version == 2 && !g_lip_trace) {
     if (c.cout % 128 == 0) return lip_conv_tc2_launch<128>(packed, c, a, st);
     return lip_conv_tc2_launch<64>(packed, c, a, st);
   }

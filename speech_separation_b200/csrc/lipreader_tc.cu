@@ -164,9 +164,12 @@ __global__ void __launch_bounds__(288, 2) k_lip_conv_tc(const __grid_constant__ 
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[k].x), "r"(v[k].y), "r"(v[k].z), "r"(v[k].w)
                      : "memory");
       }
-      fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy operand reads
+      if (!(a.dbg & 128)) fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy operand reads
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * s);   // one arrival per warp (256 arrivals on one mbarrier serialise)
+      if (lane == 0) {   // one arrival per warp (256 arrivals on one mbarrier serialise)
+        if (a.dbg & 64) asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar_full + 8 * s) : "memory");
+        else mbar_arrive(bar_full + 8 * s);
+      }
     };
     uint4 v0[4], v1[4], v2[4];
     issue(0, v0);

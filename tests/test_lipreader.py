@@ -186,3 +186,27 @@ def test_lipreader_feeds_the_separator(golden_dir):
     out = sep(mix=mix, s1_embedding=emb[0:1].contiguous(), s2_embedding=emb[1:2].contiguous())
     assert tuple(out["s1_pred"].shape) == (1, 16000)
     assert bool(torch.isfinite(out["s1_pred"]).all()) and bool(torch.isfinite(out["s2_pred"]).all())
+
+
+def test_init_lipreader_reads_the_reference_config_and_checkpoint_format(tmp_path):
+    """init_utils.py:168-207 + lipreading/utils.py:159-189: JSON config -> model; `checkpoint["model_state_dict"]` is loaded
+    by key, the classification head's tensors are ignored."""
+    import json
+
+    from speech_separation_b200 import init_lipreader
+
+    cfg = tmp_path / "lrw_resnet18_mstcn.json"   # the fields of src/lipreader/configs/lrw_resnet18_mstcn.json
+    cfg.write_text(json.dumps({"backbone_type": "resnet", "relu_type": "swish", "tcn_dropout": 0.2, "tcn_dwpw": False,
+                               "tcn_kernel_size": [3, 5, 7], "tcn_num_layers": 4, "tcn_width_mult": 1, "width_mult": 1.0}))
+    sd = LO.make_state_dict("swish", 3)
+    full = dict(sd)
+    full["tcn.mb_ms_tcn.tcn0.cbcr0_0.conv.weight"] = torch.zeros(256, 512, 3)
+    ckpt = tmp_path / "lipreader.pth"
+    torch.save({"model_state_dict": full, "epoch_idx": 80}, ckpt)
+    m = init_lipreader(str(cfg), str(ckpt))
+    assert m.relu_type == "swish" and not m.training
+    for k, v in sd.items():
+        assert torch.equal(m.state_dict()[k], v), k
+    assert "All parameters: 11182784" in str(m)      # model.py:196-207-style summary line
+    m2 = init_lipreader(str(cfg))                     # no checkpoint: the reference's random initialisation
+    assert float(m2.trunk.layer1[0].bn1.weight.min()) == 1.0

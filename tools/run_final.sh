@@ -10,3 +10,6 @@ python bench.py --model dptn_wav --batch 4 --steps 5 --warmup 3 --no-eager-basel
 python bench.py --seconds 10 --batch 16 --steps 5 --warmup 3 --no-cpu-baseline --no-eager-baseline > gpurun_out/r02_bench_10s.log 2>&1; tail -1 gpurun_out/r02_bench_10s.log | cut -c1-200
 python bench.py --engine tensor-f16res --steps 5 --warmup 3 --no-cpu-baseline --no-eager-baseline > gpurun_out/r02_bench_f16res.log 2>&1; tail -1 gpurun_out/r02_bench_f16res.log | cut -c1-200
 python tools/attn_bench.py --shapes all --versions 1,3 > gpurun_out/r02_attn_bench_final.log 2>&1; cat gpurun_out/r02_attn_bench_final.log
+# lipreader front end: parity of both engines + device time, ablation of the tcgen05 convolution kernel
+python tools/lipreader_bench.py 32 100 5 > gpurun_out/r02_lipreader_bench.log 2>&1; tail -1 gpurun_out/r02_lipreader_bench.log
+python tools/lipreader_ablate.py 32 100 > gpurun_out/r02_lipreader_ablation.log 2>&1; head -4 gpurun_out/r02_lipreader_ablation.log

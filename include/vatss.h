@@ -251,7 +251,9 @@ int vatss_profile_end(float* ms_per_stage, int* launches_per_stage, int n_stages
 #define VATSS_LIP_ENGINE_F32 0
 #define VATSS_LIP_ENGINE_TENSOR 1
 /* experiments only (tools/lipreader_ablate.py): switch parts of the tcgen05 convolution kernel off to time the rest:
- * bit 0 no gather loads, bit 1 no epilogue math / stores, bit 2 no weight TMA.  0 = production. */
+ * bit 0 no gather loads, bit 1 no epilogue math / stores, bit 2 no weight TMA, bits 3-5 no stores / activation / shortcut
+ * loads, bits 6-7 relaxed arrival / no proxy fence, bit 8 two instead of three CTAs per SM for 64-channel layers
+ * (valid results).  0 = production. */
 void vatss_debug_lipreader(int flags);
 /* select the tcgen05 convolution kernel: 1 = one tile per CTA, two CTAs per SM (default; the ablation switches and the
  * trace exist in this kernel only), 2 = persistent kernel with a separate epilogue warpgroup (bit-identical results,

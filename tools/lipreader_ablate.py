@@ -16,7 +16,7 @@ net = Lipreading(relu_type="swish", extract_feats=True).to("cuda:0").set_engine(
 vid = (torch.rand(B, T, 96, 96, device="cuda:0") * 255).round()
 lib = _lib.load()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
-for flags, what in ((-2, "persistent kernel (vatss_debug_lipreader_kernel(2))"), (-4, "persistent kernel, no epilogue"), (0, "production (one tile per CTA)"), (64, "relaxed mbarrier arrival (timing experiment)"), (128, "no fence.proxy.async (timing only, results invalid)"), (192, "relaxed arrival, no fence"), (8, "no epilogue stores"), (16, "no activation math"), (32, "no residual loads"), (56, "epilogue = TMEM read + BN only"), (1, "no gather loads"), (2, "no epilogue"), (4, "no weight TMA"), (5, "no gather, no weight TMA"),
+for flags, what in ((-2, "persistent kernel (vatss_debug_lipreader_kernel(2))"), (-4, "persistent kernel, no epilogue"), (0, "production (one tile per CTA)"), (256, "64-channel layers with two CTAs per SM / three slabs in flight instead of three CTAs / two slabs"), (64, "relaxed mbarrier arrival (timing experiment)"), (128, "no fence.proxy.async (timing only, results invalid)"), (192, "relaxed arrival, no fence"), (8, "no epilogue stores"), (16, "no activation math"), (32, "no residual loads"), (56, "epilogue = TMEM read + BN only"), (1, "no gather loads"), (2, "no epilogue"), (4, "no weight TMA"), (5, "no gather, no weight TMA"),
                     (7, "no gather / epilogue / TMA: launch + barriers + MMA only")):
     lib.vatss_debug_lipreader_kernel(2 if flags < 0 else 1)
     lib.vatss_debug_lipreader(2 if flags == -4 else max(flags, 0))
@@ -34,3 +34,8 @@ for flags, what in ((-2, "persistent kernel (vatss_debug_lipreader_kernel(2))"),
     print(f"flags {flags} ({what}): {np.median(ms):.3f} ms per {B * T} frames", flush=True)
 lib.vatss_debug_lipreader(0)
 lib.vatss_debug_lipreader_kernel(1)
+ref = extract_embeddings(net, vid)
+lib.vatss_debug_lipreader(256)
+alt = extract_embeddings(net, vid)
+lib.vatss_debug_lipreader(0)
+print("two-CTA variant of the 64-channel kernel bit-identical to production:", bool(torch.equal(ref, alt)), flush=True)

@@ -153,6 +153,35 @@ def test_cuda_utterance_boundaries_and_frame_chunks():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("B,T,H,W", [(1, 1, 88, 88), (2, 2, 70, 58), (1, 3, 33, 87), (3, 4, 16, 8)])
+def test_cuda_odd_geometries_and_short_clips(B, T, H, W):
+    """Shapes the production pipeline never produces but the reference class accepts: a single frame (all temporal taps
+    but one fall into the zero padding), odd widths after every stride-2 stage (58 -> 29 -> 15 -> 8 -> 4 -> 2), ragged last
+    row tiles, images smaller than a convolution tile - against the CPU oracle, both engines."""
+    relu_type = "prelu"
+    sd = LO.make_state_dict(relu_type, 21)
+    rng = np.random.Generator(np.random.PCG64(B * 1000 + T * 100 + H + W))
+    x = torch.from_numpy(rng.normal(0.0, 1.0, (B, 1, T, H, W)).astype(np.float32))
+    with torch.no_grad():
+        ref = LO.forward(sd, x, relu_type).numpy()
+    net = _net(relu_type, 21, "f32")
+    y = net(x.to("cuda:0"), lengths=[T] * B).cpu().numpy()
+    assert y.shape == ref.shape == (B, T, 512)
+    assert rel_l2(y, ref) < F32_TOL
+    yt = net.set_engine("tensor")(x.to("cuda:0"), lengths=[T] * B).cpu().numpy()
+    assert rel_l2(yt, ref) < TENSOR_TOL
+
+
+@pytest.mark.gpu
+def test_cuda_rejects_unsupported_geometry():
+    net = _net("swish", 2024, "tensor")
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 1, 2, 88, 120, device="cuda:0"), lengths=[2])     # wider than the front-end tile supports
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 2, 88, 88, device="cuda:0"), lengths=[2])         # not (B, 1, T, H, W)
+
+
+@pytest.mark.gpu
 def test_persistent_convolution_kernel_equals_one_tile_per_cta_kernel():
     """The persistent tcgen05 convolution (experiment, vatss_debug_lipreader_kernel(2)) against the default one-tile-per-CTA
     kernel: same K-slab order, same MMA shapes, same epilogue arithmetic - bit-identical features (270 frames: tiles in

@@ -170,6 +170,15 @@ int vatss_pit_sisnr(const float* s1p, const float* s2p, const float* s1, const f
                     const float* mix, int B, int T, double* rows_out, double* rows_loss_out,
                     double* summary_out, double* scratch, void* stream);
 
+/* Gradient of summary_out[0] (the batch-level PIT loss) with respect to the two predictions: the first piece of the
+ * reference's training step (`batch["loss"].backward()`, src/trainer/trainer.py:46, through BaseSSLoss.forward
+ * src/loss/ss_losses.py:10-26 and SiSNRLoss.forward :100-114).  `scratch` and `summary` are those a preceding
+ * vatss_pit_sisnr call on the same tensors wrote; grad_out: device pointer to the upstream scalar gradient (NULL = 1).
+ * grad_s1p / grad_s2p (B,T) f32.  Targets get no gradient (they are data). */
+int vatss_pit_sisnr_backward(const float* s1p, const float* s2p, const float* s1, const float* s2, int B, int T,
+                             const double* scratch, const double* summary, const float* grad_out, float* grad_s1p,
+                             float* grad_s2p, void* stream);
+
 /* Stand-alone entry points of the TENSOR-engine kernels (unit tests, ncu attribution).
  * vatss_tc_gemm: out = A[M,K] (fp16, row pitch lda) x W[NOUT,K]^T (fp16) + bias with epilogue
  *   epi 0: out16 fp16 | 1: out32 (+res) | 2: out32 = LN(.+res), out16 = act16(out32) | 3: out32 = LN(.)+res

@@ -381,6 +381,29 @@ def pit_sisnr_loss(s1p, s2p, s1, s2):
     return p2 if p2 < p1 else p1
 
 
+def pit_sisnr_loss_grad(s1p, s2p, s1, s2):
+    """Gradient of `pit_sisnr_loss` with respect to (s1p, s2p): what `batch["loss"].backward()` (src/trainer/trainer.py:46)
+    deposits on the predictions through BaseSSLoss.forward / SiSNRLoss.forward (ss_losses.py:10-26,100-114).
+
+    With zero-mean p_c, g_c, a = <g_c,p_c>/||g_c||^2, e = p_c - a g_c:
+        d/dp [-20 log10(||a g_c||^2 / ||e||^2)] = -(40/ln 10) (g_c/<g_c,p_c> - e/||e||^2)
+    (g_c and e sum to zero, so the centring Jacobian is the identity); batch mean and the two terms of a permutation give
+    the factor 1/(2B); the permutation is the one the forward chose for the whole batch."""
+    l = lambda a, b: sisnr_loss_rows(a, b).mean()
+    swap = (l(s1p, s2) + l(s2p, s1)) / 2 < (l(s1p, s1) + l(s2p, s2)) / 2
+    t1, t2 = (s2, s1) if swap else (s1, s2)
+    B = s1p.shape[0]
+
+    def one(pred, gt):
+        p = pred - pred.mean(axis=-1, keepdims=True)
+        g = gt - gt.mean(axis=-1, keepdims=True)
+        dot = (g * p).sum(-1, keepdims=True)
+        e = p - dot / (g * g).sum(-1, keepdims=True) * g
+        return -(40.0 / np.log(10.0)) / (2.0 * B) * (g / dot - e / (e * e).sum(-1, keepdims=True))
+
+    return one(s1p, t1), one(s2p, t2)
+
+
 def si_snr_metric_rows(pred, target, eps=None):
     """torchmetrics scale_invariant_signal_noise_ratio per row (restated; see header).
 

@@ -86,6 +86,7 @@ EXPORTS = {
     "vatss_profile_end": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "vatss_sisnr_chunks": (ctypes.c_int, [ctypes.c_int]),
     "vatss_pit_sisnr": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5),
+    "vatss_pit_sisnr_backward": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6),
     "vatss_debug_lipreader": (None, [ctypes.c_int]),
     "vatss_debug_lipreader_kernel": (None, [ctypes.c_int]),
     "vatss_debug_lipreader_trace": (None, [ctypes.c_void_p]),

@@ -477,6 +477,15 @@ int vatss_pit_sisnr(const float* s1p, const float* s2p, const float* s1, const f
                           (cudaStream_t)stream);
 }
 
+int vatss_pit_sisnr_backward(const float* s1p, const float* s2p, const float* s1, const float* s2, int B, int T,
+                             const double* scratch, const double* summary, const float* grad_out, float* grad_s1p,
+                             float* grad_s2p, void* stream) {
+  VATSS_CHECK_ARG(s1p && s2p && s1 && s2 && scratch && summary && grad_s1p && grad_s2p, "pit_sisnr_backward: NULL pointer");
+  StageScope sc(ST_SISNR, (cudaStream_t)stream);
+  return launch_pit_sisnr_backward(s1p, s2p, s1, s2, B, T, scratch, summary, grad_out, grad_s1p, grad_s2p,
+                                   (cudaStream_t)stream);
+}
+
 void vatss_debug_lipreader(int flags) { vatss::g_lip_dbg = flags; }
 void vatss_debug_lipreader_kernel(int version) { vatss::g_lip_tc_version = version == 2 ? 2 : 1; }
 void vatss_debug_lipreader_trace(void* dev_buffer) { vatss::g_lip_trace = (long long*)dev_buffer; }

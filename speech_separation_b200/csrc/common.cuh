@@ -152,5 +152,8 @@ int sisnr_chunks(int T);
 int launch_pit_sisnr(const float* s1p, const float* s2p, const float* s1, const float* s2, const float* mix,
                      int B, int T, double* rows, double* rows_loss, double* summary, double* scratch,
                      cudaStream_t st);
+int launch_pit_sisnr_backward(const float* s1p, const float* s2p, const float* s1, const float* s2, int B, int T,
+                              const double* scratch, const double* summary, const float* grad_out, float* g1, float* g2,
+                              cudaStream_t st);
 
 }  // namespace vatss

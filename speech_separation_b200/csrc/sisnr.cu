@@ -143,4 +143,58 @@ int launch_pit_sisnr(const float* s1p, const float* s2p, const float* s1, const 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Backward of the batch-level PIT loss with respect to the two predictions (first piece of the training step,
+// src/trainer/trainer.py:46 `batch["loss"].backward()` through BaseSSLoss.forward src/loss/ss_losses.py:10-26).
+//   L = (1 / 2B) sum_b [ l_b(p1, g_pi(1)) + l_b(p2, g_pi(2)) ],  l = -20 log10(||s||^2 / ||e||^2),  s = a g_c,  e = p_c - s
+//   d l / d p = -(40 / ln 10) ( g_c / <g_c, p_c>  -  e / ||e||^2 )        (g_c and e are zero-mean: the centring Jacobian is I)
+// pi is the permutation the forward chose for the WHOLE batch (summary[1], summary[2]); the per-row centred moments come
+// from the forward's scratch (raw chunk sums), so the backward reads the four waveforms once and writes two gradients.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_sisnr_loss_backward(const float* __restrict__ s1p, const float* __restrict__ s2p, const float* __restrict__ s1,
+                      const float* __restrict__ s2, int B, int T, int chunks, const double* __restrict__ scratch,
+                      const double* __restrict__ summary, const float* __restrict__ grad_out, float* __restrict__ g1,
+                      float* __restrict__ g2) {
+  const int b = blockIdx.y;
+  __shared__ double m[SISNR_NM];
+  if (threadIdx.x < SISNR_NM) {
+    double v = 0.0;
+    for (int c = 0; c < chunks; ++c) v += scratch[((size_t)b * chunks + c) * SISNR_NM + threadIdx.x];
+    m[threadIdx.x] = v;
+  }
+  __syncthreads();
+  const bool swap = summary[2] < summary[1];   // loss_perm_2 < loss_perm_1 (ss_losses.py:24)
+  const double invT = 1.0 / (double)T;
+  const double up = (grad_out ? (double)grad_out[0] : 1.0) * (-40.0 / 2.302585092994046) / (2.0 * (double)B);
+  // prediction 1 pairs with s1 (cross 10) or s2 (cross 12); prediction 2 with s2 (11) or s1 (13)
+  const PairMoments a = centred(m, 0, swap ? 3 : 2, swap ? 12 : 10, invT);
+  const PairMoments c = centred(m, 1, swap ? 2 : 3, swap ? 13 : 11, invT);
+  const double mp1 = m[0] * invT, mp2 = m[1] * invT, mg1 = m[swap ? 3 : 2] * invT, mg2 = m[swap ? 2 : 3] * invT;
+  const double al1 = a.dot / a.gg, al2 = c.dot / c.gg;
+  const double n1 = a.pp - a.dot * a.dot / a.gg, n2 = c.pp - c.dot * c.dot / c.gg;
+  const float* t1 = swap ? s2 : s1;
+  const float* t2 = swap ? s1 : s2;
+  const size_t base = (size_t)b * T;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    const double gc1 = (double)t1[base + t] - mg1, gc2 = (double)t2[base + t] - mg2;
+    const double e1 = (double)s1p[base + t] - mp1 - al1 * gc1, e2 = (double)s2p[base + t] - mp2 - al2 * gc2;
+    g1[base + t] = (float)(up * (gc1 / a.dot - e1 / n1));
+    g2[base + t] = (float)(up * (gc2 / c.dot - e2 / n2));
+  }
+}
+
+int launch_pit_sisnr_backward(const float* s1p, const float* s2p, const float* s1, const float* s2, int B, int T,
+                              const double* scratch, const double* summary, const float* grad_out, float* g1, float* g2,
+                              cudaStream_t st) {
+  VATSS_CHECK_ARG(B > 0 && T > 0, "pit_sisnr_backward: empty batch (B=%d, T=%d)", B, T);
+  const int chunks = sisnr_chunks(T);
+  int gx = (T + 256 * 8 - 1) / (256 * 8);
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, B);
+  k_sisnr_loss_backward<<<grid, 256, 0, st>>>(s1p, s2p, s1, s2, B, T, chunks, scratch, summary, grad_out, g1, g2);
+  VATSS_LAUNCH_OK();
+  return 0;
+}
+
 }  // namespace vatss

@@ -331,6 +331,38 @@ def test_loss_matches_reference_golden(V, golden_dir):
         np.testing.assert_allclose(float(one), float(z[f"c{i}.pair"][0]), rtol=2e-5)
 
 
+def test_loss_backward_matches_reference_autograd(V, golden_dir):
+    """`loss.backward()` of the drop-in SiSNRWavLoss (vatss_pit_sisnr_backward) against gradients produced by torch
+    autograd through the reference's own loss on CPU (tests/golden/loss_grad.npz), incl. the swapped-speaker case where
+    the batch-level PIT picks permutation 2, an upstream gradient != 1 and a sequence that spans several chunks."""
+    z = np.load(os.path.join(golden_dir, "loss.npz"))
+    g = np.load(os.path.join(golden_dir, "loss_grad.npz"))
+    for i in range(3):
+        t = {k: torch.from_numpy(z[f"c{i}.{k}"]).to(dev()) for k in ("s1", "s2", "s1p", "s2p")}
+        s1p, s2p = t["s1p"].clone().requires_grad_(True), t["s2p"].clone().requires_grad_(True)
+        loss = V.SiSNRWavLoss()(s1_pred=s1p, s2_pred=s2p, s1=t["s1"], s2=t["s2"])["loss"]
+        np.testing.assert_allclose(float(loss.detach()), float(z[f"c{i}.loss"]), rtol=2e-5)
+        (float(g[f"c{i}.upstream"]) * loss).backward()
+        assert rel_l2(s1p.grad.cpu().numpy(), g[f"c{i}.g1"]) < 1e-5
+        assert rel_l2(s2p.grad.cpu().numpy(), g[f"c{i}.g2"]) < 1e-5
+    # full-size property: the gradient is orthogonal to the prediction's own direction and to constants
+    # (SI-SNR is invariant to the scale and the offset of the estimate)
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    s1 = torch.randn(8, 64000, generator=gen).to(dev())
+    s2 = torch.randn(8, 64000, generator=gen).to(dev())
+    p1 = (s1 + 0.3 * torch.randn(8, 64000, generator=gen).to(dev())).requires_grad_(True)
+    p2 = (s2 + 0.5 * torch.randn(8, 64000, generator=gen).to(dev())).requires_grad_(True)
+    V.SiSNRWavLoss()(s1_pred=p1, s2_pred=p2, s1=s1, s2=s2)["loss"].backward()
+    for p in (p1, p2):
+        gr, x = p.grad.double(), p.detach().double()
+        xc = x - x.mean(-1, keepdim=True)
+        assert float((gr.sum(-1).abs() / gr.abs().sum(-1)).max()) < 1e-5
+        assert float(((gr * xc).sum(-1).abs() / (gr.norm(dim=-1) * xc.norm(dim=-1))).max()) < 1e-5
+    # no autograd requested: plain tensor, as before
+    out = V.SiSNRWavLoss()(s1_pred=p1.detach(), s2_pred=p2.detach(), s1=s1, s2=s2)["loss"]
+    assert not out.requires_grad
+
+
 @pytest.mark.parametrize("B,T", [(1, 17), (3, 8192), (32, 64000), (5, 160000)])
 def test_metrics_match_oracle(V, B, T):
     g = np.random.default_rng(B * 1000 + T)

@@ -137,3 +137,16 @@ def test_torch_port_reproduces_reference_goldens_exactly(golden_dir, kind):
         assert got.shape == z[k].shape
         # thread-count dependent reduction order inside ATen is the only freedom: far below the 1e-3 budget
         assert rel_l2(got, z[k]) < 2e-6, (kind, k, rel_l2(got, z[k]))
+
+
+def test_oracle_loss_gradient_matches_reference_autograd(golden_dir):
+    """oracle.pit_sisnr_loss_grad (closed form) against torch autograd through the reference's own SiSNRWavLoss
+    (oracle/gen_loss_grad_golden.py): the gradient `batch["loss"].backward()` leaves on the predictions."""
+    z = np.load(os.path.join(golden_dir, "loss.npz"))
+    g = np.load(os.path.join(golden_dir, "loss_grad.npz"))
+    for i in range(3):
+        a = [z[f"c{i}.{k}"].astype(np.float64) for k in ("s1p", "s2p", "s1", "s2")]
+        g1, g2 = O.pit_sisnr_loss_grad(*a)
+        up = float(g[f"c{i}.upstream"])
+        assert rel_l2(up * g1, g[f"c{i}.g1"]) < 2e-6
+        assert rel_l2(up * g2, g[f"c{i}.g2"]) < 2e-6

@@ -290,15 +290,21 @@ __global__ void __launch_bounds__(256) k_lip_im2col_front(const LipFrontArgs a, 
   }
   __syncthreads();
   const int rows = (a.H1 - oy0 < LF_ROWS) ? a.H1 - oy0 : LF_ROWS;
-  const int ntask = rows * a.W1 * (LIP_FRONT_K / 8);
-  for (int idx = threadIdx.x; idx < ntask; idx += 256) {
-    const int c = idx & 31, p = idx >> 5;
+  // thread = (16-byte chunk c of 8 taps, pixels p = warp, warp + 8, ...): the chunk - and with it the eight patch offsets -
+  // is the same for every pixel a thread writes, so the offsets live in registers (the loop was bound by its 16 shared-memory
+  // loads per 16 bytes stored: 8 offsets + 8 values)
+  const int c = threadIdx.x & 31;
+  int off[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) off[q] = tapoff[8 * c + q];
+  const int npix = rows * a.W1;
+  for (int p = threadIdx.x >> 5; p < npix; p += 8) {
     const int r = p / a.W1, ox = p - r * a.W1;
     const float* pb = patch + (2 * r) * PW + 2 * ox;
     uint32_t pk[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int o0 = tapoff[8 * c + 2 * q], o1 = tapoff[8 * c + 2 * q + 1];
+      const int o0 = off[2 * q], o1 = off[2 * q + 1];
       const __half2 h = __floats2half2_rn(o0 >= 0 ? pb[o0] : 0.f, o1 >= 0 ? pb[o1] : 0.f);
       pk[q] = *reinterpret_cast<const uint32_t*>(&h);
     }
@@ -307,38 +313,58 @@ __global__ void __launch_bounds__(256) k_lip_im2col_front(const LipFrontArgs a, 
   }
 }
 
-// MaxPool 3x3, stride 2, pad 1 over (F, H, W, C) -> (F, Ho, Wo, C); one thread per 4 channels of an output pixel
-__device__ __forceinline__ float4 lip_load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ float4 lip_load4(const __half* p) {
-  const uint2 u = *reinterpret_cast<const uint2*>(p);
+// MaxPool 3x3, stride 2, pad 1 over (F, H, W, C) -> (F, Ho, Wo, C); one thread per 8 channels of an output pixel.
+// The window is clamped instead of tested: a clamped coordinate always names a pixel that is inside the window anyway
+// (row -1 -> row 0, row H -> row H - 1), so the maximum is unchanged, the nine loads are unconditional and all in flight.
+struct LipV8 { float v[8]; };
+__device__ __forceinline__ LipV8 lip_load8(const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  return LipV8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+__device__ __forceinline__ LipV8 lip_load8(const __half* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
   const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-  return make_float4(a.x, a.y, b.x, b.y);
+  const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
+  return LipV8{{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y}};
 }
 template <typename TIN>
 __global__ void k_lip_maxpool(const TIN* __restrict__ in, int F, int H, int W, int C, int Ho, int Wo,
                               float* __restrict__ out, __half* __restrict__ out16) {
-  const int c4 = C / 4;
-  const long long n = (long long)F * Ho * Wo * c4;
+  const int c8 = C / 8;
+  const long long n = (long long)F * Ho * Wo * c8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c4);
-    const int ox = (int)((i / c4) % Wo), oy = (int)((i / ((long long)c4 * Wo)) % Ho);
-    const long long f = i / ((long long)c4 * Wo * Ho);
-    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    const int c = (int)(i % c8);
+    const int ox = (int)((i / c8) % Wo), oy = (int)((i / ((long long)c8 * Wo)) % Ho);
+    const long long f = i / ((long long)c8 * Wo * Ho);
+    LipV8 w[9];
+#pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      const int iy = 2 * oy - 1 + ky;
-      if (iy < 0 || iy >= H) continue;
+      int iy = 2 * oy - 1 + ky;
+      iy = iy < 0 ? 0 : (iy >= H ? H - 1 : iy);
+#pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int ix = 2 * ox - 1 + kx;
-        if (ix < 0 || ix >= W) continue;
-        const float4 v = lip_load4(in + (((f * H + iy) * W + ix) * (long long)C) + 4 * c);
-        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        int ix = 2 * ox - 1 + kx;
+        ix = ix < 0 ? 0 : (ix >= W ? W - 1 : ix);
+        w[ky * 3 + kx] = lip_load8(in + (((f * H + iy) * W + ix) * (long long)C) + 8 * c);
       }
     }
-    const long long o = ((f * Ho + oy) * Wo + ox) * (long long)C + 4 * c;
-    if (out) *reinterpret_cast<float4*>(out + o) = m;
+    float m[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      m[q] = w[0].v[q];
+#pragma unroll
+      for (int t = 1; t < 9; ++t) m[q] = fmaxf(m[q], w[t].v[q]);
+    }
+    const long long o = ((f * Ho + oy) * Wo + ox) * (long long)C + 8 * c;
+    if (out) {
+      *reinterpret_cast<float4*>(out + o) = make_float4(m[0], m[1], m[2], m[3]);
+      *reinterpret_cast<float4*>(out + o + 4) = make_float4(m[4], m[5], m[6], m[7]);
+    }
     if (out16) {
-      *reinterpret_cast<__half2*>(out16 + o) = __floats2half2_rn(m.x, m.y);
-      *reinterpret_cast<__half2*>(out16 + o + 2) = __floats2half2_rn(m.z, m.w);
+      const __half2 h0 = __floats2half2_rn(m[0], m[1]), h1 = __floats2half2_rn(m[2], m[3]);
+      const __half2 h2 = __floats2half2_rn(m[4], m[5]), h3 = __floats2half2_rn(m[6], m[7]);
+      *reinterpret_cast<uint4*>(out16 + o) = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                                         *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
     }
   }
 }
@@ -517,7 +543,7 @@ int lip_forward(const void* packed, size_t packed_bytes, int relu_type, const fl
     a.shift = (const float*)(pk + t[0].off_shift); a.slope = (const float*)(pk + t[0].off_slope);
     a.act = relu_type; a.out = buf0; a.out16 = nullptr; a.f0 = (int)f0; a.nf = nf;
     const int items = nf * ((g.H1 + LF_ROWS - 1) / LF_ROWS);
-    const long long npool = (long long)nf * g.H[0] * g.W[0] * 16;
+    const long long npool = (long long)nf * g.H[0] * g.W[0] * 8;
     const int pool_grid = (int)(ceil_div(npool, 256) > 4736 ? 4736 : ceil_div(npool, 256));
     if (tc) {
       // im2col (fp16) -> GEMM with the 64 x 256 weight matrix on the tensor cores (+ BN + act) -> max pool

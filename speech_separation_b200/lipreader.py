@@ -7,6 +7,7 @@ Host-side mirror of the reference's video feature extractor - the network that t
     init_lipreader             <- src/utils/init_utils.py:168-207
     get_preprocessing_pipelines <- src/lipreader/lipreading/dataloaders.py:8-29  ("val" / "test" video pipeline)
     extract_embeddings         <- make_embeddings.py:52-68 (one mouth-crop clip -> (512, T) embedding)
+    make_embeddings            <- make_embeddings.py:11-73 (directory of mouth-crop .npz -> directory of embedding .npz)
 
 Scope: the feature path the reference actually runs (`extract_feats=True`: frontend3D -> ResNet-18 trunk -> (B, T, 512),
 model.py:253-273).  The word-classification head (`self.tcn`, model.py:209-244) is never executed by the separation
@@ -259,3 +260,34 @@ def extract_embeddings(lipreader, mouth_frames):
     crop = center_crop_window(x.shape[2], x.shape[3])
     feats = lipreader._run(x, crop=crop, pre_scale=1.0 / (255.0 * PRE_STD), pre_shift=-PRE_MEAN / PRE_STD)
     return feats.transpose(1, 2)
+
+
+def make_embeddings(lipreader, mouths_dir, embeds_dir, device="cuda", max_clips_per_call=64):
+    """Mirror of make_embeddings.py:28-73 on top of `extract_embeddings`: every file of `mouths_dir` is an `.npz` whose
+    `data` array holds a (T, H, W) mouth-crop clip with values in [0, 255]; the embedding (512, T) is written to
+    `embeds_dir/<same file name>` with `np.savez_compressed(path, embedding=...)` - the files `SSDataset` reads back
+    (src/datasets/base_dataset.py:143-149).  Clips of equal shape are batched (the reference runs them one by one; the
+    results do not depend on the batch composition, bit for bit).  Returns the number of files written."""
+    import os
+
+    import numpy as np
+
+    if not os.path.isdir(mouths_dir):
+        raise NotADirectoryError(f"Input directory not found: {mouths_dir}")
+    os.makedirs(embeds_dir, exist_ok=True)
+    names = sorted(n for n in os.listdir(mouths_dir) if os.path.isfile(os.path.join(mouths_dir, n)))
+    groups = {}
+    for n in names:   # group by clip shape without keeping the pixels in memory
+        with np.load(os.path.join(mouths_dir, n)) as z:
+            groups.setdefault(tuple(z["data"].shape), []).append(n)
+    written = 0
+    for shape, members in groups.items():
+        for i in range(0, len(members), max_clips_per_call):
+            part = members[i:i + max_clips_per_call]
+            clips = np.stack([np.load(os.path.join(mouths_dir, n))["data"] for n in part]).astype(np.float32)
+            emb = extract_embeddings(lipreader, torch.from_numpy(clips).to(device))      # (len(part), 512, T)
+            emb = emb.detach().cpu().numpy()
+            for n, e in zip(part, emb):
+                np.savez_compressed(os.path.join(embeds_dir, n), embedding=e)
+                written += 1
+    return written

@@ -239,3 +239,33 @@ def test_init_lipreader_reads_the_reference_config_and_checkpoint_format(tmp_pat
     assert "All parameters: 11182784" in str(m)      # model.py:196-207-style summary line
     m2 = init_lipreader(str(cfg))                     # no checkpoint: the reference's random initialisation
     assert float(m2.trunk.layer1[0].bn1.weight.min()) == 1.0
+
+
+def test_make_embeddings_file_formats_and_batching(tmp_path, monkeypatch):
+    """make_embeddings.py:52-73: `.npz` with `data` (T, H, W) in, `.npz` with `embedding` (512, T) out, same file names;
+    clips of equal shape share a call.  Host logic only: the device call is replaced by a deterministic stand-in."""
+    import speech_separation_b200.lipreader as L
+
+    src, dst = tmp_path / "mouths", tmp_path / "embeddings"
+    src.mkdir()
+    rng = np.random.default_rng(0)
+    shapes = {"a.npz": (5, 96, 96), "b.npz": (5, 96, 96), "c.npz": (7, 96, 96), "d.npz": (5, 96, 96)}
+    for n, sh in shapes.items():
+        np.savez_compressed(src / n, data=rng.integers(0, 256, sh).astype(np.uint8))
+    calls = []
+
+    def fake_extract(lipreader, frames):
+        calls.append(tuple(frames.shape))
+        assert frames.dtype == torch.float32
+        return frames.mean(dim=(2, 3))[:, None, :].repeat(1, 512, 1)     # (B, 512, T)
+
+    monkeypatch.setattr(L, "extract_embeddings", fake_extract)
+    n = L.make_embeddings(object(), str(src), str(dst), device="cpu", max_clips_per_call=2)
+    assert n == 4 and sorted(os.listdir(dst)) == sorted(shapes)
+    assert sorted(calls) == [(1, 5, 96, 96), (1, 7, 96, 96), (2, 5, 96, 96)]
+    for name, sh in shapes.items():
+        e = np.load(dst / name)["embedding"]
+        assert e.shape == (512, sh[0]) and e.dtype == np.float32
+        np.testing.assert_allclose(e[0], np.load(src / name)["data"].astype(np.float32).mean(axis=(1, 2)), rtol=1e-6)
+    with pytest.raises(NotADirectoryError):
+        L.make_embeddings(object(), str(tmp_path / "missing"), str(dst))

@@ -269,3 +269,22 @@ def test_make_embeddings_file_formats_and_batching(tmp_path, monkeypatch):
         np.testing.assert_allclose(e[0], np.load(src / name)["data"].astype(np.float32).mean(axis=(1, 2)), rtol=1e-6)
     with pytest.raises(NotADirectoryError):
         L.make_embeddings(object(), str(tmp_path / "missing"), str(dst))
+
+
+@pytest.mark.gpu
+def test_make_embeddings_end_to_end_on_the_device(golden_dir, tmp_path):
+    """Mouth-crop `.npz` files -> `make_embeddings` -> embedding `.npz` files equal to the reference's features for the same
+    clips (the golden clips, written one per file as make_embeddings.py expects them)."""
+    from speech_separation_b200 import make_embeddings
+
+    frames, feats, seed = load_case(golden_dir, "swish", 2, 7)
+    src, dst = tmp_path / "mouths", tmp_path / "embeddings"
+    src.mkdir()
+    for b in range(2):
+        np.savez_compressed(src / f"clip{b}.npz", data=frames[b].astype(np.uint8))
+    net = _net("swish", seed, "tensor")
+    assert make_embeddings(net, str(src), str(dst), device="cuda:0") == 2
+    for b in range(2):
+        e = np.load(dst / f"clip{b}.npz")["embedding"]
+        assert e.shape == (512, 7)
+        assert rel_l2(e.T, feats[b]) < TENSOR_TOL

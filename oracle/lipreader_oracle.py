@@ -12,8 +12,9 @@ What it follows (reference, read-only):
     Normalize / CenterCrop of src/lipreader/lipreading/preprocess.py:62-103
 
 Parity pin: `tests/golden/lipreader_*.npz` are outputs of the reference's own `Lipreading` class (imported unmodified
-by oracle/gen_lipreader_golden.py) on the weights `make_state_dict` generates; tests/test_oracle_golden.py checks this
-restatement against them.  The reference ships no pretrained lipreader weights and has no tests for this path, so the
+by oracle/gen_lipreader_golden.py) on the weights `make_state_dict` generates; tests/test_lipreader.py checks both
+restatements against them: `forward` (torch CPU ops in the reference's order, fp32 / fp64) and `forward_numpy` (numpy
+only, fp64: sliding windows + einsum - none of torch's convolution, pooling or BatchNorm code).  The reference ships no pretrained lipreader weights and has no tests for this path, so the
 weights are synthetic: numpy PCG64 streams per tensor, BatchNorm running statistics and affine terms randomised so that
 the folding of BatchNorm into the convolutions is actually exercised.
 """
@@ -139,3 +140,57 @@ def forward(sd, x, relu_type, dtype=torch.float32):
             y = _act(o + r, relu_type, sd.get(p + ".relu2.weight"))
     y = y.mean(dim=(2, 3))
     return y.view(B, Tn, y.shape[1])
+
+
+# --------------------------------------------------------------------------------------
+# numpy-only restatement (fp64): independent of torch's convolution / pooling / BatchNorm kernels
+# --------------------------------------------------------------------------------------
+def _np_conv(x, w, stride, pad):
+    """x (N, C, *spatial), w (O, C, *kernel): cross-correlation with zero padding, as nn.Conv2d / nn.Conv3d compute it."""
+    nd = w.ndim - 2
+    x = np.pad(x, [(0, 0), (0, 0)] + [(p, p) for p in pad])
+    win = np.lib.stride_tricks.sliding_window_view(x, w.shape[2:], axis=tuple(range(2, 2 + nd)))
+    win = win[(slice(None), slice(None)) + tuple(slice(None, None, s) for s in stride)]   # (N, C, *out, *kernel)
+    k = "xyz"[:nd]
+    o = "pqr"[:nd]
+    return np.einsum(f"ni{o}{k},mi{k}->nm{o}", win, w, optimize=True)
+
+
+def _np_bn(x, sd, prefix):
+    shape = (1, -1) + (1,) * (x.ndim - 2)
+    g, b = sd[prefix + ".weight"].reshape(shape), sd[prefix + ".bias"].reshape(shape)
+    m, v = sd[prefix + ".running_mean"].reshape(shape), sd[prefix + ".running_var"].reshape(shape)
+    return (x - m) / np.sqrt(v + EPS) * g + b
+
+
+def _np_act(x, relu_type, slope):
+    if relu_type == "relu":
+        return np.maximum(x, 0.0)
+    if relu_type == "prelu":
+        return np.where(x >= 0, x, x * slope.reshape((1, -1) + (1,) * (x.ndim - 2)))
+    return x / (1.0 + np.exp(-x))
+
+
+def forward_numpy(sd, x, relu_type):
+    """Same contract as `forward`, numpy fp64 only: x (B, 1, T, H, W) -> (B, T, 512)."""
+    sd = {k: np.asarray(v, dtype=np.float64) for k, v in sd.items()}
+    x = np.asarray(x, dtype=np.float64)
+    B = x.shape[0]
+    y = _np_conv(x, sd["frontend3D.0.weight"], (1, 2, 2), (2, 3, 3))
+    y = _np_act(_np_bn(y, sd, "frontend3D.1"), relu_type, sd.get("frontend3D.2.weight"))
+    y = np.pad(y, [(0, 0), (0, 0), (0, 0), (1, 1), (1, 1)], constant_values=-np.inf)      # MaxPool3d(1x3x3, s 1x2x2, p 0x1x1)
+    y = np.lib.stride_tricks.sliding_window_view(y, (3, 3), axis=(3, 4))[:, :, :, ::2, ::2].max(axis=(-1, -2))
+    Tn = y.shape[2]
+    y = y.transpose(0, 2, 1, 3, 4).reshape(B * Tn, y.shape[1], y.shape[3], y.shape[4])
+    for li in range(1, 5):
+        for b in range(2):
+            p = f"trunk.layer{li}.{b}"
+            stride = 2 if (li > 1 and b == 0) else 1
+            o = _np_conv(y, sd[p + ".conv1.weight"], (stride, stride), (1, 1))
+            o = _np_act(_np_bn(o, sd, p + ".bn1"), relu_type, sd.get(p + ".relu1.weight"))
+            o = _np_bn(_np_conv(o, sd[p + ".conv2.weight"], (1, 1), (1, 1)), sd, p + ".bn2")
+            r = y
+            if (p + ".downsample.0.weight") in sd:
+                r = _np_bn(_np_conv(y, sd[p + ".downsample.0.weight"], (stride, stride), (0, 0)), sd, p + ".downsample.1")
+            y = _np_act(o + r, relu_type, sd.get(p + ".relu2.weight"))
+    return y.mean(axis=(2, 3)).reshape(B, Tn, -1)

@@ -45,6 +45,17 @@ def test_oracle_matches_reference_lipreading(golden_dir, relu_type, B, T):
     assert rel_l2(y64, feats) < 2e-6      # the reference ran in fp32
 
 
+@pytest.mark.parametrize("relu_type,B,T", [("prelu", 1, 5), ("relu", 1, 5)])
+def test_numpy_restatement_matches_reference_lipreading(golden_dir, relu_type, B, T):
+    """The numpy-only fp64 restatement (sliding windows + einsum; none of torch's convolution, pooling or BatchNorm code)
+    against the reference class's output."""
+    frames, feats, seed = load_case(golden_dir, relu_type, B, T)
+    sd = {k: v.numpy() for k, v in LO.make_state_dict(relu_type, seed).items()}
+    y = LO.forward_numpy(sd, LO.preprocess(frames)[:, None], relu_type)
+    assert y.shape == feats.shape
+    assert rel_l2(y, feats) < 2e-6
+
+
 def test_frames_generator_is_deterministic(golden_dir):
     frames, _, _ = load_case(golden_dir, "swish", 2, 7)
     assert np.array_equal(LO.make_frames(2, 7), frames)

@@ -299,3 +299,27 @@ def test_make_embeddings_end_to_end_on_the_device(golden_dir, tmp_path):
         e = np.load(dst / f"clip{b}.npz")["embedding"]
         assert e.shape == (512, 7)
         assert rel_l2(e.T, feats[b]) < TENSOR_TOL
+
+
+def test_preprocessing_matches_reference_classes_when_available():
+    """`center_crop_window` / `LO.preprocess` against the reference's own CenterCrop / Normalize classes for several frame
+    sizes (only where /root/reference exists: the build container; the committed goldens cover the 96 x 96 case anywhere)."""
+    from oracle import ref_import
+
+    if not ref_import.available():
+        pytest.skip("reference checkout not present")
+    from oracle.gen_lipreader_golden import load_reference
+    from speech_separation_b200.lipreader import center_crop_window
+
+    _, pre = load_reference()
+    pipeline = pre.Compose([pre.Normalize(0.0, 255.0), pre.CenterCrop((88, 88)), pre.Normalize(0.421, 0.165)])
+    rng = np.random.default_rng(1)
+    for h, w in ((96, 96), (88, 88), (97, 101), (120, 90), (89, 96)):
+        frames = rng.integers(0, 256, (3, h, w)).astype(np.float32)
+        want = pipeline(frames)
+        y0, x0, th, tw = center_crop_window(h, w)
+        assert want.shape == (3, th, tw)
+        got = (frames[:, y0:y0 + th, x0:x0 + tw] / 255.0 - 0.421) / 0.165
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+        if (h, w) == (96, 96):
+            np.testing.assert_array_equal(LO.preprocess(frames), want)

@@ -183,3 +183,30 @@ def test_world_size_2_reduction_matches_single_process():
     assert abs(out["loss_batch_pit"] - loss) < 1e-9
     assert abs(out["si_snri_utt_pit"] - utt) < 1e-9
     assert out["si_snri_utt_pit"] > out["si_snri_batch_pit"]  # per-utterance PIT can only help
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """The boundary is a C ABI: include/vatss.h must compile as C99 (no C++-isms, no torch types) and a C program must link
+    against libvatss_b200.so and call the entry points that need no GPU."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    hdr = os.path.join(ROOT, "include", "vatss.h")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "vatss.h"\n'
+        "int main(void) {\n"
+        "  vatss_model_desc d = {VATSS_KIND_DPTN_AV, 128, 7, 128, 6, 150, 75, 4, 1, 512, VATSS_ENGINE_AUTO, 0};\n"
+        "  int L = vatss_frames(&d, 64000), S = vatss_chunks(&d, L);\n"
+        '  printf("%d %d %d %d %zu\\n", vatss_abi_version(), L, S, vatss_sisnr_chunks(64000), vatss_lipreader_packed_bytes());\n'
+        "  return (L == 21332 && S == 283 && vatss_abi_version() == VATSS_ABI_VERSION) ? 0 : 1;\n}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "speech_separation_b200")
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    os.path.join(libdir, "libvatss_b200.so"), f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out[:4] == ["1", "21332", "283", "8"] and int(out[4]) > 0
